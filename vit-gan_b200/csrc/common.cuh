@@ -1,0 +1,115 @@
+// common.cuh -- shared device/host helpers for libvitgan_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vitgan_b200.h"
+
+namespace vg {
+
+// ---------------------------------------------------------------- error state (thread local: backward runs on autograd threads)
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // cudaPeekAtLastError -> vg_status
+
+#define VG_REQUIRE(cond, code, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      vg::set_error(__VA_ARGS__);              \
+      return (code);                           \
+    }                                          \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+int num_sms();
+
+// ---------------------------------------------------------------- dtype helpers
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-element vector load/store with conversion to/from float (16 B for fp32, 8 B for bf16)
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------- activations (fp32 math)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// epilogue activation shared by the SIMT and tcgen05 GEMMs; `a` is the aux value (ignored when unused)
+__device__ __forceinline__ float apply_act(int act, float v, float a, float prm) {
+  switch (act) {
+    case VG_ACT_GELU: return gelu_erf(v);
+    case VG_ACT_TANH: return tanhf(v);
+    case VG_ACT_SIN: return sinf(prm * v);
+    case VG_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    case VG_ACT_MUL_DGELU: return v * dgelu_erf(a);
+    case VG_ACT_MUL_DTANH: return v * (1.0f - a * a);
+    case VG_ACT_MUL_DSIN: return v * prm * cosf(prm * a);
+    case VG_ACT_MUL_DSIGMOID: return v * a * (1.0f - a);
+    default: return v;
+  }
+}
+__host__ __device__ __forceinline__ bool act_needs_aux(int act) { return act >= VG_ACT_MUL_DGELU; }
+
+// row remaps of the GEMM epilogue (see vg_gemm_args)
+__device__ __forceinline__ int64_t out_row(int m, int c_row_group) {
+  return c_row_group > 0 ? (int64_t)m + m / c_row_group + 1 : (int64_t)m;
+}
+__device__ __forceinline__ int64_t res_row(int m, int mod, int off) {
+  return mod > 0 ? (int64_t)(m % mod) + off : (int64_t)m;
+}
+
+// launchers implemented per translation unit
+int gemm_simt_launch(const vg_gemm_args& a, cudaStream_t st);
+int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st);
+bool gemm_tc_supported(const vg_gemm_args& a, const char** why);
+
+}  // namespace vg

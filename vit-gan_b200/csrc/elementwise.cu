@@ -1,0 +1,210 @@
+// elementwise.cu -- HBM-bound helpers: dtype cast (+ spectral rescale), column sums (bias gradients),
+// in-place add, row broadcast, fused Adam/AdamW.  All grid-stride, vectorised where alignment allows.
+#include "common.cuh"
+
+namespace vg {
+namespace {
+
+int grid1d(int64_t total, int block, int per_sm = 16) {
+  const int64_t need = (total + block - 1) / block;
+  return (int)max((int64_t)1, min(need, (int64_t)num_sms() * per_sm));
+}
+
+template <typename TS, typename TD>
+__global__ void cast_scale_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n,
+                                  const float* __restrict__ num, const float* __restrict__ den) {
+  float sc = 1.f;
+  if (num) sc = *num;
+  if (den) sc = sc / *den;
+  const bool scaled = num || den;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const int64_t n4 = aligned ? n / 4 : 0;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gtid; i < n4; i += gsz) {
+    float v[4];
+    Vec4<TS>::load(src + i * 4, v);
+    if (scaled) { v[0] *= sc; v[1] *= sc; v[2] *= sc; v[3] *= sc; }
+    Vec4<TD>::store(dst + i * 4, v);
+  }
+  for (int64_t i = n4 * 4 + gtid; i < n; i += gsz) {
+    float v = to_f<TS>(src[i]);
+    if (scaled) v *= sc;
+    dst[i] = from_f<TD>(v);
+  }
+}
+
+// out[n] += sum_m x[m,n]: CTA = (32-col slab) x (row slice); threads (32 cols x 8 row lanes)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* __restrict__ out,
+                              int64_t rows_per_cta) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t m1 = min(M, m0 + rows_per_cta);
+  float acc = 0.f;
+  if (n < N)
+    for (int64_t m = m0 + ty; m < m1; m += 8) acc += to_f<T>(x[m * ld + n]);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    atomicAdd(&out[n], s);
+  }
+}
+
+template <typename T>
+__global__ void add_inplace_kernel(T* __restrict__ x, const T* __restrict__ y, int64_t n) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  for (int64_t i = gtid; i < n4; i += gsz) {
+    float a[4], b[4];
+    Vec4<T>::load(x + i * 4, a);
+    Vec4<T>::load(y + i * 4, b);
+    a[0] += b[0]; a[1] += b[1]; a[2] += b[2]; a[3] += b[3];
+    Vec4<T>::store(x + i * 4, a);
+  }
+  for (int64_t i = n4 * 4 + gtid; i < n; i += gsz) x[i] = from_f<T>(to_f<T>(x[i]) + to_f<T>(y[i]));
+}
+
+template <typename T>
+__global__ void broadcast_rows_kernel(const T* __restrict__ src, int64_t src_elems, T* __restrict__ dst, int64_t reps) {
+  const int64_t total = src_elems * reps;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gtid; i < total; i += gsz) dst[i] = src[i % src_elems];
+}
+
+template <typename T>
+__global__ void copy_rows_kernel(int64_t rows, int cols, const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd) {
+  const int64_t total = rows * cols;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gtid; i < total; i += gsz) {
+    const int64_t r = i / cols; const int c = (int)(i % cols);
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+template <typename T>
+__global__ void act_bwd_kernel(int64_t n, const T* __restrict__ dy, const T* __restrict__ aux, int act, float prm, T* __restrict__ out) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gtid; i < n; i += gsz) out[i] = from_f<T>(apply_act(act, to_f<T>(dy[i]), to_f<T>(aux[i]), prm));
+}
+
+// torch.optim.Adam / AdamW single-tensor semantics (no amsgrad, no maximize):
+//   AdamW: p *= 1 - lr*wd;                  Adam: g += wd*p
+//   m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                            int decoupled, float grad_scale, const int* __restrict__ step_count) {
+  const int t = *step_count + 1;     // the counter is bumped by a separate 1-thread kernel after all tensors
+  const float bc1 = 1.f - powf(b1, (float)t);
+  const float bc2s = sqrtf(1.f - powf(b2, (float)t));
+  const float step_size = lr / bc1;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gtid; i < n; i += gsz) {
+    float pi = p[i], gi = g[i] * grad_scale;
+    if (decoupled) pi *= 1.f - lr * wd; else gi += wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;          // lerp form: m + (g-m)*(1-b1) in torch; same to 1 ulp
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+__global__ void bump_kernel(int* c) { *c += 1; }
+
+}  // namespace
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, const float* num,
+                             const float* den, void* stream) {
+  if (n == 0) return VG_OK;
+  cudaStream_t st = as_stream(stream);
+  const int grid = grid1d((n + 3) / 4, 256);
+  if (src_dtype == VG_F32 && dst_dtype == VG_BF16)
+    cast_scale_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, n, num, den);
+  else if (src_dtype == VG_F32 && dst_dtype == VG_F32)
+    cast_scale_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n, num, den);
+  else if (src_dtype == VG_BF16 && dst_dtype == VG_F32)
+    cast_scale_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, n, num, den);
+  else if (src_dtype == VG_BF16 && dst_dtype == VG_BF16)
+    cast_scale_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n, num, den);
+  else
+    VG_REQUIRE(false, VG_ERR_ARG, "cast_scale: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  return check_launch("cast_scale");
+}
+
+extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, void* stream) {
+  if (M == 0 || N == 0) return VG_OK;
+  const int xs = (N + 31) / 32;
+  int ys = (int)max((int64_t)1, min((M + 63) / 64, (int64_t)(4 * num_sms() + xs - 1) / xs));
+  const int64_t rows_per_cta = (M + ys - 1) / ys;
+  ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
+  dim3 grid(xs, ys);
+  if (dtype == VG_F32)
+    colsum_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, M, N, ldx, out, rows_per_cta);
+  else
+    colsum_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, M, N, ldx, out, rows_per_cta);
+  return check_launch("colsum");
+}
+
+extern "C" int vg_add_inplace(int dtype, void* x, const void* y, int64_t n, void* stream) {
+  if (n == 0) return VG_OK;
+  const int grid = grid1d((n + 3) / 4, 256);
+  if (dtype == VG_F32) add_inplace_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)x, (const float*)y, n);
+  else add_inplace_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((bf16*)x, (const bf16*)y, n);
+  return check_launch("add_inplace");
+}
+
+extern "C" int vg_broadcast_rows(int dtype, const void* src, int64_t src_rows, int64_t cols, void* dst, int64_t reps,
+                                 void* stream) {
+  const int64_t n = src_rows * cols;
+  if (n == 0 || reps == 0) return VG_OK;
+  const int grid = grid1d(n * reps, 256);
+  if (dtype == VG_F32) broadcast_rows_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)src, n, (float*)dst, reps);
+  else broadcast_rows_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)src, n, (bf16*)dst, reps);
+  return check_launch("broadcast_rows");
+}
+
+extern "C" int vg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int decoupled, float grad_scale,
+                            int* step_count, void* stream) {
+  VG_REQUIRE(step_count != nullptr, VG_ERR_ARG, "adam_step: step_count is NULL");
+  cudaStream_t st = as_stream(stream);
+  if (n > 0)
+    adam_kernel<<<grid1d(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                decoupled, grad_scale, step_count);
+  bump_kernel<<<1, 1, 0, st>>>(step_count);
+  return check_launch("adam_step");
+}
+
+extern "C" int vg_copy_rows(int dtype, int64_t rows, int cols, const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                            void* stream) {
+  if (rows == 0 || cols == 0) return VG_OK;
+  const int grid = grid1d(rows * cols, 256);
+  if (dtype == VG_F32) copy_rows_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(rows, cols, (const float*)src, ld_src, (float*)dst, ld_dst);
+  else copy_rows_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(rows, cols, (const bf16*)src, ld_src, (bf16*)dst, ld_dst);
+  return check_launch("copy_rows");
+}
+
+extern "C" int vg_act_backward(int dtype, int64_t n, const void* dy, const void* aux, int act, float act_param, void* out,
+                               void* stream) {
+  int bact;
+  switch (act) {
+    case VG_ACT_GELU: bact = VG_ACT_MUL_DGELU; break;
+    case VG_ACT_TANH: bact = VG_ACT_MUL_DTANH; break;
+    case VG_ACT_SIN: bact = VG_ACT_MUL_DSIN; break;
+    case VG_ACT_SIGMOID: bact = VG_ACT_MUL_DSIGMOID; break;
+    default: VG_REQUIRE(false, VG_ERR_ARG, "act_backward: activation %d has no derivative kernel", act);
+  }
+  if (n == 0) return VG_OK;
+  const int grid = grid1d(n, 256);
+  if (dtype == VG_F32) act_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(n, (const float*)dy, (const float*)aux, bact, act_param, (float*)out);
+  else act_bwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(n, (const bf16*)dy, (const bf16*)aux, bact, act_param, (bf16*)out);
+  return check_launch("act_backward");
+}

@@ -1,0 +1,411 @@
+// gemm_tc.cu -- bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands streamed by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring, persistent
+// warp-specialised CTAs.  Hand-written PTX; no CUTLASS/cuBLAS.
+//
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2..9  : epilogue: tcgen05.ld accumulator -> bias / activation / residual -> global stores
+//
+// Tile 128 x 128 x 64 (UMMA 128x128x16, 4 per k-block), NSTAGES-deep smem ring, 2 TMEM accumulator
+// stages (256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// All three products of a Linear layer run here without transposed copies in HBM:
+//   forward  C = A W^T   : A K-major , B K-major         (trans_a=0, trans_b=1)
+//   dgrad    dX = dY W   : A K-major , B MN-major        (trans_a=0, trans_b=0)
+//   wgrad    dW = dY^T X : A MN-major, B MN-major, split-K + fp32 atomic accumulate (trans_a=1, trans_b=0)
+// Replaces ATen addmm/mm under F.linear (src/v2/modules.py:128-139,161,173-175; src/v1/attention.py:46-48,102;
+// muilti_layer_perceptron.py:39; siren.py:45) and their autograd backward.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
+constexpr int NSTAGES = 6;
+constexpr int NACC = 2;
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = NACC * BN;   // 256: power of two >= 32
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("vg gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, sm_100 version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address   bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // leading byte off bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // stride byte off  bits [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
+  return d;
+}
+
+struct Params {
+  int M, N, K;
+  int trans_a, trans_b;            // see file header
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  int c_is_f32;
+  void* C; int64_t ldc;
+  const float* bias;
+  int act; float act_param;
+  const void* aux; int64_t ldaux;
+  const void* residual; int64_t ldres;
+  void* c_pre; int64_t ldpre;
+  int c_row_group, res_row_mod, res_row_off;
+  int accumulate;
+  uint32_t mn_lbo, mn_sbo, mn_kstep;   // MN-major smem descriptor geometry (debug-overridable, see gemm_tc_launch)
+};
+
+template <typename TC>
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&r)[32], int m, int n0) {
+  // one thread = one output row m, 32 consecutive columns n0..n0+31
+  const int64_t orow = out_row(m, p.c_row_group);
+  const int64_t rrow = res_row(m, p.res_row_mod, p.res_row_off);
+  TC* C = static_cast<TC*>(p.C) + orow * p.ldc + n0;
+  const TC* aux = p.aux ? static_cast<const TC*>(p.aux) + (int64_t)m * p.ldaux + n0 : nullptr;
+  const TC* res = p.residual ? static_cast<const TC*>(p.residual) + rrow * p.ldres + n0 : nullptr;
+  TC* cpre = p.c_pre ? static_cast<TC*>(p.c_pre) + (int64_t)m * p.ldpre + n0 : nullptr;
+  const int nvalid = min(32, p.N - n0);
+  constexpr int ALIGN_ELEMS = 16 / sizeof(TC) * 1;   // elements per 16 B
+  const bool vec_ok = nvalid == 32 && (p.ldc % ALIGN_ELEMS == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                      (!aux || (p.ldaux % ALIGN_ELEMS == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)) &&
+                      (!res || (p.ldres % ALIGN_ELEMS == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
+                      (!cpre || (p.ldpre % ALIGN_ELEMS == 0 && (reinterpret_cast<uintptr_t>(p.c_pre) & 15) == 0));
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {       // 8 groups of 4 columns
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[g * 4 + j]);
+    const int c = g * 4;
+    if (p.accumulate) {               // split-K partial: fp32 atomics; bias/residual contributed by split 0 only (folded by caller)
+      float* Cf = reinterpret_cast<float*>(C);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < nvalid) atomicAdd(Cf + c + j, v[j]);
+      continue;
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < nvalid) v[j] += __ldg(p.bias + n0 + c + j);
+    }
+    if (vec_ok) {
+      if (cpre) Vec4<TC>::store(cpre + c, v);
+      if (p.act != VG_ACT_NONE) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (aux) Vec4<TC>::load(aux + c, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(p.act, v[j], a[j], p.act_param);
+      }
+      if (res) {
+        float t[4];
+        Vec4<TC>::load(res + c, t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += t[j];
+      }
+      Vec4<TC>::store(C + c, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c + j < nvalid) {
+          float x = v[j];
+          if (cpre) cpre[c + j] = from_f<TC>(x);
+          const float a = aux ? to_f<TC>(aux[c + j]) : 0.f;
+          x = apply_act(p.act, x, a, p.act_param);
+          if (res) x += to_f<TC>(res[c + j]);
+          C[c + j] = from_f<TC>(x);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  extern __shared__ uint8_t smem_dyn[];
+  // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + NSTAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + NACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGES + 2 * NACC);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // whole warp: allocate TMEM columns, publish base address through smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+  // smem tile geometry per operand
+  //   K-major : [rows][64 k] 128 B per row                      -> SBO = 1024 (8 rows), k-step = 32 B
+  //   MN-major: [mn/64 blocks][64 k rows][64 mn] 128 B per row  -> LBO = 64*128 = 8192 (next 64-mn block),
+  //             SBO = 1024 (next 8 k rows), k-step (16 rows) = 2048 B
+  const uint32_t a_lbo = p.trans_a ? p.mn_lbo : 16u, a_sbo = p.trans_a ? p.mn_sbo : 1024u, a_kstep = p.trans_a ? p.mn_kstep : 32u;
+  const uint32_t b_lbo = p.trans_b ? 16u : p.mn_lbo, b_sbo = p.trans_b ? 1024u : p.mn_sbo, b_kstep = p.trans_b ? 32u : p.mn_kstep;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles, split = w / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (!p.trans_a) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);                 // box {64 k, 128 m}
+          } else {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), m_blk * BM, kb * BK);                 // box {64 m, 64 k} x2
+            tma_load_2d(sa + 8192, &tmap_a, full_bar(stage), m_blk * BM + 64, kb * BK);
+          }
+          if (p.trans_b) {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);                 // box {64 k, 128 n}
+          } else {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), n_blk * BN, kb * BK);                 // box {64 n, 64 k} x2
+            tma_load_2d(sb + 8192, &tmap_b, full_bar(stage), n_blk * BN + 64, kb * BK);
+          }
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.trans_a ? 1u : 0u) << 15) |
+                             ((p.trans_b ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / (p.n_tiles * p.m_tiles);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);                 // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t ad = make_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t bd = make_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            tc_mma(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));                       // frees the smem slot when these MMAs retire
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int ew = warp - 2;               // 0..7
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = ew >> 2;              // which 64-column half of the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + quad * 32 + lane;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 2; cc += 32) {
+        const int col = half * (BN / 2) + cc;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col), r);
+        const int n0 = n_blk * BN + col;
+        if (m < p.M && n0 < p.N) {
+          if (p.c_is_f32) epilogue_chunk<float>(p, r, m, n0);
+          else epilogue_chunk<bf16>(p, r, m, n0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows, cols] (leading dim ld elements) -> tensor map with box {box_cols, box_rows}, 128B swizzle
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VG_REQUIRE(enc != nullptr, VG_ERR_LAUNCH, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_REQUIRE(r == CUDA_SUCCESS, VG_ERR_LAUNCH, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)cols, (long long)ld);
+  return VG_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
+  static int sm100 = -1;
+  if (sm100 < 0) sm100 = vg_device_is_sm100();
+  if (!sm100) { *why = "device is not sm_100"; return false; }
+  if (a.ab_dtype != VG_BF16) { *why = "A/B must be bf16"; return false; }
+  if (a.M < 1 || a.N < 8 || a.K < 1) { *why = "degenerate shape (N < 8)"; return false; }
+  if (a.lda % 8 || a.ldb % 8) { *why = "lda/ldb must be multiples of 8 elements (16 B TMA pitch)"; return false; }
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15)) { *why = "A/B must be 16 B aligned"; return false; }
+  if (a.accumulate && a.c_dtype != VG_F32) { *why = "accumulate needs fp32 C"; return false; }
+  if (a.accumulate && (a.act != VG_ACT_NONE || a.c_pre || a.bias || a.residual)) { *why = "accumulate supports a plain epilogue only"; return false; }
+  if (act_needs_aux(a.act) && !a.aux) { *why = "activation needs aux"; return false; }
+  return true;
+}
+
+int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap ma, mb;
+  int rc;
+  // A: trans_a=0 stored [M,K] -> box {64 k, 128 m};  trans_a=1 stored [K,M] -> box {64 m, 64 k}
+  rc = a.trans_a ? make_map(&ma, a.A, a.K, a.M, a.lda, 64, 64) : make_map(&ma, a.A, a.M, a.K, a.lda, 64, BM);
+  if (rc) return rc;
+  // B: trans_b=1 stored [N,K] -> box {64 k, 128 n};  trans_b=0 stored [K,N] -> box {64 n, 64 k}
+  rc = a.trans_b ? make_map(&mb, a.B, a.N, a.K, a.ldb, 64, BN) : make_map(&mb, a.B, a.K, a.N, a.ldb, 64, 64);
+  if (rc) return rc;
+
+  Params p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.trans_a = a.trans_a; p.trans_b = a.trans_b;
+  p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + BN - 1) / BN;
+  p.kb_total = (a.K + BK - 1) / BK;
+  p.splits = 1;
+  const int sms = num_sms();
+  if (a.accumulate) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int want = (sms + tiles - 1) / tiles;
+    p.splits = max(1, min(want, (p.kb_total + 3) / 4));     // >= 4 k-blocks (256 of K) per split
+  }
+  p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.c_is_f32 = a.c_dtype == VG_F32;
+  p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.act = a.act; p.act_param = a.act_param;
+  p.aux = a.aux; p.ldaux = a.ldaux; p.residual = a.residual; p.ldres = a.ldres; p.c_pre = a.c_pre; p.ldpre = a.ldpre;
+  p.c_row_group = a.c_row_group; p.res_row_mod = a.res_row_mod; p.res_row_off = a.res_row_off; p.accumulate = a.accumulate;
+  p.mn_lbo = 8192u; p.mn_sbo = 1024u; p.mn_kstep = 2048u;
+  if (const char* dbg = getenv("VG_TC_MN_DESC")) {   // bring-up knob: "lbo,sbo,kstep" in bytes
+    unsigned l = 0, sb = 0, ks = 0;
+    if (sscanf(dbg, "%u,%u,%u", &l, &sb, &ks) == 3) { p.mn_lbo = l; p.mn_sbo = sb; p.mn_kstep = ks; }
+  }
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = min(total, sms);
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, p);
+  return check_launch("gemm_tc");
+}
+
+}  // namespace vg

@@ -1,0 +1,370 @@
+// norm.cu -- LayerNorm and self-modulated LayerNorm (SLN), forward and backward.  HBM-bound:
+// one warp per row, 4-wide vector loads, row kept in registers, warp-shuffle reductions, fp32 math.
+// Algorithmic bytes: fwd 2*rows*E*sizeof(T); bwd 4*rows*E*sizeof(T) (dy, x, [dres], dx).
+//   LayerNorm : src/v2/modules.py:168,172,225 ; src/v1/transformer.py:18-19 (eps 1e-5, biased var, affine)
+//   SLN       : src/v1/spectral_layer_norm.py:19-20  y = gamma_s * w * LN(h) + beta_s * w
+#include "common.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int MAXV = 8;            // up to 8 float4 per lane -> E <= 1024 (kernels are templated on NV <= MAXV)
+constexpr int WARPS = 8;           // warps per CTA
+constexpr int MAXE = MAXV * 128;
+
+
+template <typename T, int NV>
+__device__ __forceinline__ void load_row(const T* p, int E, int lane, float (&v)[NV][4]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < E) Vec4<T>::load(p + c, v[i]);
+    else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+  }
+}
+template <typename T, int NV>
+__device__ __forceinline__ void store_row(T* p, int E, int lane, const float (&v)[NV][4]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < E) Vec4<T>::store(p + c, v[i]);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void load_vec(const float* p, int E, int lane, float (&v)[NV][4]) {
+  load_row<float, NV>(p, E, lane, v);
+}
+
+template <int NV>
+__device__ __forceinline__ void row_stats(const float (&x)[NV][4], int E, int lane, float& mean, float& rstd, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (x[i][0] + x[i][1]) + (x[i][2] + x[i][3]);
+  mean = warp_sum(s) / (float)E;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < E) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float d = x[i][j] - mean; q = fmaf(d, d, q); }
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+}
+
+// ------------------------------------------------------------------------------------------------ LN forward
+template <typename T, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_fwd_kernel(int64_t rows, int E, const T* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  float g[NV][4], b[NV][4];
+  load_vec(gamma, E, lane, g);
+  load_vec(beta, E, lane, b);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float v[NV][4];
+    load_row<T, NV>(x + r * E, E, lane, v);
+    float mean, rstd;
+    row_stats(v, E, lane, mean, rstd, eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = fmaf((v[i][j] - mean) * rstd, g[i][j], b[i][j]);
+    store_row<T, NV>(y + r * E, E, lane, v);
+    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  }
+}
+
+// flush per-warp column partials: smem atomics, then one global atomic per column per CTA
+template <int NV>
+__device__ __forceinline__ void flush_cols(float* sm, float* gl, const float (&acc)[NV][4], int E, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < E) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sm[c + j], acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LN backward
+template <typename T, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_dg[MAXE], s_db[MAXE];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  float g[NV][4], adg[NV][4], adb[NV][4];
+  load_vec(gamma, E, lane, g);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { adg[i][j] = 0.f; adb[i][j] = 0.f; }
+  const float invE = 1.0f / (float)E;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float xv[NV][4], dv[NV][4];
+    load_row<T, NV>(x + r * E, E, lane, xv);
+    load_row<T, NV>(dy + r * E, E, lane, dv);
+    const float mu = mean[r], rs = rstd[r];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xv[i][j] - mu) * rs;       // padded lanes: dy = 0 -> contribute nothing
+        const float gd = dv[i][j] * g[i][j];
+        adg[i][j] = fmaf(dv[i][j], xh, adg[i][j]);
+        adb[i][j] += dv[i][j];
+        c1 += gd;
+        c2 = fmaf(gd, xh, c2);
+        xv[i][j] = xh; dv[i][j] = gd;
+      }
+    c1 = warp_sum(c1) * invE;
+    c2 = warp_sum(c2) * invE;
+    if (dres != nullptr) {
+      float rv[NV][4];
+      load_row<T, NV>(dres + r * E, E, lane, rv);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dv[i][j] = rv[i][j] + rs * (dv[i][j] - c1 - xv[i][j] * c2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dv[i][j] = rs * (dv[i][j] - c1 - xv[i][j] * c2);
+    }
+    store_row<T, NV>(dx + r * E, E, lane, dv);
+  }
+  flush_cols(s_dg, dgamma, adg, E, lane);
+  flush_cols(s_db, dbeta, adb, E, lane);
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) { atomicAdd(&dgamma[i], s_dg[i]); atomicAdd(&dbeta[i], s_db[i]); }
+}
+
+// ------------------------------------------------------------------------------------------------ SLN forward
+template <typename T, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+sln_fwd_kernel(int64_t rows, int64_t h_rows, int F, const T* __restrict__ h, const T* __restrict__ w,
+               const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ gamma_s,
+               const float* __restrict__ beta_s, T* __restrict__ y, float* __restrict__ mean_out,
+               float* __restrict__ rstd_out, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  float g[NV][4], b[NV][4];
+  load_vec(ln_g, F, lane, g);
+  load_vec(ln_b, F, lane, b);
+  const float gs = *gamma_s, bs = *beta_s;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float hv[NV][4], wv[NV][4];
+    load_row<T, NV>(h + (r % h_rows) * F, F, lane, hv);
+    load_row<T, NV>(w + r * F, F, lane, wv);
+    float mean, rstd;
+    row_stats(hv, F, lane, mean, rstd, eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float n = fmaf((hv[i][j] - mean) * rstd, g[i][j], b[i][j]);
+        hv[i][j] = gs * wv[i][j] * n + bs * wv[i][j];      // same association as the reference expression
+      }
+    store_row<T, NV>(y + r * F, F, lane, hv);
+    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SLN backward
+template <typename T, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+sln_bwd_kernel(int64_t rows, int64_t h_rows, int F, const T* __restrict__ dy, const T* __restrict__ h,
+               const T* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
+               const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ gamma_s,
+               const float* __restrict__ beta_s, const T* __restrict__ dh_res, const T* __restrict__ dw_res,
+               void* __restrict__ dh_out, T* __restrict__ dw, float* __restrict__ dgamma_s,
+               float* __restrict__ dbeta_s, float* __restrict__ dln_g, float* __restrict__ dln_b) {
+  __shared__ float s_dg[MAXE], s_db[MAXE];
+  __shared__ float s_scal[2];
+  for (int i = threadIdx.x; i < F; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  if (threadIdx.x < 2) s_scal[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  const bool bcast = h_rows < rows;
+  float g[NV][4], b[NV][4], adg[NV][4], adb[NV][4];
+  load_vec(ln_g, F, lane, g);
+  load_vec(ln_b, F, lane, b);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { adg[i][j] = 0.f; adb[i][j] = 0.f; }
+  const float gs = *gamma_s, bs = *beta_s;
+  const float invF = 1.0f / (float)F;
+  float a_gs = 0.f, a_bs = 0.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const int64_t hr = r % h_rows;
+    float hv[NV][4], wv[NV][4], dv[NV][4];
+    load_row<T, NV>(h + hr * F, F, lane, hv);
+    load_row<T, NV>(w + r * F, F, lane, wv);
+    load_row<T, NV>(dy + r * F, F, lane, dv);
+    const float mu = mean[r], rs = rstd[r];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (hv[i][j] - mu) * rs;
+        const float n = fmaf(xh, g[i][j], b[i][j]);      // LN output
+        const float da = dv[i][j] * wv[i][j];            // d/d(gamma_s*n + beta_s)
+        a_gs = fmaf(da, n, a_gs);
+        a_bs += da;
+        wv[i][j] = dv[i][j] * (gs * n + bs);             // dw
+        const float dn = da * gs;                        // grad of LN output
+        adg[i][j] = fmaf(dn, xh, adg[i][j]);
+        adb[i][j] += dn;
+        const float gd = dn * g[i][j];
+        c1 += gd;
+        c2 = fmaf(gd, xh, c2);
+        hv[i][j] = xh; dv[i][j] = gd;
+      }
+    c1 = warp_sum(c1) * invF;
+    c2 = warp_sum(c2) * invF;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dv[i][j] = rs * (dv[i][j] - c1 - hv[i][j] * c2);   // dh
+    if (dw_res != nullptr) {
+      float rv[NV][4];
+      load_row<T, NV>(dw_res + r * F, F, lane, rv);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[i][j] += rv[i][j];
+    }
+    store_row<T, NV>(dw + r * F, F, lane, wv);
+    if (bcast) {   // h is (S,F) shared by the whole batch: reduce over b with fp32 atomics
+      float* dh32 = static_cast<float*>(dh_out) + hr * F;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < F) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) atomicAdd(&dh32[c + j], dv[i][j]);
+        }
+      }
+    } else {
+      if (dh_res != nullptr) {
+        float rv[NV][4];
+        load_row<T, NV>(dh_res + r * F, F, lane, rv);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dv[i][j] += rv[i][j];
+      }
+      store_row<T, NV>(static_cast<T*>(dh_out) + r * F, F, lane, dv);
+    }
+  }
+  flush_cols(s_dg, dln_g, adg, F, lane);
+  flush_cols(s_db, dln_b, adb, F, lane);
+  a_gs = warp_sum(a_gs);
+  a_bs = warp_sum(a_bs);
+  if (lane == 0) { atomicAdd(&s_scal[0], a_gs); atomicAdd(&s_scal[1], a_bs); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F; i += blockDim.x) { atomicAdd(&dln_g[i], s_dg[i]); atomicAdd(&dln_b[i], s_db[i]); }
+  if (threadIdx.x == 0) { atomicAdd(dgamma_s, s_scal[0]); atomicAdd(dbeta_s, s_scal[1]); }
+}
+
+int grid_for_rows(int64_t rows, int ctas_per_sm) {
+  const int64_t need = (rows + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+  return (int)max((int64_t)1, min(need, cap));
+}
+
+}  // namespace
+}  // namespace vg
+
+using namespace vg;
+
+// pick the register tile: NV float4 per lane covers E <= NV*128
+#define VG_NV_DISPATCH(E, CALL)            \
+  do {                                     \
+    if ((E) <= 128) { constexpr int NV = 1; CALL; }       \
+    else if ((E) <= 256) { constexpr int NV = 2; CALL; }  \
+    else if ((E) <= 512) { constexpr int NV = 4; CALL; }  \
+    else { constexpr int NV = 8; CALL; }                  \
+  } while (0)
+
+#define VG_NORM_CHECK(E)                                                                                        \
+  VG_REQUIRE((E) > 0 && (E) % 4 == 0 && (E) <= MAXE, VG_ERR_SHAPE, "norm: feature dim %d must be a multiple of 4 and <= %d", (E), MAXE)
+
+extern "C" int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, const float* gamma, const float* beta,
+                                void* y, float* mean, float* rstd, float eps, void* stream) {
+  VG_NORM_CHECK(E);
+  if (rows == 0) return VG_OK;
+  const int grid = grid_for_rows(rows, 8);
+  if (dtype == VG_F32)
+    VG_NV_DISPATCH(E, (ln_fwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)x, gamma, beta, (float*)y, mean, rstd, eps)));
+  else
+    VG_NV_DISPATCH(E, (ln_fwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, eps)));
+  return check_launch("layernorm_fwd");
+}
+
+extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
+                                const float* rstd, const float* gamma, const void* dres, void* dx, float* dgamma,
+                                float* dbeta, void* stream) {
+  VG_NORM_CHECK(E);
+  if (rows == 0) return VG_OK;
+  const int grid = grid_for_rows(rows, 2);   // fewer CTAs -> fewer global atomics for dgamma/dbeta
+  if (dtype == VG_F32)
+    VG_NV_DISPATCH(E, (ln_bwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
+                                                                      (const float*)dres, (float*)dx, dgamma, dbeta)));
+  else
+    VG_NV_DISPATCH(E, (ln_bwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+                                                                     (const bf16*)dres, (bf16*)dx, dgamma, dbeta)));
+  return check_launch("layernorm_bwd");
+}
+
+extern "C" int vg_sln_fwd(int dtype, int64_t rows, int64_t h_rows, int F, const void* h, const void* w,
+                          const float* ln_g, const float* ln_b, const float* gamma_s, const float* beta_s, void* y,
+                          float* mean, float* rstd, float eps, void* stream) {
+  VG_NORM_CHECK(F);
+  VG_REQUIRE(h_rows > 0 && rows % h_rows == 0, VG_ERR_SHAPE, "sln: rows %lld not a multiple of h_rows %lld", (long long)rows, (long long)h_rows);
+  if (rows == 0) return VG_OK;
+  const int grid = grid_for_rows(rows, 8);
+  if (dtype == VG_F32)
+    VG_NV_DISPATCH(F, (sln_fwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, h_rows, F, (const float*)h, (const float*)w, ln_g, ln_b,
+                                                                       gamma_s, beta_s, (float*)y, mean, rstd, eps)));
+  else
+    VG_NV_DISPATCH(F, (sln_fwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, h_rows, F, (const bf16*)h, (const bf16*)w, ln_g, ln_b,
+                                                                      gamma_s, beta_s, (bf16*)y, mean, rstd, eps)));
+  return check_launch("sln_fwd");
+}
+
+extern "C" int vg_sln_bwd(int dtype, int64_t rows, int64_t h_rows, int F, const void* dy, const void* h, const void* w,
+                          const float* mean, const float* rstd, const float* ln_g, const float* ln_b,
+                          const float* gamma_s, const float* beta_s, const void* dh_res, const void* dw_res, void* dh,
+                          void* dw, float* dgamma_s, float* dbeta_s, float* dln_g, float* dln_b, void* stream) {
+  VG_NORM_CHECK(F);
+  VG_REQUIRE(h_rows > 0 && rows % h_rows == 0, VG_ERR_SHAPE, "sln: rows %lld not a multiple of h_rows %lld", (long long)rows, (long long)h_rows);
+  VG_REQUIRE(!(h_rows < rows && dh_res), VG_ERR_ARG, "sln_bwd: dh_res unsupported with broadcast h");
+  if (rows == 0) return VG_OK;
+  const int grid = grid_for_rows(rows, 2);
+  if (dtype == VG_F32)
+    VG_NV_DISPATCH(F, (sln_bwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, h_rows, F, (const float*)dy, (const float*)h, (const float*)w,
+        mean, rstd, ln_g, ln_b, gamma_s, beta_s, (const float*)dh_res, (const float*)dw_res, dh, (float*)dw, dgamma_s, dbeta_s, dln_g, dln_b)));
+  else
+    VG_NV_DISPATCH(F, (sln_bwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, h_rows, F, (const bf16*)dy, (const bf16*)h, (const bf16*)w,
+        mean, rstd, ln_g, ln_b, gamma_s, beta_s, (const bf16*)dh_res, (const bf16*)dw_res, dh, (bf16*)dw, dgamma_s, dbeta_s, dln_g, dln_b)));
+  return check_launch("sln_bwd");
+}

@@ -1,0 +1,379 @@
+"""torch.autograd.Function wrappers: one per reference block, forward and backward both made of this
+library's sm_100a kernels (ops.py -> C ABI).  Parameters stay the reference's fp32 nn.Parameters with the
+reference's names/shapes; packed / bf16 operand copies are built at call time and cached per parameter
+version (state_dict must not change).
+
+Precision: ``set_precision("bf16")`` (fast path: bf16 activations and GEMM operands on tcgen05, fp32
+accumulate/statistics, 2e-2 tolerance) or ``"fp32"`` (parity path: fp32 everywhere on CUDA cores, 1e-4).
+Double backward is not supported (the reference's active path never needs it).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import lib as L
+from . import ops
+
+_PRECISION = "bf16"
+_SKIP_PARAM_GRADS = False
+
+
+def set_precision(p: str):
+    global _PRECISION
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = p
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def act_dtype() -> torch.dtype:
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
+class skip_param_grads:
+    """Context: blocks return None for parameter gradients (used for the discriminator during the generator
+    update, where the reference computes D weight gradients only to zero them at the next iteration:
+    src/v2/training.py:177,204-210; src/v1/gan.py:222,247-251)."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global _SKIP_PARAM_GRADS
+        self.prev, _SKIP_PARAM_GRADS = _SKIP_PARAM_GRADS, self.enabled
+
+    def __exit__(self, *a):
+        global _SKIP_PARAM_GRADS
+        _SKIP_PARAM_GRADS = self.prev
+
+
+# --------------------------------------------------------------------------------------------------
+# operand cache: packed (and, on the fast path, bf16) copies of parameters, rebuilt when a parameter's
+# version counter changes (optimizer.step()).  Disable while capturing CUDA graphs so the casts are captured.
+# --------------------------------------------------------------------------------------------------
+_cache: dict = {}
+_cache_enabled = True
+
+
+def set_operand_cache(enabled: bool):
+    global _cache_enabled
+    _cache_enabled = enabled
+    _cache.clear()
+
+
+def invalidate_operands(param_ids):
+    """Drop cached operand copies that involve any of the given parameter ids (after an out-of-band update)."""
+    for key in [k for k in _cache if any(i in param_ids for i in k[0])]:
+        del _cache[key]
+
+
+def packed(params, dtype, cols=None, scales=None):
+    """Stack 2-D (or flattenable) fp32 parameters along dim 0 into one [sum(rows), cols] tensor of `dtype`.
+    scales: optional list of (num, den) 1-element device tensors (spectral rescale) per parameter."""
+    if len(params) == 1 and params[0].dtype == dtype and scales is None:
+        p = params[0].detach()
+        return p if p.dim() == 2 else p.reshape(p.shape[0], -1)
+    key = (tuple(id(p) for p in params), dtype)
+    ver = tuple((p._version, p.data_ptr()) for p in params)
+    if _cache_enabled and scales is None:
+        hit = _cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+    with torch.no_grad():
+        flat = [p.detach().reshape(p.shape[0], -1) if p.dim() != 1 else p.detach().reshape(-1, 1) for p in params]
+        cols = flat[0].shape[1]
+        out = torch.empty(sum(f.shape[0] for f in flat), cols, dtype=dtype, device=flat[0].device)
+        r = 0
+        for i, f in enumerate(flat):
+            num, den = scales[i] if scales is not None else (None, None)
+            ops.cast(f, dtype, out=out[r:r + f.shape[0]], num=num, den=den)
+            r += f.shape[0]
+    if _cache_enabled and scales is None:
+        _cache[key] = (ver, out)
+    return out
+
+
+def packed_vec(params):
+    """Concatenate fp32 bias vectors (stay fp32)."""
+    if len(params) == 1:
+        return params[0].detach()
+    return packed(params, torch.float32).reshape(-1)
+
+
+def _want(ctx, idx):
+    return ctx.needs_input_grad[idx] and not ctx.skip_pg
+
+
+# --------------------------------------------------------------------------------------------------
+# Linear (+ activation): y = act(x W^T + b)
+# --------------------------------------------------------------------------------------------------
+_ACT_BWD = {L.ACT_GELU: L.ACT_MUL_DGELU, L.ACT_TANH: L.ACT_MUL_DTANH, L.ACT_SIN: L.ACT_MUL_DSIN,
+            L.ACT_SIGMOID: L.ACT_MUL_DSIGMOID}
+
+
+class LinearFn(Function):
+    """nn.Linear (+ fused activation).  x: (..., K) activation dtype or fp32; returns (..., N) in `out_dtype`.
+    compute='act' -> operands in the activation dtype; compute='fp32' -> fp32 CUDA-core GEMM (tiny heads)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, act_param, compute, out_dtype):
+        cdt = act_dtype() if compute == "act" else torch.float32
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != cdt:
+            x2 = ops.cast(x2, cdt)
+        w = packed([weight], cdt)
+        odt = out_dtype or cdt
+        need_pre = act in (L.ACT_GELU, L.ACT_SIN)
+        res = ops.gemm(x2, w, bias=None if bias is None else bias.detach(), act=act, act_param=act_param,
+                       want_pre=need_pre, out_dtype=odt)
+        y, pre = res if need_pre else (res, None)
+        ctx.save_for_backward(x2, weight, pre if need_pre else (y if act != L.ACT_NONE else None))
+        ctx.meta = (act, act_param, cdt, x.shape, x.dtype, bias is not None)
+        ctx.skip_pg = _SKIP_PARAM_GRADS
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, weight, aux = ctx.saved_tensors
+        act, act_param, cdt, xshape, xdtype, has_bias = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        if act != L.ACT_NONE:   # dpre = dy * act'(.)
+            dy2 = _act_backward(dy2, aux, act, act_param)
+        if dy2.dtype != cdt:
+            dy2 = ops.cast(dy2, cdt)
+        w = packed([weight], cdt)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dy2, w, trans_b=False, out_dtype=cdt)
+            if dx.dtype != xdtype:
+                dx = ops.cast(dx, xdtype)
+            dx = dx.reshape(xshape)
+        if _want(ctx, 1):
+            dw = ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True).reshape(weight.shape)
+        if has_bias and _want(ctx, 2):
+            db = ops.colsum(dy2)
+        return dx, dw, db, None, None, None, None
+
+
+def _act_backward(dy2, aux, act, act_param):
+    """dpre = dy * act'(aux) for a standalone Linear(+activation) layer (vg_act_backward kernel)."""
+    aux2 = aux.reshape(dy2.shape)
+    if dy2.dtype != aux2.dtype:
+        dy2 = ops.cast(dy2, aux2.dtype)
+    return ops.act_backward(dy2, aux2.contiguous(), act, act_param)
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm
+# --------------------------------------------------------------------------------------------------
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        y, mean, rstd = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps)
+        ctx.save_for_backward(x2, mean, rstd, weight)
+        ctx.skip_pg = _SKIP_PARAM_GRADS
+        return y.reshape(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, mean, rstd, weight = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape).contiguous()
+        dx, dg, db = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach())
+        keep = not ctx.skip_pg
+        return dx.reshape(dy.shape), dg if keep else None, db if keep else None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# v2 EmbedLayer: conv(k=s=P)+bias, +pos (patch rows), CLS row       src/v2/modules.py:82-100
+# --------------------------------------------------------------------------------------------------
+class EmbedV2Fn(Function):
+    @staticmethod
+    def forward(ctx, img, conv_w, conv_b, pos, cls, patch):
+        adt = act_dtype()
+        B, Cc, I, _ = img.shape
+        E = conv_w.shape[0]
+        N = (I // patch) ** 2
+        patches = ops.im2col(img, patch, adt)                        # [B*N, C*P*P]
+        w = packed([conv_w], adt)                                     # [E, C*P*P]
+        posd = packed([pos.reshape(N, E)], adt)
+        x = torch.empty(B, N + 1, E, dtype=adt, device=img.device)
+        ops.gemm(patches, w, bias=conv_b.detach(), residual=posd, res_row_mod=N, c_row_group=N, out=x.view(B * (N + 1), E))
+        ops.fill_rows(x, 0, cls.detach().reshape(E))
+        ctx.save_for_backward(patches, conv_w)
+        ctx.meta = (B, Cc, I, patch, N, E, pos.shape, cls.shape)
+        ctx.skip_pg = _SKIP_PARAM_GRADS
+        return x
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dx):
+        patches, conv_w = ctx.saved_tensors
+        B, Cc, I, patch, N, E, pos_shape, cls_shape = ctx.meta
+        dtok, dcls, dpos = ops.embed_bwd_split(dx.contiguous(), pos_has_cls=False)
+        dimg = dw = db = None
+        if ctx.needs_input_grad[0]:
+            w = packed([conv_w], dtok.dtype)
+            dpatches = ops.gemm(dtok, w, trans_b=False)
+            dimg = ops.col2im(dpatches, B, Cc, I, patch)
+        if ctx.skip_pg:
+            return dimg, None, None, None, None, None
+        dw = ops.gemm(dtok, patches, trans_a=True, trans_b=False, accumulate=True).reshape(conv_w.shape)
+        db = ops.colsum(dtok)
+        return dimg, dw, db, dpos.reshape(pos_shape), dcls.reshape(cls_shape), None
+
+
+# --------------------------------------------------------------------------------------------------
+# attention sub-layer helpers (shared by SelfAttentionFn and EncoderFn)
+# --------------------------------------------------------------------------------------------------
+def _attn_fwd(xn, B, S, H, wqkv, bqkv, wo, bo, residual, scale, mode=L.ATTN_DOT):
+    E3 = wqkv.shape[0]
+    hd = E3 // 3
+    d = hd // H
+    qkv = ops.gemm(xn, wqkv, bias=bqkv)                                            # fused Q|K|V projection
+    o, lse = ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale, mode)
+    y = ops.gemm(o, wo, bias=bo, residual=residual)                                # out-proj (+bias, +skip)
+    return y, qkv, o, lse
+
+
+def _attn_bwd(dy, xn, qkv, o, lse, B, S, H, wqkv, wo, scale, want_pg, mode=L.ATTN_DOT, has_bias=True):
+    hd = qkv.shape[1] // 3
+    d = hd // H
+    g = {}
+    if want_pg:
+        g["wo"] = ops.gemm(dy, o, trans_a=True, trans_b=False, accumulate=True)
+        if has_bias:
+            g["bo"] = ops.colsum(dy)
+    d_o = ops.gemm(dy, wo, trans_b=False)
+    dqkv = ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, d_o, lse, B, H, S, d, scale, mode)
+    if want_pg:
+        g["wqkv"] = ops.gemm(dqkv, xn, trans_a=True, trans_b=False, accumulate=True)
+        if has_bias:
+            g["bqkv"] = ops.colsum(dqkv)
+    dxn = ops.gemm(dqkv, wqkv, trans_b=False)
+    return dxn, g
+
+
+class SelfAttentionFn(Function):
+    """v2 SelfAttention.forward (src/v2/modules.py:123-162): fused QKV GEMM -> flash attention -> out-proj."""
+
+    @staticmethod
+    def forward(ctx, x, n_heads, wq, bq, wk, bk, wv, bv, wo, bo):
+        adt = act_dtype()
+        B, S, E = x.shape
+        x2 = x.reshape(B * S, E)
+        if x2.dtype != adt:
+            x2 = ops.cast(x2, adt)
+        wqkv, bqkv = packed([wq, wk, wv], adt), packed_vec([bq, bk, bv])
+        wo_ = packed([wo], adt)
+        scale = 1.0 / math.sqrt(E // n_heads)
+        y, qkv, o, lse = _attn_fwd(x2.contiguous(), B, S, n_heads, wqkv, bqkv, wo_, bo.detach(), None, scale)
+        ctx.save_for_backward(x2, qkv, o, lse, wq, wk, wv, wo)
+        ctx.meta = (B, S, E, n_heads, scale, x.dtype)
+        ctx.skip_pg = _SKIP_PARAM_GRADS
+        return y.reshape(B, S, E)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, qkv, o, lse, wq, wk, wv, wo = ctx.saved_tensors
+        B, S, E, H, scale, xdtype = ctx.meta
+        adt = x2.dtype
+        dy2 = dy.reshape(B * S, E).contiguous()
+        dxn, g = _attn_bwd(dy2, x2, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale,
+                           not ctx.skip_pg)
+        dx = dxn if dxn.dtype == xdtype else ops.cast(dxn, xdtype)
+        if ctx.skip_pg:
+            return (dx.reshape(B, S, E), None) + (None,) * 8
+        dw, db = g["wqkv"], g["bqkv"]
+        return (dx.reshape(B, S, E), None, dw[:E], db[:E], dw[E:2 * E], db[E:2 * E], dw[2 * E:], db[2 * E:], g["wo"], g["bo"])
+
+
+# --------------------------------------------------------------------------------------------------
+# v2 Encoder block (src/v2/modules.py:165-183): pre-LN attention + GELU MLP, both with skip connections
+# --------------------------------------------------------------------------------------------------
+class EncoderFn(Function):
+    @staticmethod
+    def forward(ctx, x, n_heads, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2):
+        adt = act_dtype()
+        B, S, E = x.shape
+        x2 = x.reshape(B * S, E)
+        if x2.dtype != adt:
+            x2 = ops.cast(x2, adt)
+        x2 = x2.contiguous()
+        scale = 1.0 / math.sqrt(E // n_heads)
+        xn1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w.detach(), n1b.detach())
+        x1, qkv, o, lse = _attn_fwd(xn1, B, S, n_heads, packed([wq, wk, wv], adt), packed_vec([bq, bk, bv]),
+                                    packed([wo], adt), bo.detach(), x2, scale)
+        xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w.detach(), n2b.detach())
+        g, u = ops.gemm(xn2, packed([w1], adt), bias=b1.detach(), act=L.ACT_GELU, want_pre=True)   # fc1 + GELU
+        y = ops.gemm(g, packed([w2], adt), bias=b2.detach(), residual=x1)                           # fc2 + skip
+        ctx.save_for_backward(x2, mean1, rstd1, xn1, qkv, o, lse, x1, mean2, rstd2, xn2, u, g,
+                              n1w, wq, wk, wv, wo, n2w, w1, w2)
+        ctx.meta = (B, S, E, n_heads, scale, x.dtype)
+        ctx.skip_pg = _SKIP_PARAM_GRADS
+        return y.reshape(B, S, E)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (x2, mean1, rstd1, xn1, qkv, o, lse, x1, mean2, rstd2, xn2, u, g, n1w, wq, wk, wv, wo, n2w, w1, w2) = ctx.saved_tensors
+        B, S, E, H, scale, xdtype = ctx.meta
+        adt = x2.dtype
+        pg = not ctx.skip_pg
+        dy2 = dy.reshape(B * S, E).contiguous()
+        if dy2.dtype != adt:
+            dy2 = ops.cast(dy2, adt)
+        # ---- MLP half
+        dw2 = db2 = dw1 = db1 = None
+        if pg:
+            dw2 = ops.gemm(dy2, g, trans_a=True, trans_b=False, accumulate=True)
+            db2 = ops.colsum(dy2)
+        du = ops.gemm(dy2, packed([w2], adt), trans_b=False, act=L.ACT_MUL_DGELU, aux=u)       # dgrad fc2 x gelu'(u)
+        if pg:
+            dw1 = ops.gemm(du, xn2, trans_a=True, trans_b=False, accumulate=True)
+            db1 = ops.colsum(du)
+        dxn2 = ops.gemm(du, packed([w1], adt), trans_b=False)
+        dx1, dn2w, dn2b = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w.detach(), dres=dy2)
+        # ---- attention half
+        dxn1, ga = _attn_bwd(dx1, xn1, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale, pg)
+        dx, dn1w, dn1b = ops.layernorm_bwd(dxn1, x2, mean1, rstd1, n1w.detach(), dres=dx1)
+        if dx.dtype != xdtype:
+            dx = ops.cast(dx, xdtype)
+        dx = dx.reshape(B, S, E)
+        if not pg:
+            return (dx, None) + (None,) * 16
+        dw, db = ga["wqkv"], ga["bqkv"]
+        return (dx, None, dn1w, dn1b, dw[:E], db[:E], dw[E:2 * E], db[E:2 * E], dw[2 * E:], db[2 * E:], ga["wo"], ga["bo"],
+                dn2w, dn2b, dw1, db1, dw2, db2)
+
+
+# --------------------------------------------------------------------------------------------------
+# CLS-row gather (x[:, 0, :]) with scatter backward
+# --------------------------------------------------------------------------------------------------
+class ClsRowFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, S, E = x.shape
+        xc = x.contiguous()
+        out = torch.empty(B, E, dtype=x.dtype, device=x.device)
+        ops.copy_rows(xc, S * E, B, E, out, E)
+        ctx.shape = (B, S, E)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        B, S, E = ctx.shape
+        dx = torch.zeros(B, S, E, dtype=dy.dtype, device=dy.device)
+        ops.copy_rows(dy.contiguous(), E, B, E, dx, S * E)
+        return dx

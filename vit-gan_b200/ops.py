@@ -1,0 +1,290 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers + the current stream.
+
+PyTorch is plumbing here (device memory, streams); every arithmetic kernel launched below is one of this
+repository's own sm_100a kernels.  All functions require CUDA tensors and raise on anything else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as L
+from .lib import lib, check
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+_TORCH = {L.F32: torch.float32, L.BF16: torch.bfloat16}
+
+# launches of this library's kernels since the last reset (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"vitgan_b200: unsupported dtype {t.dtype}") from None
+
+
+def _req(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"vitgan_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rowmajor2d(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"vitgan_b200: `{name}` must be 2-D with unit inner stride, got {tuple(t.shape)}/{t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, act=L.ACT_NONE, act_param=0.0, aux=None, residual=None,
+         want_pre=False, out=None, out_dtype=None, accumulate=False, c_row_group=0, res_row_mod=0, res_row_off=0,
+         path=L.GEMM_AUTO):
+    """C[M,N] = opA(a) @ opB(b) with the fused epilogue of vg_gemm (see include/vitgan_b200.h).
+
+    a: [M,K] (or [K,M] if trans_a); b: [N,K] if trans_b (an nn.Linear weight) else [K,N].
+    Returns C, or (C, pre_activation) when want_pre.
+    """
+    _req(a, "a"); _req(b, "b")
+    lda, ldb = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[0], b.shape[1]) if trans_b else (b.shape[1], b.shape[0])
+    if K != Kb:
+        raise ValueError(f"vitgan_b200.gemm: inner dims differ ({K} vs {Kb})")
+    if a.dtype != b.dtype:
+        raise TypeError(f"vitgan_b200.gemm: A/B dtypes differ ({a.dtype} vs {b.dtype})")
+    if out is None:
+        rows = M + (M // c_row_group if c_row_group > 0 else 0)
+        odt = out_dtype or (torch.float32 if accumulate else a.dtype)
+        out = (torch.zeros if accumulate else torch.empty)((rows, N), dtype=odt, device=a.device)
+    ldc = _rowmajor2d(out, "out")
+    pre = torch.empty((M, N), dtype=out.dtype, device=a.device) if want_pre else None
+    g = L.GemmArgs()
+    g.path, g.ab_dtype, g.c_dtype = path, dt(a), dt(out)
+    g.trans_a, g.trans_b, g.M, g.N, g.K = int(trans_a), int(trans_b), M, N, K
+    g.A, g.lda, g.B, g.ldb, g.C, g.ldc = a.data_ptr(), lda, b.data_ptr(), ldb, out.data_ptr(), ldc
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != N:
+            raise ValueError("vitgan_b200.gemm: bias must be fp32 of length N")
+        g.bias = bias.data_ptr()
+    g.act, g.act_param = act, float(act_param)
+    for name, t in (("aux", aux), ("residual", residual)):
+        if t is not None and t.dtype != out.dtype:
+            raise TypeError(f"vitgan_b200.gemm: `{name}` dtype {t.dtype} must equal the output dtype {out.dtype}")
+    if aux is not None:
+        g.aux, g.ldaux = aux.data_ptr(), _rowmajor2d(aux, "aux")
+    if residual is not None:
+        g.residual, g.ldres = residual.data_ptr(), _rowmajor2d(residual, "residual")
+    if pre is not None:
+        g.c_pre, g.ldpre = pre.data_ptr(), N
+    g.c_row_group, g.res_row_mod, g.res_row_off, g.accumulate = c_row_group, res_row_mod, res_row_off, int(accumulate)
+    check(lib.vg_gemm(C.byref(g), stream()), "vg_gemm")
+    _count()
+    return (out, pre) if want_pre else out
+
+
+def cast(src: torch.Tensor, dtype: torch.dtype, out=None, num=None, den=None):
+    """out = dtype(src * num/den)  (num/den: optional 1-element fp32 device tensors)."""
+    _req(src, "src")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    check(lib.vg_cast_scale(src.data_ptr(), dt(src), out.data_ptr(), dt(out), src.numel(), _ptr(num), _ptr(den), stream()),
+          "vg_cast_scale")
+    _count()
+    return out
+
+
+def colsum(x2d: torch.Tensor, out=None):
+    _req(x2d, "x")
+    ld = _rowmajor2d(x2d, "x")
+    if out is None:
+        out = torch.zeros(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+    check(lib.vg_colsum(x2d.data_ptr(), dt(x2d), x2d.shape[0], x2d.shape[1], ld, out.data_ptr(), stream()), "vg_colsum")
+    _count()
+    return out
+
+
+def layernorm_fwd(x2d, gamma, beta, eps=1e-5):
+    _req(x2d, "x")
+    rows, e = x2d.shape
+    y = torch.empty_like(x2d)
+    mean = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty_like(mean)
+    check(lib.vg_layernorm_fwd(dt(x2d), rows, e, x2d.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                               mean.data_ptr(), rstd.data_ptr(), eps, stream()), "vg_layernorm_fwd")
+    _count()
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None):
+    rows, e = x2d.shape
+    dx = torch.empty_like(x2d)
+    dgb = torch.zeros(2, e, dtype=torch.float32, device=x2d.device)
+    check(lib.vg_layernorm_bwd(dt(x2d), rows, e, dy2d.data_ptr(), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                               gamma.data_ptr(), _ptr(dres), dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), stream()),
+          "vg_layernorm_bwd")
+    _count()
+    return dx, dgb[0], dgb[1]
+
+
+def sln_fwd(h2d, w2d, ln_g, ln_b, gamma_s, beta_s, eps=1e-5):
+    rows, f = w2d.shape
+    y = torch.empty_like(w2d)
+    mean = torch.empty(rows, dtype=torch.float32, device=w2d.device)
+    rstd = torch.empty_like(mean)
+    check(lib.vg_sln_fwd(dt(w2d), rows, h2d.shape[0], f, h2d.data_ptr(), w2d.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(),
+                         gamma_s.data_ptr(), beta_s.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), eps, stream()),
+          "vg_sln_fwd")
+    _count()
+    return y, mean, rstd
+
+
+def sln_bwd(dy2d, h2d, w2d, mean, rstd, ln_g, ln_b, gamma_s, beta_s, dh_res=None, dw_res=None):
+    rows, f = w2d.shape
+    h_rows = h2d.shape[0]
+    bcast = h_rows < rows
+    dh = torch.zeros(h_rows, f, dtype=torch.float32, device=w2d.device) if bcast else torch.empty_like(h2d)
+    dw = torch.empty_like(w2d)
+    small = torch.zeros(2 + 2 * f, dtype=torch.float32, device=w2d.device)   # dgamma_s, dbeta_s, dln_g, dln_b
+    check(lib.vg_sln_bwd(dt(w2d), rows, h_rows, f, dy2d.data_ptr(), h2d.data_ptr(), w2d.data_ptr(), mean.data_ptr(),
+                         rstd.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), gamma_s.data_ptr(), beta_s.data_ptr(),
+                         _ptr(dh_res), _ptr(dw_res), dh.data_ptr(), dw.data_ptr(), small[0:1].data_ptr(),
+                         small[1:2].data_ptr(), small[2:2 + f].data_ptr(), small[2 + f:].data_ptr(), stream()), "vg_sln_bwd")
+    _count()
+    return dh, dw, small[0:1], small[1:2], small[2:2 + f], small[2 + f:]
+
+
+def attention_fwd(q, k, v, B, H, S, d, scale, mode=L.ATTN_DOT, ld_qkv=None, out=None):
+    """q,k,v: 2-D row-major views [B*S, >=H*d] sharing the leading dim (slices of a fused projection output)."""
+    ld = ld_qkv or q.stride(0)
+    if out is None:
+        out = torch.empty(B * S, H * d, dtype=q.dtype, device=q.device)
+    lse = torch.empty(B * H * S, dtype=torch.float32, device=q.device)
+    check(lib.vg_attention_fwd(dt(q), mode, B, H, S, d, q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(),
+                               out.stride(0), lse.data_ptr(), scale, stream()), "vg_attention_fwd")
+    _count()
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, d_o, lse, B, H, S, d, scale, mode=L.ATTN_DOT, dqkv=None):
+    """Returns dqkv [B*S, 3*H*d] laid out like a fused projection output (dq | dk | dv)."""
+    hd = H * d
+    if dqkv is None:
+        dqkv = torch.empty(B * S, 3 * hd, dtype=q.dtype, device=q.device)
+    delta = torch.empty(B * H * S, dtype=torch.float32, device=q.device)
+    check(lib.vg_attention_bwd(dt(q), mode, B, H, S, d, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), o.data_ptr(),
+                               d_o.data_ptr(), o.stride(0), lse.data_ptr(), dqkv.data_ptr(), dqkv[:, hd:].data_ptr(),
+                               dqkv[:, 2 * hd:].data_ptr(), dqkv.stride(0), scale, delta.data_ptr(), stream()),
+          "vg_attention_bwd")
+    _count(3)
+    return dqkv
+
+
+def im2col(img: torch.Tensor, P: int, dtype: torch.dtype):
+    _req(img, "img")
+    B, Cc, I, _ = img.shape
+    img = img.contiguous().float()
+    out = torch.empty(B * (I // P) ** 2, Cc * P * P, dtype=dtype, device=img.device)
+    check(lib.vg_im2col_patches(_DT[dtype], B, Cc, I, P, img.data_ptr(), out.data_ptr(), stream()), "vg_im2col_patches")
+    _count()
+    return out
+
+
+def col2im(dpatches: torch.Tensor, B, Cc, I, P):
+    dimg = torch.empty(B, Cc, I, I, dtype=torch.float32, device=dpatches.device)
+    check(lib.vg_col2im_patches(dt(dpatches), B, Cc, I, P, dpatches.data_ptr(), dimg.data_ptr(), stream()), "vg_col2im_patches")
+    _count()
+    return dimg
+
+
+def v1_tokens_fwd(img, win, stride, n_side, dtype):
+    B, Cc, I, _ = img.shape
+    img = img.contiguous().float()
+    out = torch.empty(B * n_side * n_side, Cc * win * win, dtype=dtype, device=img.device)
+    check(lib.vg_v1_tokens_fwd(_DT[dtype], B, Cc, I, win, stride, n_side, img.data_ptr(), out.data_ptr(), stream()), "vg_v1_tokens_fwd")
+    _count()
+    return out
+
+
+def v1_tokens_bwd(dtokens, B, Cc, I, win, stride, n_side):
+    dimg = torch.zeros(B, Cc, I, I, dtype=torch.float32, device=dtokens.device)
+    check(lib.vg_v1_tokens_bwd(dt(dtokens), B, Cc, I, win, stride, n_side, dtokens.data_ptr(), dimg.data_ptr(), stream()), "vg_v1_tokens_bwd")
+    _count()
+    return dimg
+
+
+def fill_rows(x3d, row, v, v2=None):
+    B, S, E = x3d.shape
+    check(lib.vg_fill_rows(dt(x3d), B, S, E, row, v.data_ptr(), _ptr(v2), x3d.data_ptr(), stream()), "vg_fill_rows")
+    _count()
+
+
+def embed_bwd_split(dx3d, pos_has_cls: bool):
+    B, S, E = dx3d.shape
+    dtok = torch.empty(B * (S - 1), E, dtype=dx3d.dtype, device=dx3d.device)
+    dcls = torch.zeros(E, dtype=torch.float32, device=dx3d.device)
+    dpos = torch.zeros(S if pos_has_cls else S - 1, E, dtype=torch.float32, device=dx3d.device)
+    check(lib.vg_embed_bwd_split(dt(dx3d), B, S, E, dx3d.data_ptr(), dtok.data_ptr(), dcls.data_ptr(), dpos.data_ptr(),
+                                 int(pos_has_cls), stream()), "vg_embed_bwd_split")
+    _count()
+    return dtok, dcls, dpos
+
+
+def copy_rows(src, ld_src, rows, cols, dst, ld_dst):
+    check(lib.vg_copy_rows(dt(src), rows, cols, src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, stream()), "vg_copy_rows")
+    _count()
+
+
+def act_backward(dy, aux, act, act_param=0.0):
+    if dy.dtype != aux.dtype:
+        raise TypeError("vitgan_b200.act_backward: dy/aux dtypes differ")
+    out = torch.empty_like(dy)
+    check(lib.vg_act_backward(dt(dy), dy.numel(), dy.data_ptr(), aux.data_ptr(), act, float(act_param), out.data_ptr(), stream()),
+          "vg_act_backward")
+    _count()
+    return out
+
+
+def add_(x, y):
+    check(lib.vg_add_inplace(dt(x), x.data_ptr(), y.data_ptr(), x.numel(), stream()), "vg_add_inplace")
+    _count()
+    return x
+
+
+def broadcast_rows(src2d, reps):
+    out = torch.empty(reps * src2d.shape[0], src2d.shape[1], dtype=src2d.dtype, device=src2d.device)
+    check(lib.vg_broadcast_rows(dt(src2d), src2d.data_ptr(), src2d.shape[0], src2d.shape[1], out.data_ptr(), reps, stream()),
+          "vg_broadcast_rows")
+    _count()
+    return out
+
+
+def sigma_max(mat_ptrs: torch.Tensor, n_mats, rows, cols, u_state, n_iters, out=None):
+    """mat_ptrs: int64 device tensor of fp32 matrix addresses."""
+    if out is None:
+        out = torch.empty(n_mats, dtype=torch.float32, device=u_state.device)
+    check(lib.vg_sigma_max(mat_ptrs.data_ptr(), n_mats, rows, cols, u_state.data_ptr(), n_iters, out.data_ptr(), stream()),
+          "vg_sigma_max")
+    _count()
+    return out
+
+
+def adam_step(p, g, m, v, step_count, lr, b1, b2, eps, wd, decoupled, grad_scale=1.0):
+    check(lib.vg_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd,
+                           int(decoupled), grad_scale, step_count.data_ptr(), stream()), "vg_adam_step")
+    _count(2)

@@ -1,0 +1,214 @@
+"""The G+D training step around the CUDA-backed modules: the reference's call sequence, flat gradient /
+parameter storage, a fused Adam(W) step, bucketed data-parallel all-reduce, and whole-step CUDA-graph capture.
+
+Call sites mirrored: src/v2/training.py:177-211 and src/v1/gan.py:222-252 (identical 3 D passes + 1 G pass).
+Everything here is host-side orchestration; the arithmetic lives in libvitgan_b200 (and torch's loss heads).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import functional as Fn
+from . import ops
+
+
+# --------------------------------------------------------------------------------------------------
+# flat storage: parameters and gradients of one network as views into two flat fp32 buffers
+# --------------------------------------------------------------------------------------------------
+class FlatNet:
+    """Re-homes the parameters (and .grad) of `module` into flat fp32 buffers WITHOUT replacing the
+    nn.Parameter objects (names, shapes, optimizer references and state_dict stay intact).
+    `exclude(name, param)` leaves a parameter out (e.g. the reference-frozen q/k/v of the v1 discriminator)."""
+
+    def __init__(self, module, exclude=None):
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad and not (exclude and exclude(n, p))]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        dev = self.params[0].device
+        # 16-byte aligned slots so every view is vector-load friendly
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.param_ids = {id(p) for p in self.params}
+        self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat_param[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        """Keeps .grad as views of the flat buffer (autograd then accumulates in place)."""
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+
+class FusedAdam:
+    """torch.optim.Adam / AdamW semantics (single launch over the flat buffers; vg_adam_step).
+    Mirrors AdamW(lr, weight_decay=1e-3) of src/v2/training.py:150-157 and Adam(lr, betas=(0.5,0.999)) of
+    src/v1/gan.py:316-328.  The step counter lives on the device so the update is graph-capturable."""
+
+    def __init__(self, net: FlatNet, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+        self.net, self.lr, self.betas, self.eps, self.wd, self.decoupled = net, lr, betas, eps, weight_decay, decoupled
+        dev = net.flat_param.device
+        self.exp_avg = torch.zeros_like(net.flat_param)
+        self.exp_avg_sq = torch.zeros_like(net.flat_param)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.grad_scale = 1.0
+
+    def zero_grad(self, set_to_none=False):
+        self.net.zero_grad()
+
+    def step(self):
+        with torch.no_grad():
+            ops.adam_step(self.net.flat_param, self.net.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                          self.betas[0], self.betas[1], self.eps, self.wd, self.decoupled, self.grad_scale)
+        Fn.invalidate_operands(self.net.param_ids)   # the kernel wrote parameter memory behind autograd's back
+
+
+# --------------------------------------------------------------------------------------------------
+# data parallel: bucketed gradient all-reduce, launched from backward hooks, overlapped with backward
+# --------------------------------------------------------------------------------------------------
+class GradBuckets:
+    """Splits a FlatNet's gradient buffer into contiguous buckets (reverse registration order ~ backward
+    order) and all-reduces a bucket asynchronously as soon as every gradient in it has been accumulated in
+    an *armed* backward pass.  Works with NCCL (GPU, one process per GPU) and gloo (CPU tests).
+
+    The D network is armed only for its second backward (grads of pass 1 accumulate locally);
+    the G network for its only backward.  `finish()` waits and rescales by 1/world_size."""
+
+    def __init__(self, net: FlatNet, n_buckets=2, group=None, average_in_place=True):
+        self.net, self.group, self.average_in_place = net, group, average_in_place
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n_buckets = max(1, min(n_buckets, len(net.params)))
+        per = (net.numel + n_buckets - 1) // n_buckets
+        self.bucket_of, self.bounds = [], []
+        # bucket boundaries on parameter boundaries
+        start, b = 0, 0
+        for i, (p, o) in enumerate(zip(net.params, net.offsets)):
+            end = net.offsets[i + 1] if i + 1 < len(net.params) else net.numel
+            self.bucket_of.append(b)
+            if end - start >= per and i + 1 < len(net.params) and b + 1 < n_buckets:
+                self.bounds.append((start, end)); start = end; b += 1
+        self.bounds.append((start, net.numel))
+        self.n = len(self.bounds)
+        self.sizes = [0] * self.n
+        for b in self.bucket_of:
+            self.sizes[b] += 1
+        self.armed = False
+        self.pending = [0] * self.n
+        self.works = []
+        for i, p in enumerate(net.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(param):
+            if not self.armed or self.world == 1:
+                return
+            b = self.bucket_of[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        s, e = self.bounds[b]
+        self.works.append(dist.all_reduce(self.net.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def arm(self):
+        self.armed = True
+        self.pending = list(self.sizes)
+        self.works = []
+
+    def finish(self):
+        """Wait for the launched buckets, reduce any bucket whose hooks did not all fire (unused params), average."""
+        if self.world > 1:
+            for b in range(self.n):
+                if self.pending[b] > 0:
+                    self._launch(b)
+            for w in self.works:
+                w.wait()
+            if self.average_in_place:       # else the optimizer folds 1/world into its update (FusedAdam.grad_scale)
+                self.net.flat_grad.mul_(1.0 / self.world)
+        self.armed = False
+        self.works = []
+
+
+# --------------------------------------------------------------------------------------------------
+# the step
+# --------------------------------------------------------------------------------------------------
+def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_buckets=None, g_buckets=None,
+             skip_unused_d_grads=False):
+    """One adversarial iteration: D(real), G(noise), D(fake.detach()) -> D step; D(fake) -> G step.
+
+    loss_kind 'ce'  : nn.CrossEntropyLoss with class-index targets (v2; shim Q2)
+    loss_kind 'bce' : nn.BCELoss with float (B,1) targets (v1)
+    skip_unused_d_grads: do not produce D's parameter gradients in the third pass (the reference computes
+    and then discards them, training.py:177 / gan.py:222); dgrad still flows to G.  Off by default.
+    """
+    b, dev = real.shape[0], real.device
+    if loss_kind == "ce":
+        ones = torch.ones(b, dtype=torch.long, device=dev)
+        zeros = torch.zeros(b, dtype=torch.long, device=dev)
+        crit = F.cross_entropy
+    else:
+        ones = torch.ones(b, 1, device=dev)
+        zeros = torch.zeros(b, 1, device=dev)
+        crit = F.binary_cross_entropy
+    disc_opt.zero_grad(set_to_none=False) if isinstance(disc_opt, FusedAdam) else disc_opt.zero_grad(set_to_none=True)
+    loss_real = crit(disc(real).float(), ones)
+    loss_real.backward()
+    fake = gen(noise)
+    if d_buckets is not None:
+        d_buckets.arm()
+    loss_fake = crit(disc(fake.detach()).float(), zeros)
+    loss_fake.backward()
+    if d_buckets is not None:
+        d_buckets.finish()
+    disc_opt.step()
+    gen_opt.zero_grad(set_to_none=False) if isinstance(gen_opt, FusedAdam) else gen_opt.zero_grad(set_to_none=True)
+    if g_buckets is not None:
+        g_buckets.arm()
+    with Fn.skip_param_grads(skip_unused_d_grads):
+        out = disc(fake)
+    loss_g = crit(out.float(), ones)
+    loss_g.backward()     # with skip_unused_d_grads only D's blocks were recorded with skip_pg; G's are unaffected
+    if g_buckets is not None:
+        g_buckets.finish()
+    gen_opt.step()
+    return loss_real.detach(), loss_fake.detach(), loss_g.detach()
+
+
+class GraphedStep:
+    """Whole-step CUDA graph: the ~600 kernel launches of one G+D iteration are captured once and replayed
+    with one cudaGraphLaunch (the small-E configs are launch-bound).  Inputs are copied
+    into static buffers; losses are read from static outputs.  Requires FusedAdam (device-side step counter)."""
+
+    def __init__(self, gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", warmup=3, **kw):
+        self.real, self.noise = real.clone(), noise.clone()
+        self.args = (gen, disc, gen_opt, disc_opt)
+        self.kw = dict(loss_kind=loss_kind, **kw)
+        Fn.set_operand_cache(False)        # casts/packs must be part of the captured work
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                gan_step(*self.args, self.real, self.noise, **self.kw)
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = gan_step(*self.args, self.real, self.noise, **self.kw)
+
+    def __call__(self, real, noise):
+        self.real.copy_(real, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        self.graph.replay()
+        return self.losses

@@ -1,0 +1,552 @@
+"""Host-side mirror of the reference's v1 ViTGAN modules (src/v1/*.py) on the sm_100a kernels.
+
+Generator     : mapping Linear -> 4 x TransformerSLN -> SLN -> 2 x SIREN -> view      (generator.py:58-69)
+Discriminator : scrambled overlapping-patch encoder -> 4 x Transformer with L2-distance attention and
+                spectral rescale of q/k/v -> Linear(432->1) -> sigmoid                 (discriminatorViT.py:44-51)
+
+Same class names, parameter names/shapes and state_dict keys as the reference.  The external shims the
+reference needs to run at all are constructor defaults here.  Reference quirks kept:
+  Q4  D's q/k/v weights never train (the reference orphans them) -> their gradients are not produced
+      unless ``train_qkv=True`` is set on the MultiHeadSelfAttention module (used by gradient parity tests);
+  Q5  sigma_max by power iteration with a persistent vector instead of 3 SVDs per head per forward;
+  Q6/Q7  +||q-k||_2 scores, scale 1/sqrt(H*d).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import functional as Fn
+from . import lib as L
+from . import ops
+from .functional import act_dtype, packed
+
+
+@dataclasses.dataclass
+class V1Config:
+    """The fields of src/v1/config.py:20-70 that reach the hot path (same names where they exist)."""
+
+    image_size: int = 32
+    number_of_channels: int = 3
+    lattent_space_size: int = 1024
+    feature_hidden_size: int = 384
+    g_layers: int = 4
+    output_hidden_dimension: int = 768
+    d_layers: int = 4
+    number_of_heads: int = 4
+    patch_size: int = 8
+    overlap: int = 2
+    omega_0: int = 30
+    d_out_features: int = 1
+
+
+# ==================================================================================================
+# autograd Functions
+# ==================================================================================================
+class SLNFn(Function):
+    """SLN.forward (spectral_layer_norm.py:19-20).  h: (S,F) fp32 parameter (first G layer, broadcast over the
+    batch) or (B,S,F) activations; w: (B,S,F)."""
+
+    @staticmethod
+    def forward(ctx, h, w, ln_w, ln_b, gamma, beta):
+        adt = act_dtype()
+        B, S, F_ = w.shape
+        w2 = w.reshape(B * S, F_)
+        if w2.dtype != adt:
+            w2 = ops.cast(w2, adt)
+        h2 = h.reshape(-1, F_)
+        if h2.dtype != adt:
+            h2 = ops.cast(h2, adt)
+        y, mean, rstd = ops.sln_fwd(h2.contiguous(), w2.contiguous(), ln_w.detach(), ln_b.detach(), gamma.detach().reshape(1),
+                                    beta.detach().reshape(1))
+        ctx.save_for_backward(h2, w2, mean, rstd, ln_w, ln_b, gamma, beta)
+        ctx.meta = (h.shape, h.dtype, w.shape, w.dtype)
+        ctx.skip_pg = Fn._SKIP_PARAM_GRADS
+        return y.reshape(B, S, F_)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        h2, w2, mean, rstd, ln_w, ln_b, gamma, beta = ctx.saved_tensors
+        hshape, hdtype, wshape, wdtype = ctx.meta
+        dy2 = dy.reshape(w2.shape).contiguous()
+        if dy2.dtype != w2.dtype:
+            dy2 = ops.cast(dy2, w2.dtype)
+        dh, dw, dgs, dbs, dlg, dlb = ops.sln_bwd(dy2, h2, w2, mean, rstd, ln_w.detach(), ln_b.detach(),
+                                                 gamma.detach().reshape(1), beta.detach().reshape(1))
+        if dh.dtype != hdtype:
+            dh = ops.cast(dh, hdtype)
+        if dw.dtype != wdtype:
+            dw = ops.cast(dw, wdtype)
+        if ctx.skip_pg:
+            return dh.reshape(hshape), dw.reshape(wshape), None, None, None, None
+        return dh.reshape(hshape), dw.reshape(wshape), dlg, dlb, dgs.reshape(gamma.shape), dbs.reshape(beta.shape)
+
+
+class MSAFn(Function):
+    """MultiHeadSelfAttention.forward (attention.py:97-103) incl. every Attention head (:43-52):
+    one grouped [F -> 3*H*d] projection GEMM from the 3H separate weight tensors (packed at call time),
+    flash attention (dot or L2), out-proj GEMM with bias and the block's residual fused in the epilogue.
+
+    inputs: x (B,S,F); res None | (B,S,F) | (S,F); sig None | fp32 [2,3H] (row 0 sigma_init, row 1 sigma_now) in the
+    order of `ws`; ws = q_0,k_0,v_0,q_1,... (reference module order)."""
+
+    @staticmethod
+    def forward(ctx, x, res, lp, n_heads, train_qkv, sig, wo, bo, *ws):
+        adt = act_dtype()
+        B, S, F_ = x.shape
+        x2 = x.reshape(B * S, F_)
+        if x2.dtype != adt:
+            x2 = ops.cast(x2, adt)
+        x2 = x2.contiguous()
+        H = n_heads
+        d = ws[0].shape[0]
+        order = [3 * h + j for j in range(3) for h in range(H)]            # q heads | k heads | v heads
+        scales = None if sig is None else [(sig[0, i:i + 1], sig[1, i:i + 1]) for i in order]
+        wqkv = packed([ws[i] for i in order], adt, scales=scales)
+        wo_ = packed([wo], adt)
+        mode = L.ATTN_L2 if lp == 2 else L.ATTN_DOT
+        scale = 1.0 / math.sqrt(H * d)                                       # attention.py:16,51,90 (Q7)
+        res2, rmod = None, 0
+        if res is not None:
+            res2 = res.reshape(-1, F_)
+            if res2.dtype != adt:
+                res2 = ops.cast(res2, adt)
+            res2 = res2.contiguous()
+            rmod = S if res2.shape[0] == S and B > 1 else 0
+        hd = H * d
+        qkv = ops.gemm(x2, wqkv)
+        o, lse = ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale, mode)
+        y = ops.gemm(o, wo_, bias=bo.detach(), residual=res2, res_row_mod=rmod)
+        ctx.save_for_backward(x2, qkv, o, lse, wqkv, wo)
+        ctx.meta = (B, S, F_, H, d, scale, mode, x.dtype, None if res is None else (res.shape, res.dtype), order,
+                    train_qkv, [w.shape for w in ws])
+        ctx.skip_pg = Fn._SKIP_PARAM_GRADS
+        return y.reshape(B, S, F_)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, qkv, o, lse, wqkv, wo = ctx.saved_tensors
+        B, S, F_, H, d, scale, mode, xdtype, resinfo, order, train_qkv, wshapes = ctx.meta
+        adt = x2.dtype
+        hd = H * d
+        pg = not ctx.skip_pg
+        dy2 = dy.reshape(B * S, F_).contiguous()
+        if dy2.dtype != adt:
+            dy2 = ops.cast(dy2, adt)
+        dwo = dbo = None
+        if pg:
+            dwo = ops.gemm(dy2, o, trans_a=True, trans_b=False, accumulate=True)
+            dbo = ops.colsum(dy2)
+        d_o = ops.gemm(dy2, packed([wo], adt), trans_b=False)
+        dqkv = ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, d_o, lse, B, H, S, d, scale, mode)
+        dws = [None] * len(wshapes)
+        if pg and train_qkv:
+            dw = ops.gemm(dqkv, x2, trans_a=True, trans_b=False, accumulate=True)          # [3*H*d, F]
+            for pos, i in enumerate(order):
+                dws[i] = dw[pos * d:(pos + 1) * d]
+        dx = ops.gemm(dqkv, wqkv, trans_b=False)
+        if dx.dtype != xdtype:
+            dx = ops.cast(dx, xdtype)
+        dres = None
+        if resinfo is not None:
+            rshape, rdtype = resinfo
+            if len(rshape) == 2 and B > 1:         # (S,F) residual broadcast over the batch: reduce over b
+                dres = ops.colsum(dy2.reshape(B, S * F_)).reshape(rshape)
+            else:
+                dres = dy2.reshape(rshape)
+            if dres.dtype != rdtype:
+                dres = ops.cast(dres, rdtype)
+        return (dx.reshape(B, S, F_), dres, None, None, None, None, dwo, dbo, *dws)
+
+
+class LinearResFn(Function):
+    """y = x W^T + b + res   (block MLP with the default ``layers=[]``: one Linear, no activation;
+    muilti_layer_perceptron.py:37-42, transformer.py:44,87)."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias):
+        adt = act_dtype()
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.dtype != adt:
+            x2 = ops.cast(x2, adt)
+        r2 = res.reshape(-1, weight.shape[0])
+        if r2.dtype != adt:
+            r2 = ops.cast(r2, adt)
+        y = ops.gemm(x2.contiguous(), packed([weight], adt), bias=bias.detach(), residual=r2.contiguous())
+        ctx.save_for_backward(x2, weight)
+        ctx.meta = (shp, x.dtype, res.shape, res.dtype)
+        ctx.skip_pg = Fn._SKIP_PARAM_GRADS
+        return y.reshape(res.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        shp, xdtype, rshape, rdtype = ctx.meta
+        adt = x2.dtype
+        dy2 = dy.reshape(-1, weight.shape[0]).contiguous()
+        if dy2.dtype != adt:
+            dy2 = ops.cast(dy2, adt)
+        dx = ops.gemm(dy2, packed([weight], adt), trans_b=False)
+        dw = db = None
+        if not ctx.skip_pg:
+            dw = ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True)
+            db = ops.colsum(dy2)
+        dres = dy2 if rdtype == adt else ops.cast(dy2, rdtype)
+        if dx.dtype != xdtype:
+            dx = ops.cast(dx, xdtype)
+        return dx.reshape(shp), dres.reshape(rshape), dw, db
+
+
+class PatchEncoderFn(Function):
+    """PatchEncoder.forward (patch_encoder.py:39-52): scrambled token gather -> Linear(432->F, no bias) with
+    +pos (rows 1..n) and the CLS slot fused in the GEMM epilogue; CLS row = cls + pos[0]."""
+
+    @staticmethod
+    def forward(ctx, img, proj_w, cls, pos, win, stride, n_side):
+        adt = act_dtype()
+        B, Cc, I, _ = img.shape
+        n = n_side * n_side
+        F_ = proj_w.shape[0]
+        tok = ops.v1_tokens_fwd(img, win, stride, n_side, adt)                       # [B*n, C*win*win]
+        posd = packed([pos], adt)
+        x = torch.empty(B, n + 1, F_, dtype=adt, device=img.device)
+        ops.gemm(tok, packed([proj_w], adt), residual=posd, res_row_mod=n, res_row_off=1, c_row_group=n,
+                 out=x.view(B * (n + 1), F_))
+        ops.fill_rows(x, 0, cls.detach().reshape(F_), pos.detach()[0])
+        ctx.save_for_backward(tok, proj_w)
+        ctx.meta = (B, Cc, I, win, stride, n_side, cls.shape, pos.shape)
+        ctx.skip_pg = Fn._SKIP_PARAM_GRADS
+        return x
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dx):
+        tok, proj_w = ctx.saved_tensors
+        B, Cc, I, win, stride, n_side, cls_shape, pos_shape = ctx.meta
+        dtok, dcls, dpos = ops.embed_bwd_split(dx.contiguous(), pos_has_cls=True)
+        dimg = None
+        if ctx.needs_input_grad[0]:
+            dtokens = ops.gemm(dtok, packed([proj_w], dtok.dtype), trans_b=False)
+            dimg = ops.v1_tokens_bwd(dtokens, B, Cc, I, win, stride, n_side)
+        if ctx.skip_pg:
+            return dimg, None, None, None, None, None, None
+        dw = ops.gemm(dtok, tok, trans_a=True, trans_b=False, accumulate=True)
+        return dimg, dw, dcls.reshape(cls_shape), dpos.reshape(pos_shape), None, None, None
+
+
+# ==================================================================================================
+# forward bodies (duck-typed: also bound onto reference instances by patch.patch_v1)
+# ==================================================================================================
+SIGMA_COLD_ITERS = 400     # first call per module: cold-start power iteration (~200 it for 4e-7)
+SIGMA_WARM_ITERS = 4       # afterwards the persistent vector is already converged
+
+
+def _msa_sigma(self, ws):
+    """[2, 3H] fp32 table (row 0 sigma_init, row 1 sigma_now) for the spectral rescale (attention.py:54-64), or None."""
+    heads = self.attention_heads
+    if not heads[0].spectral_scaling:
+        return None
+    dev = ws[0].device
+    key = tuple(w.data_ptr() for w in ws)
+    st = getattr(self, "_vg_sigma_state", None)
+    if st is None or st["key"] != key:
+        with torch.no_grad():
+            init = torch.tensor([float(s) for hd in heads for s in hd.init_spectrum], dtype=torch.float32)
+            sig = torch.empty(2, len(ws), dtype=torch.float32, device=dev)
+            sig[0] = init.to(dev)
+            st = {"key": key, "u": torch.zeros(len(ws), ws[0].shape[0], dtype=torch.float32, device=dev), "sig": sig,
+                  "warm": False, "ptrs": torch.tensor(key, dtype=torch.int64).to(dev)}
+        object.__setattr__(self, "_vg_sigma_state", st)
+    ops.sigma_max(st["ptrs"], len(ws), ws[0].shape[0], ws[0].shape[1], st["u"],
+                  SIGMA_WARM_ITERS if st["warm"] else SIGMA_COLD_ITERS, out=st["sig"][1])
+    st["warm"] = True
+    return st["sig"]
+
+
+def msa_forward(self, x, res=None):
+    """MultiHeadSelfAttention.forward (attention.py:97-103); `res` is the block's skip connection (fused)."""
+    heads = self.attention_heads
+    ws = [w for hd in heads for w in (hd.q.weight, hd.k.weight, hd.v.weight)]
+    lp = 2 if heads[0].attention_func.__name__ == "_l2att" else 1
+    sig = _msa_sigma(self, [w.detach() for w in ws])
+    train_qkv = getattr(self, "train_qkv", not heads[0].spectral_scaling)     # Q4: spectral heads are frozen
+    return MSAFn.apply(x, res, lp, len(heads), train_qkv, sig, self.output_linear.weight, self.output_linear.bias, *ws)
+
+
+def sln_forward(self, h, w):
+    return SLNFn.apply(h, w, self.layer_norm.weight, self.layer_norm.bias, self.gamma, self.beta)
+
+
+def _mlp_single(mlp):
+    if len(mlp.model) != 1:
+        raise NotImplementedError("vitgan_b200.v1: only the reference default MLP (layers=[]: one Linear) is implemented")
+    return mlp.model[0][0]
+
+
+def mlp_forward(self, x):
+    """MLP.forward, default single Linear (muilti_layer_perceptron.py:37-42)."""
+    lin = _mlp_single(self)
+    return Fn.LinearFn.apply(x, lin.weight, lin.bias, L.ACT_NONE, 0.0, "act", None)
+
+
+def transformer_sln_forward(self, h, x):
+    """TransformerSLN.forward (transformer.py:85-88) -> (x, hf)."""
+    htmp = msa_forward(self.msha, sln_forward(self.layer_norm_1, h, x), res=h)
+    lin = _mlp_single(self.mlp)
+    hf = LinearResFn.apply(sln_forward(self.layer_norm_2, htmp, x), htmp, lin.weight, lin.bias)
+    return x, hf
+
+
+def transformer_forward(self, x):
+    """Transformer.forward (transformer.py:40-45)."""
+    if x.dtype != act_dtype():
+        x = x.to(act_dtype())
+    x1 = Fn.LayerNormFn.apply(x, self.layer_norm_1.weight, self.layer_norm_1.bias, self.layer_norm_1.eps)
+    x = msa_forward(self.msha, x1, res=x)
+    x2 = Fn.LayerNormFn.apply(x, self.layer_norm_2.weight, self.layer_norm_2.bias, self.layer_norm_2.eps)
+    lin = _mlp_single(self.mlp)
+    return LinearResFn.apply(x2, x, lin.weight, lin.bias)
+
+
+def siren_forward(self, x):
+    """SIREN.forward (siren.py:44-45): sin(omega_0 * (xW^T + b)), sine taken on the fp32 accumulator."""
+    return Fn.LinearFn.apply(x, self.linear.weight, self.linear.bias, L.ACT_SIN, float(self.siren_parameters.omega_0),
+                             "act", None)
+
+
+def patch_encoder_forward(self, images):
+    """PatchEncoder.forward (patch_encoder.py:39-52)."""
+    if images.dim() != 4:
+        raise AssertionError("Expected input image tensor to be of shape BxCxHxW")
+    if images.shape[2] != images.shape[3]:
+        raise AssertionError("The provided images are not square shaped")
+    win = self.patch_size + 2 * self.overlap
+    n_side = int(round(math.sqrt(self.number_of_tokens)))
+    return PatchEncoderFn.apply(images, self.projection_matrix.weight, self.cls_token, self.positional_embedding, win,
+                                self.stride, n_side)
+
+
+def generator_forward(self, x):
+    """Generator.forward (generator.py:58-69)."""
+    i, f = self._vg_image_size, self._vg_feature
+    weights = mlp_forward(self.mapping_mlp, x).view(-1, i, f)
+    h = self.embedding
+    for tf in self.transformer_layers:
+        weights, h = transformer_sln_forward(tf, h, weights)
+    weights = sln_forward(self.sln, h, weights)
+    y = siren_forward(self.output_network[0], weights)
+    last = self.output_network[1]
+    y = Fn.LinearFn.apply(y, last.linear.weight, last.linear.bias, L.ACT_SIN, float(last.siren_parameters.omega_0), "act",
+                          torch.float32)                                  # image leaves the generator in fp32
+    return y.view(x.shape[0], self._vg_channels, i, i)
+
+
+def discriminator_forward(self, images):
+    """Discriminator.forward (discriminatorViT.py:44-51)."""
+    tokens = patch_encoder_forward(self.patch_encoder, images)
+    for t in self.transformer_layers:
+        tokens = transformer_forward(t, tokens)
+    lin = _mlp_single(self.mlp)
+    c = Fn.ClsRowFn.apply(tokens)
+    return Fn.LinearFn.apply(c, lin.weight, lin.bias, L.ACT_SIGMOID, 0.0, "act", torch.float32)
+
+
+FORWARDS = {
+    "SLN": sln_forward,
+    "MultiHeadSelfAttention": msa_forward,
+    "MLP": mlp_forward,
+    "Transformer": transformer_forward,
+    "TransformerSLN": transformer_sln_forward,
+    "SIREN": siren_forward,
+    "PatchEncoder": patch_encoder_forward,
+    "Generator": generator_forward,
+    "Discriminator": discriminator_forward,
+}
+
+
+def prepare_reference_module(m):
+    """Cache on a reference Generator the module-global config values its forward reads (generator.py:60,67)."""
+    if type(m).__name__ == "Generator" and not hasattr(m, "_vg_image_size"):
+        i, f = m.embedding.shape
+        object.__setattr__(m, "_vg_image_size", i)
+        object.__setattr__(m, "_vg_feature", f)
+        object.__setattr__(m, "_vg_channels", m.output_network[1].linear.out_features // i)
+
+
+# ==================================================================================================
+# module classes (mirror): same names / parameters / registration order (=> same seeded init) as the reference
+# ==================================================================================================
+class SIRENParameters:
+    def __init__(self, input_features, output_features, bias=True, is_first=False, omega_0=30):
+        self.input_features, self.output_features, self.bias = input_features, output_features, bias
+        self.is_first, self.omega_0 = is_first, omega_0
+
+
+class TransformerParameters:
+    def __init__(self, input_features, spectral_scaling, lp, number_of_heads=4):
+        self.input_features, self.spectral_scaling, self.lp, self.number_of_heads = input_features, spectral_scaling, lp, number_of_heads
+
+
+class MLP(nn.Module):
+    """Default MLP of the reference (layers=[]): ModuleList([Sequential(Linear, Dropout)])."""
+
+    def __init__(self, input_features, output_features, dropout_rate=0.0):
+        super().__init__()
+        self.model = nn.ModuleList([nn.Sequential(nn.Linear(input_features, output_features), nn.Dropout(dropout_rate))])
+
+    forward = mlp_forward
+
+
+class SLN(nn.Module):
+    def __init__(self, number_of_features):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(number_of_features)
+        self.beta = nn.Parameter(torch.randn(1, 1, 1))
+        self.gamma = nn.Parameter(torch.randn(1, 1, 1))
+
+    forward = sln_forward
+
+
+class Attention(nn.Module):
+    """Parameter container for one head (attention.py:7-41); the math runs grouped in MultiHeadSelfAttention."""
+
+    def __init__(self, transformer_parameters, output_features, scale=None):
+        super().__init__()
+        self.output_features = output_features
+        self.scale = output_features if scale is None else scale
+        self.spectral_scaling = transformer_parameters.spectral_scaling
+        assert transformer_parameters.lp in [1, 2], f"Unsupported norm for attention: lp={transformer_parameters.lp} but should be 1 or 2"
+        self.attention_func = self._l1att if transformer_parameters.lp == 1 else self._l2att
+        f = transformer_parameters.input_features
+        self.q = nn.Linear(f, output_features, bias=False)
+        self.k = nn.Linear(f, output_features, bias=False)
+        self.v = nn.Linear(f, output_features, bias=False)
+        if self.spectral_scaling:   # attention.py:37-39: sigma at construction (host-side, one-off, not the hot path)
+            with torch.no_grad():
+                self.init_spectrum = [torch.linalg.svdvals(w.weight).max() for w in (self.q, self.k, self.v)]
+
+    def _l2att(self, q, k):   # markers only: msa_forward dispatches on the bound name
+        raise RuntimeError("vitgan_b200: heads are evaluated by MultiHeadSelfAttention")
+
+    def _l1att(self, q, k):
+        raise RuntimeError("vitgan_b200: heads are evaluated by MultiHeadSelfAttention")
+
+    def forward(self, x):
+        raise RuntimeError("vitgan_b200: call the enclosing MultiHeadSelfAttention (heads are fused into one kernel)")
+
+
+class MultiHeadSelfAttention(nn.Module):
+    def __init__(self, transformer_parameters, output_size, head_dimension):
+        super().__init__()
+        self.output_dimension = transformer_parameters.number_of_heads * head_dimension
+        self.output_features = output_size
+        self.attention_heads = nn.ModuleList([
+            Attention(transformer_parameters, output_features=head_dimension, scale=self.output_dimension)
+            for _ in range(transformer_parameters.number_of_heads)])
+        self.output_linear = nn.Linear(self.output_dimension, self.output_features)
+
+    forward = msa_forward
+
+
+class Transformer(nn.Module):
+    def __init__(self, transformer_parameters, attention_dropout_rate=0.2, mlp_dropout=0.2):
+        super().__init__()
+        f = transformer_parameters.input_features
+        self.head_output_dimension = f // transformer_parameters.number_of_heads
+        self.layer_norm_1 = nn.LayerNorm(f)
+        self.layer_norm_2 = nn.LayerNorm(f)
+        self.attention_dropout = nn.Dropout(attention_dropout_rate)
+        self.msha = MultiHeadSelfAttention(transformer_parameters, head_dimension=self.head_output_dimension, output_size=f)
+        self.mlp = MLP(f, f, dropout_rate=mlp_dropout)
+        self.input_features = f      # shim Q3
+
+    forward = transformer_forward
+
+
+class TransformerSLN(nn.Module):
+    def __init__(self, transformer_parameters, attention_dropout_rate=0.2, mlp_dropout=0.2):
+        super().__init__()
+        f = transformer_parameters.input_features
+        self.head_output_dimension = f // transformer_parameters.number_of_heads
+        self.layer_norm_1 = SLN(number_of_features=f)
+        self.layer_norm_2 = SLN(number_of_features=f)
+        self.attention_dropout = nn.Dropout(attention_dropout_rate)
+        self.msha = MultiHeadSelfAttention(transformer_parameters, head_dimension=self.head_output_dimension, output_size=f)
+        self.mlp = MLP(f, f, dropout_rate=mlp_dropout)
+
+    forward = transformer_sln_forward
+
+
+class SIREN(nn.Module):
+    def __init__(self, siren_parameters):
+        self.siren_parameters = siren_parameters
+        super().__init__()
+        p = siren_parameters
+        self.linear = nn.Linear(p.input_features, p.output_features, bias=p.bias)
+        with torch.no_grad():   # siren.py:29-42
+            if p.is_first:
+                self.linear.weight.uniform_(-1 / p.input_features, 1 / p.input_features)
+            else:
+                b = np.sqrt(6 / p.input_features) / p.omega_0
+                self.linear.weight.uniform_(-b, b)
+
+    forward = siren_forward
+
+
+class PatchEncoder(nn.Module):
+    def __init__(self, cfg: V1Config, projection_output_size=None):
+        super().__init__()
+        self.patch_size, self.overlap = cfg.patch_size, cfg.overlap
+        win = self.patch_size + 2 * self.overlap
+        self.token_size = cfg.number_of_channels * win ** 2                                       # patch_encoder.py:17-19
+        self.stride = (cfg.image_size - self.patch_size - 2 * self.overlap) // self.patch_size + 1  # :20-22
+        self.number_of_tokens = ((cfg.image_size - (win - 1) - 1) // self.stride + 1) ** 2          # :23-27
+        self.projection_output_size = projection_output_size or self.token_size                   # shim Q3 (= 432)
+        self.projection_matrix = nn.Linear(self.token_size, self.projection_output_size, bias=False)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, self.projection_output_size))
+        self.positional_embedding = nn.Parameter(torch.randn(self.number_of_tokens + 1, self.projection_output_size))
+        self.dropout = nn.Dropout(p=0.0)
+
+    forward = patch_encoder_forward
+
+
+class Generator(nn.Module):
+    def __init__(self, cfg: V1Config | None = None):
+        super().__init__()
+        cfg = cfg or V1Config()
+        i, f = cfg.image_size, cfg.feature_hidden_size
+        self.mapping_mlp = MLP(cfg.lattent_space_size, i * f)
+        self.embedding = nn.Parameter(torch.randn(i, f))
+        tp = TransformerParameters(input_features=f, spectral_scaling=False, lp=1, number_of_heads=cfg.number_of_heads)
+        self.transformer_layers = nn.ModuleList([TransformerSLN(tp) for _ in range(cfg.g_layers)])
+        self.sln = SLN(number_of_features=f)
+        self.output_network = nn.Sequential(
+            SIREN(SIRENParameters(f, cfg.output_hidden_dimension, is_first=True, omega_0=cfg.omega_0)),
+            SIREN(SIRENParameters(cfg.output_hidden_dimension, cfg.number_of_channels * i, is_first=False, omega_0=cfg.omega_0)))
+        self._vg_image_size, self._vg_feature, self._vg_channels = i, f, cfg.number_of_channels
+
+    forward = generator_forward
+
+
+class Discriminator(nn.Module):
+    def __init__(self, cfg: V1Config | None = None):
+        super().__init__()
+        cfg = cfg or V1Config()
+        self.patch_encoder = PatchEncoder(cfg)
+        tp = TransformerParameters(input_features=self.patch_encoder.token_size, spectral_scaling=True, lp=2,
+                                   number_of_heads=cfg.number_of_heads)
+        self.transformer_layers = nn.ModuleList([Transformer(tp) for _ in range(cfg.d_layers)])
+        self.mlp = MLP(self.transformer_layers[-1].input_features, cfg.d_out_features)
+        self.sigmoid = nn.Sigmoid()
+
+    forward = discriminator_forward
