@@ -1,0 +1,303 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (vitgan_b200.ops -> libvitgan_b200.so)
+and compared with the CPU oracle / plain torch fp32 formulas on the same seeded inputs.
+Tolerances (BASELINE.json): 1e-4 relative for fp32, 2e-2 for bf16 (max|a-b| / max|b| per tensor)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import harness, v1 as o1
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL, BF16_TOL = 1e-4, 2e-2
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import vitgan_b200
+    return vitgan_b200
+
+
+def rel(a, b):
+    return harness.rel_err(a, b)
+
+
+def gen(seed=0):
+    return torch.Generator("cpu").manual_seed(seed)
+
+
+def act_ref(act, v, aux, prm):
+    if act == 1: return F.gelu(v)
+    if act == 2: return torch.tanh(v)
+    if act == 3: return torch.sin(prm * v)
+    if act == 4: return torch.sigmoid(v)
+    if act == 5: return v * (0.5 * (1 + torch.erf(aux / math.sqrt(2))) + aux * torch.exp(-0.5 * aux * aux) / math.sqrt(2 * math.pi))
+    if act == 6: return v * (1 - aux * aux)
+    if act == 7: return v * prm * torch.cos(prm * aux)
+    if act == 8: return v * aux * (1 - aux)
+    return v
+
+
+GEMM_SHAPES = [(128, 128, 64), (256, 384, 128), (1000, 200, 72), (33280 // 8, 128, 256), (65, 10, 128), (7, 8, 16)]
+
+
+@pytest.mark.parametrize("path", ["simt_f32", "simt_bf16", "tc"])
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_layouts(vb, path, ta, tb, M, N, K):
+    L = vb.lib
+    g = gen(M + N + K)
+    dt = torch.float32 if path == "simt_f32" else torch.bfloat16
+    a = torch.randn((K, M) if ta else (M, K), generator=g).to(dt)
+    b = torch.randn((N, K) if tb else (K, N), generator=g).to(dt)
+    if path == "tc" and (a.shape[1] % 8 or b.shape[1] % 8):
+        pytest.skip("tcgen05 path needs 16-byte row pitch (checked separately in test_gemm_tc_rejects)")
+    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float())
+    out = vb.ops.gemm(a.cuda(), b.cuda(), trans_a=bool(ta), trans_b=bool(tb), out_dtype=torch.float32,
+                      path=L.GEMM_TCGEN05 if path == "tc" else L.GEMM_SIMT)
+    assert rel(out, ref) < 1e-5 * max(1, K / 64)
+
+
+@pytest.mark.parametrize("path", ["simt", "tc"])
+def test_gemm_split_k_accumulate(vb, path):
+    L = vb.lib
+    g = gen(3)
+    dy = torch.randn(33280 // 4, 384, generator=g).bfloat16()
+    x = torch.randn(33280 // 4, 128, generator=g).bfloat16()
+    ref = dy.float().t() @ x.float()
+    out = vb.ops.gemm(dy.cuda(), x.cuda(), trans_a=True, trans_b=False, accumulate=True,
+                      path=L.GEMM_TCGEN05 if path == "tc" else L.GEMM_SIMT)
+    assert out.dtype == torch.float32 and rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("path", ["simt_f32", "simt_bf16", "tc"])
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+def test_gemm_epilogue(vb, path, act):
+    L = vb.lib
+    g = gen(act)
+    dt = torch.float32 if path == "simt_f32" else torch.bfloat16
+    M, N, K = 300, 136, 64
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dt)
+    w = (torch.randn(N, K, generator=g) * 0.2).to(dt)
+    bias = torch.randn(N, generator=g)
+    aux = (torch.rand(M, N, generator=g) * 0.9).to(dt)
+    res = torch.randn(M, N, generator=g).to(dt)
+    pre_ref = a.float() @ w.float().t() + bias
+    ref = act_ref(act, pre_ref, aux.float(), 30.0 if act in (3, 7) else 0.0) + res.float()
+    out, pre = vb.ops.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), act=act, act_param=30.0 if act in (3, 7) else 0.0,
+                           aux=aux.cuda() if act >= 5 else None, residual=res.cuda(), want_pre=True,
+                           path=L.GEMM_TCGEN05 if path == "tc" else L.GEMM_SIMT)
+    tol = FP32_TOL if dt == torch.float32 else BF16_TOL
+    if act in (3, 7) and dt != torch.float32:
+        tol = 0.1   # sin(30 x) amplifies the bf16 rounding of the stored output 30x; the fp32 accumulator path is exact
+    assert rel(pre, pre_ref) < tol and rel(out, ref) < tol
+
+
+def test_gemm_row_remaps(vb):
+    """CLS slot (c_row_group) + positional-embedding broadcast (res_row_mod/off) of the patch-embed epilogue."""
+    g = gen(5)
+    B, n, K, E = 3, 16, 48, 64
+    a = torch.randn(B * n, K, generator=g)
+    w = torch.randn(E, K, generator=g)
+    pos = torch.randn(n + 1, E, generator=g)
+    ref = torch.zeros(B, n + 1, E)
+    ref[:, 1:] = (a @ w.t()).view(B, n, E) + pos[1:]
+    out = torch.zeros(B * (n + 1), E, device="cuda")
+    vb.ops.gemm(a.cuda(), w.cuda(), residual=pos.cuda(), res_row_mod=n, res_row_off=1, c_row_group=n, out=out)
+    assert rel(out.view(B, n + 1, E), ref) < FP32_TOL
+    for path in (vb.lib.GEMM_SIMT, vb.lib.GEMM_TCGEN05):
+        out = torch.zeros(B * (n + 1), E, device="cuda", dtype=torch.bfloat16)
+        vb.ops.gemm(a.cuda().bfloat16(), w.cuda().bfloat16(), residual=pos.cuda().bfloat16(), res_row_mod=n, res_row_off=1,
+                    c_row_group=n, out=out, path=path)
+        assert rel(out.view(B, n + 1, E), ref) < BF16_TOL
+
+
+def test_gemm_tc_rejects_and_errors(vb):
+    a = torch.randn(16, 10, device="cuda").bfloat16()       # K=10 -> 20-byte pitch: not TMA-able
+    w = torch.randn(32, 10, device="cuda").bfloat16()
+    with pytest.raises(vb.lib.VitganError, match="unsupported"):
+        vb.ops.gemm(a, w, path=vb.lib.GEMM_TCGEN05)
+    vb.ops.gemm(a, w)   # AUTO falls to the library's own CUDA-core kernel, never to torch/CPU
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        vb.ops.gemm(a.cpu(), w.cpu())
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("rows,E", [(33, 32), (130, 128), (65 * 4, 432), (50, 768)])
+def test_layernorm(vb, dt, tol, rows, E):
+    g = gen(rows + E)
+    x = (torch.randn(rows, E, generator=g) * 2 + 0.5).to(dt)
+    gam, bet = torch.randn(E, generator=g), torch.randn(E, generator=g)
+    dy = torch.randn(rows, E, generator=g).to(dt)
+    dres = torch.randn(rows, E, generator=g).to(dt)
+    xr = x.float().requires_grad_(True); gr = gam.clone().requires_grad_(True); br = bet.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (E,), gr, br, 1e-5)
+    yr.backward(dy.float())
+    y, mean, rstd = vb.ops.layernorm_fwd(x.cuda(), gam.cuda(), bet.cuda())
+    assert rel(y, yr) < tol
+    assert rel(mean, x.float().mean(1)) < 1e-5
+    dx, dg, db = vb.ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dres=dres.cuda())
+    assert rel(dx, xr.grad + dres.float()) < tol
+    assert rel(dg, gr.grad) < max(tol, 1e-4) and rel(db, br.grad) < max(tol, 1e-4)
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("bcast", [False, True])
+def test_sln(vb, dt, tol, bcast):
+    g = gen(9)
+    B, S, Fd = 3, 10, 384
+    h = torch.randn((S, Fd) if bcast else (B, S, Fd), generator=g).to(dt)
+    w = torch.randn(B, S, Fd, generator=g).to(dt)
+    p = {"layer_norm.weight": torch.randn(Fd, generator=g), "layer_norm.bias": torch.randn(Fd, generator=g),
+         "gamma": torch.randn(1, 1, 1, generator=g), "beta": torch.randn(1, 1, 1, generator=g)}
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    hr, wr = h.float().requires_grad_(True), w.float().requires_grad_(True)
+    yr = o1.sln(p, "", hr, wr)
+    dy = torch.randn(B, S, Fd, generator=g).to(dt)
+    yr.backward(dy.float())
+    c = lambda t: t.detach().cuda()
+    y, mean, rstd = vb.ops.sln_fwd(c(h).reshape(-1, Fd), c(w).reshape(-1, Fd), c(p["layer_norm.weight"]), c(p["layer_norm.bias"]),
+                                   c(p["gamma"]).reshape(1), c(p["beta"]).reshape(1))
+    assert rel(y, yr.reshape(-1, Fd)) < tol
+    dh, dw, dgs, dbs, dlg, dlb = vb.ops.sln_bwd(c(dy).reshape(-1, Fd), c(h).reshape(-1, Fd), c(w).reshape(-1, Fd), mean, rstd,
+                                                c(p["layer_norm.weight"]), c(p["layer_norm.bias"]), c(p["gamma"]).reshape(1),
+                                                c(p["beta"]).reshape(1))
+    assert rel(dh, hr.grad.reshape(-1, Fd)) < tol and rel(dw, wr.grad.reshape(-1, Fd)) < tol
+    t2 = max(tol, 2e-4)
+    assert rel(dgs, p["gamma"].grad.reshape(1)) < t2 and rel(dbs, p["beta"].grad.reshape(1)) < t2
+    assert rel(dlg, p["layer_norm.weight"].grad) < t2 and rel(dlb, p["layer_norm.bias"].grad) < t2
+
+
+def attn_ref(q, k, v, scale, mode):
+    # q,k,v: (B,H,S,d) fp32
+    if mode == 1:
+        s = torch.cdist(q, k, p=2)       # S > 25 -> matmul path, same as the reference
+    else:
+        s = q @ k.transpose(-1, -2)
+    return torch.softmax(s * scale, -1) @ v
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("B,H,S,d", [(3, 4, 65, 32), (2, 4, 65, 108), (2, 4, 64, 96), (1, 2, 257, 192), (2, 2, 30, 12)])
+def test_attention(vb, dt, tol, mode, B, H, S, d):
+    g = gen(S + d + mode)
+    hd = H * d
+    qkv = (torch.randn(B * S, 3 * hd, generator=g) * (1.0 if mode else 0.7)).to(dt)
+    d_o = torch.randn(B * S, hd, generator=g).to(dt)
+    scale = 1.0 / math.sqrt(d if mode == 0 else hd)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = [ref_in[:, i * hd:(i + 1) * hd].reshape(B, S, H, d).permute(0, 2, 1, 3) for i in range(3)]
+    oref = attn_ref(q, k, v, scale, mode).permute(0, 2, 1, 3).reshape(B * S, hd)
+    oref.backward(d_o.float())
+    qc = qkv.cuda()
+    o, lse = vb.ops.attention_fwd(qc[:, :hd], qc[:, hd:2 * hd], qc[:, 2 * hd:], B, H, S, d, scale, mode)
+    assert rel(o, oref) < tol
+    # backward consumes the GPU forward's own (rounded) o / lse, like the real pipeline
+    dqkv = vb.ops.attention_bwd(qc[:, :hd], qc[:, hd:2 * hd], qc[:, 2 * hd:], o, d_o.cuda(), lse, B, H, S, d, scale, mode)
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, i * hd:(i + 1) * hd], ref_in.grad[:, i * hd:(i + 1) * hd]) < tol, name
+
+
+def test_attention_l2_zero_distance_is_finite(vb):
+    """q == k rows give dist = 0 on the diagonal: gradients must stay finite (guarded 1/dist), SURVEY Q6."""
+    B, H, S, d = 1, 1, 40, 16
+    x = torch.randn(B * S, d, generator=gen(1)).cuda()
+    qkv = torch.cat([x, x, x], 1).contiguous()
+    o, lse = vb.ops.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, S, d, 0.25, 1)
+    dqkv = vb.ops.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, torch.ones_like(o), lse, B, H, S, d, 0.25, 1)
+    assert torch.isfinite(o).all() and torch.isfinite(dqkv).all()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_patch_gathers(vb, dt):
+    g = gen(2)
+    B, C, I, P = 3, 3, 32, 4
+    img = torch.randn(B, C, I, I, generator=g)
+    ref = F.unfold(img, kernel_size=P, stride=P).transpose(1, 2).reshape(B * (I // P) ** 2, C * P * P)
+    out = vb.ops.im2col(img.cuda(), P, dt)
+    assert torch.equal(out.float().cpu(), ref.to(dt).float())            # pure data movement: bit exact
+    back = vb.ops.col2im(out, B, C, I, P)
+    assert torch.equal(back.cpu(), img.to(dt).float())
+    # v1 scrambled tokens against the oracle restatement of patch_encoder.py:54-73, 32 and 64 px
+    for I in (32, 64):
+        cfg = o1.V1Config(image_size=I)
+        n = int(round(math.sqrt(cfg.number_of_tokens)))
+        img = torch.randn(2, 3, I, I, generator=g)
+        tok = vb.ops.v1_tokens_fwd(img.cuda(), cfg.window, cfg.stride, n, dt)
+        ref = o1.get_tokens(img, cfg).reshape(-1, cfg.token_size)
+        assert torch.equal(tok.float().cpu(), ref.to(dt).float())
+        # adjoint check: <gather(x), y> == <x, scatter(y)>
+        y = torch.randn(ref.shape, generator=g)
+        imgr = img.clone().requires_grad_(True)
+        (o1.get_tokens(imgr, cfg).reshape(-1, cfg.token_size) * y).sum().backward()
+        dimg = vb.ops.v1_tokens_bwd(y.to(dt).cuda(), 2, 3, I, cfg.window, cfg.stride, n)
+        assert rel(dimg, imgr.grad) < (1e-5 if dt == torch.float32 else BF16_TOL)
+
+
+def test_embed_split_colsum_fill(vb):
+    g = gen(4)
+    B, S, E = 5, 17, 64
+    dx = torch.randn(B, S, E, generator=g)
+    for has_cls in (False, True):
+        dtok, dcls, dpos = vb.ops.embed_bwd_split(dx.cuda(), has_cls)
+        assert torch.equal(dtok.cpu().view(B, S - 1, E), dx[:, 1:])
+        assert rel(dcls, dx[:, 0].sum(0)) < 1e-6
+        assert rel(dpos, dx.sum(0) if has_cls else dx[:, 1:].sum(0)) < 1e-6
+    x = torch.randn(1000, 200, generator=g)
+    assert rel(vb.ops.colsum(x.cuda()), x.sum(0)) < 1e-5
+    assert rel(vb.ops.colsum(x.bfloat16().cuda()), x.bfloat16().float().sum(0)) < 1e-5
+    t = torch.zeros(B, S, E, device="cuda")
+    v, v2 = torch.randn(E, generator=g), torch.randn(E, generator=g)
+    vb.ops.fill_rows(t, 0, v.cuda(), v2.cuda())
+    assert torch.equal(t[:, 0].cpu(), (v + v2).expand(B, E)) and t[:, 1:].abs().sum() == 0
+
+
+def test_sigma_max_power_iteration(vb):
+    """vs the reference's full SVD (attention.py:54-58) on v1-discriminator-shaped weights."""
+    g = gen(6)
+    mats = [(torch.rand(108, 432, generator=g) * 2 - 1) / math.sqrt(432) for _ in range(12)]
+    dev = [m.cuda() for m in mats]
+    ptrs = torch.tensor([m.data_ptr() for m in dev], dtype=torch.int64).cuda()
+    u = torch.zeros(12, 108, device="cuda")
+    s_cold = vb.ops.sigma_max(ptrs, 12, 108, 432, u, 400)
+    ref = torch.stack([torch.linalg.svdvals(m).max() for m in mats])
+    assert rel(s_cold, ref) < 1e-4
+    s_warm = vb.ops.sigma_max(ptrs, 12, 108, 432, u, 4)        # persistent vector: already converged
+    assert rel(s_warm, s_cold) < 1e-6
+    # a matrix too large for shared memory takes the global-memory variant
+    big = torch.randn(300, 400, generator=g)
+    bp = torch.tensor([big.cuda().data_ptr()], dtype=torch.int64).cuda()
+    bigc = big.cuda()
+    bp = torch.tensor([bigc.data_ptr()], dtype=torch.int64).cuda()
+    sb = vb.ops.sigma_max(bp, 1, 300, 400, torch.zeros(1, 300, device="cuda"), 600)
+    assert rel(sb, torch.linalg.svdvals(big).max().reshape(1)) < 1e-3
+
+
+@pytest.mark.parametrize("decoupled,wd,betas", [(True, 1e-3, (0.9, 0.999)), (False, 0.0, (0.5, 0.999))])
+def test_fused_adam_matches_torch(vb, decoupled, wd, betas):
+    g = gen(8)
+    p0 = torch.randn(10007, generator=g)
+    pr = p0.clone().requires_grad_(True)
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([pr], lr=5e-4, betas=betas, weight_decay=wd)
+    p = p0.cuda(); m = torch.zeros_like(p); v = torch.zeros_like(p); cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(5):
+        gr = torch.randn(10007, generator=g)
+        pr.grad = gr.clone()
+        opt.step()
+        vb.ops.adam_step(p, gr.cuda(), m, v, cnt, 5e-4, betas[0], betas[1], 1e-8, wd, decoupled)
+    assert int(cnt.item()) == 5 and rel(p, pr) < 1e-6
+
+
+def test_cast_scale_and_act_backward(vb):
+    g = gen(10)
+    x = torch.randn(1001, generator=g)
+    num, den = torch.tensor([3.0]).cuda(), torch.tensor([4.0]).cuda()
+    assert rel(vb.ops.cast(x.cuda(), torch.bfloat16, num=num, den=den), (x * 0.75).bfloat16().float()) < 4e-3
+    assert torch.equal(vb.ops.cast(x.cuda(), torch.bfloat16).cpu(), x.bfloat16())
+    dy, aux = torch.randn(64, 33, generator=g), torch.rand(64, 33, generator=g)
+    for act, prm in ((1, 0.0), (2, 0.0), (3, 30.0), (4, 0.0)):
+        out = vb.ops.act_backward(dy.cuda(), aux.cuda(), act, prm)
+        assert rel(out, act_ref(act + 4, dy, aux, prm)) < 1e-5

@@ -132,6 +132,7 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5):
 
 
 def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None):
+    _req(x2d, "x2d")
     rows, e = x2d.shape
     dx = torch.empty_like(x2d)
     dgb = torch.zeros(2, e, dtype=torch.float32, device=x2d.device)
@@ -143,6 +144,7 @@ def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None):
 
 
 def sln_fwd(h2d, w2d, ln_g, ln_b, gamma_s, beta_s, eps=1e-5):
+    _req(w2d, "w2d")
     rows, f = w2d.shape
     y = torch.empty_like(w2d)
     mean = torch.empty(rows, dtype=torch.float32, device=w2d.device)
@@ -155,6 +157,7 @@ def sln_fwd(h2d, w2d, ln_g, ln_b, gamma_s, beta_s, eps=1e-5):
 
 
 def sln_bwd(dy2d, h2d, w2d, mean, rstd, ln_g, ln_b, gamma_s, beta_s, dh_res=None, dw_res=None):
+    _req(w2d, "w2d")
     rows, f = w2d.shape
     h_rows = h2d.shape[0]
     bcast = h_rows < rows
@@ -171,6 +174,7 @@ def sln_bwd(dy2d, h2d, w2d, mean, rstd, ln_g, ln_b, gamma_s, beta_s, dh_res=None
 
 def attention_fwd(q, k, v, B, H, S, d, scale, mode=L.ATTN_DOT, ld_qkv=None, out=None):
     """q,k,v: 2-D row-major views [B*S, >=H*d] sharing the leading dim (slices of a fused projection output)."""
+    _req(q, "q")
     ld = ld_qkv or q.stride(0)
     if out is None:
         out = torch.empty(B * S, H * d, dtype=q.dtype, device=q.device)
@@ -183,6 +187,7 @@ def attention_fwd(q, k, v, B, H, S, d, scale, mode=L.ATTN_DOT, ld_qkv=None, out=
 
 def attention_bwd(q, k, v, o, d_o, lse, B, H, S, d, scale, mode=L.ATTN_DOT, dqkv=None):
     """Returns dqkv [B*S, 3*H*d] laid out like a fused projection output (dq | dk | dv)."""
+    _req(q, "q")
     hd = H * d
     if dqkv is None:
         dqkv = torch.empty(B * S, 3 * hd, dtype=q.dtype, device=q.device)
@@ -206,6 +211,7 @@ def im2col(img: torch.Tensor, P: int, dtype: torch.dtype):
 
 
 def col2im(dpatches: torch.Tensor, B, Cc, I, P):
+    _req(dpatches, "dpatches")
     dimg = torch.empty(B, Cc, I, I, dtype=torch.float32, device=dpatches.device)
     check(lib.vg_col2im_patches(dt(dpatches), B, Cc, I, P, dpatches.data_ptr(), dimg.data_ptr(), stream()), "vg_col2im_patches")
     _count()
@@ -213,6 +219,7 @@ def col2im(dpatches: torch.Tensor, B, Cc, I, P):
 
 
 def v1_tokens_fwd(img, win, stride, n_side, dtype):
+    _req(img, "img")
     B, Cc, I, _ = img.shape
     img = img.contiguous().float()
     out = torch.empty(B * n_side * n_side, Cc * win * win, dtype=dtype, device=img.device)
@@ -222,6 +229,7 @@ def v1_tokens_fwd(img, win, stride, n_side, dtype):
 
 
 def v1_tokens_bwd(dtokens, B, Cc, I, win, stride, n_side):
+    _req(dtokens, "dtokens")
     dimg = torch.zeros(B, Cc, I, I, dtype=torch.float32, device=dtokens.device)
     check(lib.vg_v1_tokens_bwd(dt(dtokens), B, Cc, I, win, stride, n_side, dtokens.data_ptr(), dimg.data_ptr(), stream()), "vg_v1_tokens_bwd")
     _count()
@@ -229,12 +237,14 @@ def v1_tokens_bwd(dtokens, B, Cc, I, win, stride, n_side):
 
 
 def fill_rows(x3d, row, v, v2=None):
+    _req(x3d, "x3d")
     B, S, E = x3d.shape
     check(lib.vg_fill_rows(dt(x3d), B, S, E, row, v.data_ptr(), _ptr(v2), x3d.data_ptr(), stream()), "vg_fill_rows")
     _count()
 
 
 def embed_bwd_split(dx3d, pos_has_cls: bool):
+    _req(dx3d, "dx3d")
     B, S, E = dx3d.shape
     dtok = torch.empty(B * (S - 1), E, dtype=dx3d.dtype, device=dx3d.device)
     dcls = torch.zeros(E, dtype=torch.float32, device=dx3d.device)
@@ -246,11 +256,13 @@ def embed_bwd_split(dx3d, pos_has_cls: bool):
 
 
 def copy_rows(src, ld_src, rows, cols, dst, ld_dst):
+    _req(src, "src")
     check(lib.vg_copy_rows(dt(src), rows, cols, src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, stream()), "vg_copy_rows")
     _count()
 
 
 def act_backward(dy, aux, act, act_param=0.0):
+    _req(dy, "dy")
     if dy.dtype != aux.dtype:
         raise TypeError("vitgan_b200.act_backward: dy/aux dtypes differ")
     out = torch.empty_like(dy)
@@ -261,12 +273,14 @@ def act_backward(dy, aux, act, act_param=0.0):
 
 
 def add_(x, y):
+    _req(x, "x")
     check(lib.vg_add_inplace(dt(x), x.data_ptr(), y.data_ptr(), x.numel(), stream()), "vg_add_inplace")
     _count()
     return x
 
 
 def broadcast_rows(src2d, reps):
+    _req(src2d, "src2d")
     out = torch.empty(reps * src2d.shape[0], src2d.shape[1], dtype=src2d.dtype, device=src2d.device)
     check(lib.vg_broadcast_rows(dt(src2d), src2d.data_ptr(), src2d.shape[0], src2d.shape[1], out.data_ptr(), reps, stream()),
           "vg_broadcast_rows")
