@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- GAN training images/s for one full G+D step (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W                       (this repo's CUDA path)
+  python bench.py --impl reference --gpus N --steps K --warmup W      (reference algorithm on the host CPU cores)
+
+Default workload = BASELINE.json configs[1] ("c2"): main-v2.py default ViT-GAN, 32x32 RGB, batch 512 per GPU, bf16.
+Other workloads: c1 (v2 defaults B=64 fp32), c3 (v1 SLN-G / L2-spectral-D at 64x64, 128 per GPU), c4 (scaled v2
+128x128 patch 8 dim 768 depth 12, global batch 2048 strong-scaled), c5 (generator-only sampling, B=4096).
+
+One JSON line on stdout (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
+step driven from pinned HOST buffers (H2D of real+noise and D2H of the three losses inside the timed region);
+`roofline` = the dominant kernel timed alone with CUDA events; `cpu_baseline` = the oracle on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a whole-step CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW instead of the fused flat Adam kernel")
+    ap.add_argument("--keep-unused-d-grads", action="store_true",
+                    help="also compute D's parameter gradients in the G pass (the reference computes, then discards them)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def workload_spec(name, n_gpus, batch_override):
+    """-> dict(kind, per_gpu_batch, global_batch, scaling, precision, cfg kwargs, description)."""
+    if name in ("c1", "c2", "c5"):
+        pb = {"c1": 64, "c2": 512, "c5": 4096}[name]
+        spec = dict(kind="v2" if name != "c5" else "v2_sample", over={}, scaling="weak", precision="fp32" if name == "c1" else "bf16",
+                    desc={"c1": "main-v2 default ViT-GAN 32x32, B=64/GPU, fp32 parity path",
+                          "c2": "main-v2 default ViT-GAN 32x32 RGB (E128 L6 H4 P4 S65), B=512/GPU, bf16",
+                          "c5": "v2 generator-only sampling (eval), B=4096/GPU, bf16"}[name])
+    elif name == "c4":
+        pb = 2048 // n_gpus
+        spec = dict(kind="v2", over=dict(image_size=128, patch_size=8, embeddings_dimension=768, transformer_blocks_count=12),
+                    scaling="strong", precision="bf16", desc="scaled ViT-GAN 128x128 P8 E768 L12 (H4 m2), global batch 2048, bf16")
+    else:
+        pb = 128
+        spec = dict(kind="v1", over=dict(image_size=64), scaling="weak", precision="bf16",
+                    desc="main-v1 ViTGAN variant (SLN generator, L2-attention spectral discriminator) 64x64, B=128/GPU, bf16")
+    if batch_override:
+        pb = batch_override
+    spec.update(per_gpu_batch=pb, global_batch=pb * n_gpus, name=name)
+    return spec
+
+
+def step_flops_per_image(spec, skip_unused):
+    """Algorithmic FLOPs per image of one G+D step: 9 F_D + 3 F_G, or 8 F_D + 3 F_G when the
+    discarded D weight gradients of the third pass are not computed (their FLOPs leave the numerator too)."""
+    from oracle import v1 as o1, v2 as o2
+    if spec["kind"].startswith("v2"):
+        cfg = o2.V2Config(**spec["over"])
+        fd, fg = o2.flops_per_image_fwd(cfg, False), o2.flops_per_image_fwd(cfg, True)
+    else:
+        cfg = o1.V1Config(**spec["over"])
+        fd, fg = o1.flops_per_image_fwd(cfg, False), o1.flops_per_image_fwd(cfg, True)
+    if spec["kind"] == "v2_sample":
+        return fg
+    return (8 if skip_unused else 9) * fd + 3 * fg
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def cpu_oracle_rate(spec, seconds_budget, steps, warmup):
+    """Time the oracle (CPU restatement of the reference, bit-exact to it: tests/test_oracle_vs_reference.py) on a
+    bounded sample of the workload: same model/config, per-step batch shrunk so the run fits the time budget."""
+    from oracle import harness, v1 as o1, v2 as o2
+    torch.set_num_threads(os.cpu_count() or 1)
+    if spec["kind"].startswith("v2"):
+        cfg = o2.V2Config(**spec["over"], batch_size=3 * spec["over"].get("image_size", 32) ** 2)
+        orc = harness.OracleV2(cfg, seed=0)
+        mk = lambda b, n: harness.synthetic_batches_v2(cfg, b, n)
+    else:
+        cfg = o1.V1Config(**spec["over"])
+        orc = harness.OracleV1(cfg, seed=0)
+        mk = lambda b, n: harness.synthetic_batches_v1(cfg, b, n)
+    if spec["kind"] == "v2_sample":
+        run = lambda r, n: orc.generator(n)
+    else:
+        run = lambda r, n: orc.step(r, n)
+    # calibrate on a small batch, then pick the batch that fits the budget
+    probe = 8
+    (r, n), = mk(probe, 1)
+    with torch.no_grad() if spec["kind"] == "v2_sample" else torch.enable_grad():
+        t0 = time.perf_counter(); run(r, n); t1 = time.perf_counter()
+        per_img = (t1 - t0) / probe
+        b = int(max(probe, min(spec["per_gpu_batch"], seconds_budget / max(per_img, 1e-9) / (steps + warmup))))
+        data = mk(b, steps + warmup)
+        for r, n in data[:warmup]:
+            run(r, n)
+        t0 = time.perf_counter()
+        for r, n in data[warmup:]:
+            run(r, n)
+        dt = time.perf_counter() - t0
+    return dict(value=b * steps / dt, batch=b, steps=steps, ms_per_step=1e3 * dt / steps, cores=torch.get_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = workload_spec(args.workload, args.gpus, args.batch)
+    res = cpu_oracle_rate(spec, seconds_budget=150.0, steps=args.steps, warmup=args.warmup)
+    unit = "samples/s" if spec["kind"] == "v2_sample" else "img/s"
+    sample = f"oracle CPU port (bit-exact to the reference modules), same model, per-step batch {res['batch']} instead of {spec['per_gpu_batch']}"
+    line = {
+        "impl": "reference", "metric": "gan_train_images_per_sec" if unit == "img/s" else "generator_samples_per_sec",
+        "value": res["value"], "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{spec['name']}: {spec['desc']}", "per_gpu_batch": spec["per_gpu_batch"], "cpu_sample_batch": res["batch"]},
+        "cpu_baseline": {"value": res["value"], "unit": unit, "cores": res["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": res["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ kernel roofline (dominant kernel, timed alone)
+def time_kernel(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()                         # > L2 (126 MB): next launch starts cold in L2
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        e.synchronize()
+        ts.append(s.elapsed_time(e))
+    return statistics.mean(ts)
+
+
+def kernel_rooflines(vb, spec, pk):
+    """Per-launch algorithmic FLOPs/bytes over the CUDA-event time of each hot kernel, at this workload's shapes."""
+    from oracle import v2 as o2
+    if not spec["kind"].startswith("v2"):
+        return None, []
+    cfg = o2.V2Config(**spec["over"])
+    B, S, E, H, m = spec["per_gpu_batch"], cfg.seq_len, cfg.embeddings_dimension, cfg.attention_heads_count, cfg.mlp_ratio
+    M, d = B * S, cfg.embeddings_dimension // cfg.attention_heads_count
+    dev = "cuda"
+    bf = torch.bfloat16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    x = torch.randn(M, E, device=dev).to(bf)
+    wqkv = torch.randn(3 * E, E, device=dev).to(bf)
+    bq = torch.randn(3 * E, device=dev)
+    qkv = torch.randn(M, 3 * E, device=dev).to(bf)
+    w1 = torch.randn(m * E, E, device=dev).to(bf)
+    b1 = torch.randn(m * E, device=dev)
+    out = []
+
+    def entry(name, fn, flops, bytes_, iters=20):
+        t = time_kernel(fn, iters, flush) * 1e-3
+        tf, gb = flops / t / 1e12, bytes_ / t / 1e9
+        bound = "tensor" if flops / bytes_ > pk["tf_burst"] * 1e3 / pk["hbm"] else "hbm"
+        out.append({"kernel": name, "bound": bound, "us": t * 1e6, "tflops": tf, "gbs": gb,
+                    "frac_tensor": tf / pk["tf_burst"], "frac_hbm": gb / pk["hbm"], "alg_flops": flops, "alg_bytes": bytes_})
+
+    L = vb.lib
+    entry("gemm_tc fwd qkv [M,E]x[E,3E]+bias", lambda: vb.ops.gemm(x, wqkv, bias=bq, path=L.GEMM_TCGEN05),
+          2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E))
+    entry("gemm_tc fwd fc1+gelu [M,E]x[E,mE]", lambda: vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05),
+          2.0 * M * m * E * E, 2.0 * (M * E + m * E * E + 2 * M * m * E))
+    entry("gemm_tc dgrad qkv [M,3E]x[3E,E]", lambda: vb.ops.gemm(qkv, wqkv, trans_b=False, path=L.GEMM_TCGEN05),
+          2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + 3 * E * E + M * E))
+    entry("gemm_tc wgrad qkv [3E,M]x[M,E] split-K", lambda: vb.ops.gemm(qkv, x, trans_a=True, trans_b=False, accumulate=True, path=L.GEMM_TCGEN05),
+          2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + M * E) + 4.0 * 3 * E * E)
+    hd = E
+    scale = d ** -0.5
+    o, lse = vb.ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale)
+    entry("attention fwd (flash, CUDA cores)", lambda: vb.ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale),
+          4.0 * B * H * S * S * d, 2.0 * (4 * M * E), iters=5)
+    entry("attention bwd (flash, CUDA cores)", lambda: vb.ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, o, lse, B, H, S, d, scale),
+          8.0 * B * H * S * S * d, 2.0 * (8 * M * E), iters=5)
+    g, b_ = torch.ones(E, device=dev), torch.zeros(E, device=dev)
+    entry("layernorm fwd", lambda: vb.ops.layernorm_fwd(x, g, b_), 8.0 * M * E, 2.0 * 2 * M * E)
+    del flush
+    dom = out[0]
+    key = "frac_tensor" if dom["bound"] == "tensor" else "frac_hbm"
+    roof = {"kernel": dom["kernel"], "bound": dom["bound"],
+            "achieved": dom["tflops"] if dom["bound"] == "tensor" else dom["gbs"],
+            "peak": pk["tf_burst"] if dom["bound"] == "tensor" else pk["hbm"],
+            "unit": "TFLOP/s" if dom["bound"] == "tensor" else "GB/s", "frac": dom[key], "traffic": None,
+            "peak_source": pk["src"], "us_per_launch": dom["us"]}
+    return roof, out
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import vitgan_b200 as vb
+    from oracle import harness, v1 as o1, v2 as o2      # synthetic data generator + FLOP formulas + cpu_baseline leg only
+
+    spec = workload_spec(args.workload, world, args.batch)
+    prec = args.precision or spec["precision"]
+    vb.set_precision(prec)
+    pk = peaks()
+    B = spec["per_gpu_batch"]
+    skip_unused = not args.keep_unused_d_grads
+    torch.manual_seed(0)
+    if spec["kind"].startswith("v2"):
+        I = spec["over"].get("image_size", 32)
+        cfg = vb.v2.Config(**spec["over"], batch_size=3 * I * I)
+        gan = vb.v2.ViTGAN(cfg).cuda()
+        gen, disc, loss_kind = gan.generator, gan.discriminator, "ce"
+        ocfg = o2.V2Config(**spec["over"], batch_size=3 * I * I)
+        mk = lambda n, seed: harness.synthetic_batches_v2(ocfg, B, n, seed=seed)
+        opt = lambda net: vb.train.FusedAdam(net, 5e-4, weight_decay=1e-3, decoupled=True)
+        topt = lambda ps: torch.optim.AdamW(ps, lr=5e-4, weight_decay=1e-3, capturable=True)
+    else:
+        I = spec["over"]["image_size"]
+        gen = vb.v1.Generator(vb.v1.V1Config(**spec["over"])).cuda()
+        disc = vb.v1.Discriminator(vb.v1.V1Config(**spec["over"])).cuda()
+        loss_kind = "bce"
+        ocfg = o1.V1Config(**spec["over"])
+        mk = lambda n, seed: harness.synthetic_batches_v1(ocfg, B, n, seed=seed)
+        opt = lambda net: vb.train.FusedAdam(net, 2e-4, betas=(0.5, 0.999))
+        topt = lambda ps: torch.optim.Adam(ps, lr=2e-4, betas=(0.5, 0.999), capturable=True)
+
+    n_data = 4
+    host = [(r.pin_memory(), n.pin_memory()) for r, n in mk(n_data, 1234 + rank)]     # each rank its own shard of the global batch
+    devb = [(r.cuda(), n.cuda()) for r, n in host]
+    unit = "img/s"
+
+    if spec["kind"] == "v2_sample":
+        unit = "samples/s"
+        gen.eval()
+
+        def one(real, noise):
+            with torch.no_grad():
+                return (gen(noise).mean(),)
+        d_b = g_b = None
+        step_fn = one
+        graph_used = False
+    else:
+        frozen = (lambda n, p: n.endswith((".q.weight", ".k.weight", ".v.weight"))) if spec["kind"] == "v1" else None
+        if args.torch_optim:
+            gopt = topt(list(gen.parameters()))
+            dopt = topt([p for n, p in disc.named_parameters() if not (frozen and frozen(n, p))])
+            d_b = g_b = None
+            assert world == 1, "--torch-optim is a single-GPU diagnostic"
+        else:
+            gnet, dnet = vb.train.FlatNet(gen), vb.train.FlatNet(disc, exclude=frozen)
+            gopt, dopt = opt(gnet), opt(dnet)
+            d_b = g_b = None
+            if world > 1:
+                d_b = vb.train.GradBuckets(dnet, n_buckets=2, average_in_place=False)
+                g_b = vb.train.GradBuckets(gnet, n_buckets=2, average_in_place=False)
+                gopt.grad_scale = dopt.grad_scale = 1.0 / world
+
+        def eager(real, noise):
+            return vb.train.gan_step(gen, disc, gopt, dopt, real, noise, loss_kind, d_buckets=d_b, g_buckets=g_b,
+                                     skip_unused_d_grads=skip_unused)
+        # launches per step, counted on one eager step (the graph replays exactly these)
+        eager(*devb[0])
+        torch.cuda.synchronize()
+        vb.ops.launch_count = 0
+        eager(*devb[1])
+        torch.cuda.synchronize()
+        launches_per_step = vb.ops.launch_count
+        step_fn, graph_used = eager, False
+        if not args.no_graph:
+            try:
+                gs = vb.train.GraphedStep(gen, disc, gopt, dopt, devb[0][0], devb[0][1], loss_kind, warmup=2, d_buckets=d_b,
+                                          g_buckets=g_b, skip_unused_d_grads=skip_unused)
+                step_fn, graph_used = gs, True
+            except Exception as ex:      # fall back to eager launches of the same kernels (never to another implementation)
+                if rank == 0:
+                    print(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {ex}); running eager", file=sys.stderr)
+                torch.cuda.synchronize()
+                vb.set_operand_cache(True)
+    if spec["kind"] == "v2_sample":
+        vb.ops.launch_count = 0
+        step_fn(*devb[0]); torch.cuda.synchronize()
+        launches_per_step = vb.ops.launch_count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(n_steps, from_host):
+        total_ms = 0.0
+        last = None
+        for i in range(n_steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if from_host:
+                hr, hn = host[i % n_data]
+                real, noise = hr.cuda(non_blocking=True), hn.cuda(non_blocking=True)
+                last = step_fn(real, noise)
+                vals = torch.stack([t.float().reshape(()) for t in last]).cpu()      # D2H read of the step's result
+            else:
+                last = step_fn(*devb[i % n_data])
+            e.record()
+            e.synchronize()
+            total_ms += s.elapsed_time(e)
+        return total_ms, last
+
+    # ---- warm-up, then the device-resident timed region
+    timed(max(args.warmup, 3), False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    ms, last = timed(args.steps, False)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    # ---- end to end: pinned host buffers in, losses out, every step
+    timed(2, True)
+    barrier()
+    ms_e2e, last_e2e = timed(args.steps, True)
+    barrier()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    losses = [float(x) for x in torch.stack([v.float().reshape(()) for v in last]).cpu()]
+    finite = all(x == x and abs(x) != float("inf") for x in losses)
+
+    if rank == 0:
+        imgs = spec["global_batch"] * args.steps
+        value, e2e_value = imgs / (ms * 1e-3), imgs / (ms_e2e * 1e-3)
+        fl = step_flops_per_image(spec, skip_unused)
+        step_tf = value * fl / world / 1e12          # per GPU
+        roof, all_k = kernel_rooflines(vb, spec, pk) if world == 1 else (None, [])
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_oracle_rate(spec, seconds_budget=25.0, steps=2, warmup=1)
+            cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
+                   "sample": f"oracle CPU port of the reference step, same model, batch {r['batch']}, {r['steps']} timed steps"}
+        h2d = sum(x.numel() * x.element_size() for x in host[0])
+        line = {
+            "metric": "gan_train_images_per_sec" if unit == "img/s" else "generator_samples_per_sec",
+            "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
+            "dtype": prec, "data": "synthetic",
+            "config": {"workload": f"{spec['name']}: {spec['desc']}", "per_gpu_batch": B, "global_batch": spec["global_batch"],
+                       "parallelism": f"dp{world}", "cuda_graph": graph_used, "optimizer": "torch" if args.torch_optim else "fused flat Adam(W) kernel",
+                       "d_param_grads_in_g_pass": not skip_unused,
+                       "l2": "192 MiB buffer written between timed steps (L2 flush); step working set is >1 GB anyway"},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(last_e2e),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "clocks": clocks, "wall_s_timed_region": t_wall, "losses_last_step": losses, "losses_finite": finite,
+            "step_flops_per_image": fl, "step_tflops_per_gpu": step_tf, "step_frac_of_bf16_sustained": step_tf / pk["tf_sust"],
+            "peaks": pk, "roofline": roof, "kernels": all_k, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
