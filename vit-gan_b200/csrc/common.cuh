@@ -97,6 +97,37 @@ __device__ __forceinline__ float apply_act(int act, float v, float a, float prm)
     default: return v;
   }
 }
+// compile-time activation; FAST selects hardware approximations (bf16 tensor-core path, 2e-2 tolerance),
+// otherwise the accurate libdevice functions (fp32 parity path, 1e-4 tolerance)
+template <int ACT, bool FAST>
+__device__ __forceinline__ float act_t(float v, float a, float prm) {
+  if (ACT == VG_ACT_GELU) return gelu_erf(v);
+  if (ACT == VG_ACT_TANH) {
+    if (FAST) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v)); return t; }
+    return tanhf(v);
+  }
+  if (ACT == VG_ACT_SIN) return FAST ? __sinf(prm * v) : sinf(prm * v);
+  if (ACT == VG_ACT_SIGMOID) return FAST ? __fdividef(1.0f, 1.0f + __expf(-v)) : 1.0f / (1.0f + expf(-v));
+  if (ACT == VG_ACT_MUL_DGELU) return v * dgelu_erf(a);
+  if (ACT == VG_ACT_MUL_DTANH) return v * (1.0f - a * a);
+  if (ACT == VG_ACT_MUL_DSIN) return v * prm * (FAST ? __cosf(prm * a) : cosf(prm * a));
+  if (ACT == VG_ACT_MUL_DSIGMOID) return v * a * (1.0f - a);
+  return v;
+}
+// run `body.template operator()<ACT>()` for the runtime activation code (one switch per tile, not per element)
+#define VG_ACT_SWITCH(act, CALL)                                   \
+  switch (act) {                                                   \
+    case VG_ACT_GELU: { constexpr int ACT = VG_ACT_GELU; CALL; } break;                 \
+    case VG_ACT_TANH: { constexpr int ACT = VG_ACT_TANH; CALL; } break;                 \
+    case VG_ACT_SIN: { constexpr int ACT = VG_ACT_SIN; CALL; } break;                   \
+    case VG_ACT_SIGMOID: { constexpr int ACT = VG_ACT_SIGMOID; CALL; } break;           \
+    case VG_ACT_MUL_DGELU: { constexpr int ACT = VG_ACT_MUL_DGELU; CALL; } break;       \
+    case VG_ACT_MUL_DTANH: { constexpr int ACT = VG_ACT_MUL_DTANH; CALL; } break;       \
+    case VG_ACT_MUL_DSIN: { constexpr int ACT = VG_ACT_MUL_DSIN; CALL; } break;         \
+    case VG_ACT_MUL_DSIGMOID: { constexpr int ACT = VG_ACT_MUL_DSIGMOID; CALL; } break; \
+    default: { constexpr int ACT = VG_ACT_NONE; CALL; } break;                          \
+  }
+
 __host__ __device__ __forceinline__ bool act_needs_aux(int act) { return act >= VG_ACT_MUL_DGELU; }
 
 // row remaps of the GEMM epilogue (see vg_gemm_args)

@@ -12,6 +12,42 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, NTHREADS = 256;
 
+template <typename TC, int ACT>
+__device__ __forceinline__ void simt_epilogue(const vg_gemm_args& g, const float (&acc)[TM][TN], int mbase, int nbase) {
+  TC* __restrict__ C = static_cast<TC*>(g.C);
+  const TC* __restrict__ aux = static_cast<const TC*>(g.aux);
+  const TC* __restrict__ res = static_cast<const TC*>(g.residual);
+  TC* __restrict__ cpre = static_cast<TC*>(g.c_pre);
+  const bool first_split = blockIdx.z == 0;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = mbase + i;
+    if (m >= g.M) continue;
+    const int64_t orow = out_row(m, g.c_row_group);
+    const int64_t rrow = res_row(m, g.res_row_mod, g.res_row_off);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = nbase + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.accumulate) {   // split-K partial sums: linear epilogue only (bias/residual added by split 0)
+        if (first_split) {
+          if (g.bias) v += g.bias[n];
+          if (res) v += to_f<TC>(res[rrow * g.ldres + n]);
+        }
+        atomicAdd(reinterpret_cast<float*>(C) + orow * g.ldc + n, v);
+      } else {
+        if (g.bias) v += g.bias[n];
+        if (cpre) cpre[(int64_t)m * g.ldpre + n] = from_f<TC>(v);
+        const float a = (aux != nullptr) ? to_f<TC>(aux[(int64_t)m * g.ldaux + n]) : 0.f;
+        v = act_t<ACT, false>(v, a, g.act_param);
+        if (res) v += to_f<TC>(res[rrow * g.ldres + n]);
+        C[orow * g.ldc + n] = from_f<TC>(v);
+      }
+    }
+  }
+}
+
 template <typename TAB, typename TC>
 __global__ void __launch_bounds__(NTHREADS)
 gemm_simt_kernel(vg_gemm_args g, int k_per_split) {
@@ -74,39 +110,8 @@ gemm_simt_kernel(vg_gemm_args g, int k_per_split) {
     __syncthreads();
   }
 
-  // ---- epilogue
-  TC* __restrict__ C = static_cast<TC*>(g.C);
-  const TC* __restrict__ aux = static_cast<const TC*>(g.aux);
-  const TC* __restrict__ res = static_cast<const TC*>(g.residual);
-  TC* __restrict__ cpre = static_cast<TC*>(g.c_pre);
-  const bool first_split = blockIdx.z == 0;
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int m = m0 + ty * TM + i;
-    if (m >= g.M) continue;
-    const int64_t orow = out_row(m, g.c_row_group);
-    const int64_t rrow = res_row(m, g.res_row_mod, g.res_row_off);
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = n0 + tx * TN + j;
-      if (n >= g.N) continue;
-      float v = acc[i][j];
-      if (g.accumulate) {   // split-K partial sums: linear epilogue only (bias/residual added by split 0)
-        if (first_split) {
-          if (g.bias) v += g.bias[n];
-          if (res) v += to_f<TC>(res[rrow * g.ldres + n]);
-        }
-        atomicAdd(reinterpret_cast<float*>(C) + orow * g.ldc + n, v);
-      } else {
-        if (g.bias) v += g.bias[n];
-        if (cpre) cpre[(int64_t)m * g.ldpre + n] = from_f<TC>(v);
-        const float a = (aux != nullptr) ? to_f<TC>(aux[(int64_t)m * g.ldaux + n]) : 0.f;
-        v = apply_act(g.act, v, a, g.act_param);
-        if (res) v += to_f<TC>(res[rrow * g.ldres + n]);
-        C[orow * g.ldc + n] = from_f<TC>(v);
-      }
-    }
-  }
+  // ---- epilogue (activation dispatched once per thread, element loops are branch-free)
+  VG_ACT_SWITCH(g.act, (simt_epilogue<TC, ACT>(g, acc, m0 + ty * TM, n0 + tx * TN)))
 }
 
 }  // namespace

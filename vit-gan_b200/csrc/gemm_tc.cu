@@ -23,13 +23,14 @@ namespace vg {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
-constexpr int NSTAGES = 6;
+constexpr int NSTAGES = 4;
 constexpr int NACC = 2;
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_BYTES = 8192;         // per epilogue warp: two 4 KB swizzled staging tiles (32 rows x 128 B each)
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int TMEM_COLS = NACC * BN;   // 256: power of two >= 32
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -66,6 +67,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -90,6 +116,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, sm_100 version 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -116,9 +154,11 @@ struct Params {
   int c_row_group, res_row_mod, res_row_off;
   int accumulate;
   uint32_t mn_lbo, mn_sbo, mn_kstep;   // MN-major smem descriptor geometry (debug-overridable, see gemm_tc_launch)
+  int dbg;                             // bring-up switches (VG_TC_DBG): 1 = epilogue skips global memory, 2 = force direct epilogue
+  int epi_tma;                         // 1: smem-staged epilogue with TMA loads (residual/aux) and TMA stores / reduce-add
 };
 
-template <typename TC>
+template <typename TC, int ACT>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&r)[32], int m, int n0) {
   // one thread = one output row m, 32 consecutive columns n0..n0+31
   const int64_t orow = out_row(m, p.c_row_group);
@@ -153,11 +193,11 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
     }
     if (vec_ok) {
       if (cpre) Vec4<TC>::store(cpre + c, v);
-      if (p.act != VG_ACT_NONE) {
+      if (ACT != VG_ACT_NONE) {
         float a[4] = {0.f, 0.f, 0.f, 0.f};
         if (aux) Vec4<TC>::load(aux + c, a);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = apply_act(p.act, v[j], a[j], p.act_param);
+        for (int j = 0; j < 4; ++j) v[j] = act_t<ACT, true>(v[j], a[j], p.act_param);
       }
       if (res) {
         float t[4];
@@ -173,7 +213,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
           float x = v[j];
           if (cpre) cpre[c + j] = from_f<TC>(x);
           const float a = aux ? to_f<TC>(aux[c + j]) : 0.f;
-          x = apply_act(p.act, x, a, p.act_param);
+          x = act_t<ACT, true>(x, a, p.act_param);
           if (res) x += to_f<TC>(res[c + j]);
           C[c + j] = from_f<TC>(x);
         }
@@ -182,17 +222,90 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
   }
 }
 
+// Staged epilogue, one 32-column chunk of one accumulator row per thread.
+//   bf16: the warp's 64 columns live in ONE 4 KB tile (32 rows x 128 B); chunk cc covers 16 B chunks 4cc..4cc+3
+//   fp32: chunk cc has its own 4 KB tile (32 rows x 32 fp32)
+// Tiles use the TMA 128B swizzle: 16 B chunk L of row r is stored at r*128 + ((L ^ (r & 7)) * 16)  (conflict-free).
+// bufC holds the residual tile on entry (if any) and the output on exit; bufX holds aux on entry or c_pre on exit.
+template <bool F32, int ACT>
+__device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r)[32], int lane, int cc, int n0,
+                                             uint32_t bufC, uint32_t bufX) {
+  const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+  const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
+  if (F32) {
+    const uint32_t base = (cc == 0 ? bufC : bufX) + row_off;      // fp32: second chunk uses the second tile
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[g * 4 + j]);
+      const uint32_t addr = base + (((uint32_t)g ^ sw) << 4);
+      if (!p.accumulate) {
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const int n = n0 + g * 4 + j; v[j] += (n < p.N) ? __ldg(p.bias + n) : 0.f; }
+        }
+        if (ACT != VG_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = act_t<ACT, true>(v[j], 0.f, p.act_param);
+        }
+        if (has_res) {
+          uint32_t a, b, c, d;
+          lds128(addr, a, b, c, d);
+          v[0] += __uint_as_float(a); v[1] += __uint_as_float(b); v[2] += __uint_as_float(c); v[3] += __uint_as_float(d);
+        }
+      }
+      sts128(addr, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {        // 8 columns -> one 16 B chunk
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
+      const uint32_t off = row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int n = n0 + h * 8 + j; v[j] += (n < p.N) ? __ldg(p.bias + n) : 0.f; }
+      }
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (has_aux) {
+        uint32_t x0, x1, x2, x3;
+        lds128(bufX + off, x0, x1, x2, x3);
+        a[0] = bf16_lo(x0); a[1] = bf16_hi(x0); a[2] = bf16_lo(x1); a[3] = bf16_hi(x1);
+        a[4] = bf16_lo(x2); a[5] = bf16_hi(x2); a[6] = bf16_lo(x3); a[7] = bf16_hi(x3);
+      }
+      if (has_pre) sts128(bufX + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      if (ACT != VG_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_t<ACT, true>(v[j], a[j], p.act_param);
+      }
+      if (has_res) {
+        uint32_t x0, x1, x2, x3;
+        lds128(bufC + off, x0, x1, x2, x3);
+        v[0] += bf16_lo(x0); v[1] += bf16_hi(x0); v[2] += bf16_lo(x1); v[3] += bf16_hi(x1);
+        v[4] += bf16_lo(x2); v[5] += bf16_hi(x2); v[6] += bf16_lo(x3); v[7] += bf16_hi(x3);
+      }
+      sts128(bufC + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
+               const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
   extern __shared__ uint8_t smem_dyn[];
   // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + NSTAGES * STAGE_BYTES;
+  const uint32_t stg_base = smem_base + NSTAGES * STAGE_BYTES;          // 1024-aligned (stage bytes are multiples of 1024)
+  const uint32_t bar_base = stg_base + EPI_WARPS * STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + NACC + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGES + 2 * NACC);
+  auto warp_bar = [&](int w) { return bar_base + 8u * (2 * NSTAGES + 2 * NACC + w); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGES + 2 * NACC + EPI_WARPS);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(warp_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // whole warp: allocate TMEM columns, publish base address through smem
@@ -285,26 +399,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access (warp id % 4)
     const int half = ew >> 2;              // which 64-column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const int m = m_blk * BM + quad * 32 + lane;
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 2; cc += 32) {
-        const int col = half * (BN / 2) + cc;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col), r);
-        const int n0 = n_blk * BN + col;
-        if (m < p.M && n0 < p.N) {
-          if (p.c_is_f32) epilogue_chunk<float>(p, r, m, n0);
-          else epilogue_chunk<bf16>(p, r, m, n0);
+    if (p.epi_tma) {
+      const uint32_t bufC = stg_base + (uint32_t)ew * STG_BYTES, bufX = bufC + 4096u;
+      const uint32_t wbar = warp_bar(ew);
+      uint32_t wphase = 0;
+      const bool f32 = p.c_is_f32 != 0;
+      const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
+        const int m0 = m_blk * BM + quad * 32, n0 = n_blk * BN + half * 64;
+        // staging tiles are free once the previous tile's bulk stores have READ them
+        if (lane == 0) tma_wait_read();
+        __syncwarp();
+        if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
+          mbar_expect_tx(wbar, (has_res ? (f32 ? 8192u : 4096u) : 0u) + (has_aux ? 4096u : 0u));
+          if (has_res) {
+            tma_load_2d(bufC, &tmap_res, wbar, n0, m0);
+            if (f32) tma_load_2d(bufX, &tmap_res, wbar, n0 + 32, m0);
+          }
+          if (has_aux) tma_load_2d(bufX, &tmap_aux, wbar, n0, m0);
         }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+        tmem_ld32_nowait(taddr, r0);
+        tmem_ld32_nowait(taddr + 32u, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator is in registers: release TMEM to the MMA warp
+        if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
+        if (!(p.dbg & 1)) {
+          if (f32) {
+            VG_ACT_SWITCH(p.act, (staged_chunk<true, ACT>(p, r0, lane, 0, n0, bufC, bufX), staged_chunk<true, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX)))
+          } else {
+            VG_ACT_SWITCH(p.act, (staged_chunk<false, ACT>(p, r0, lane, 0, n0, bufC, bufX), staged_chunk<false, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX)))
+          }
+          fence_async_smem();                  // generic-proxy smem writes -> visible to the async (TMA) proxy
+          __syncwarp();
+          if (lane == 0 && m0 < p.M && n0 < p.N) {
+            if (p.accumulate) {
+              tma_reduce_add_2d(&tmap_c, bufC, n0, m0);
+              if (n0 + 32 < p.N) tma_reduce_add_2d(&tmap_c, bufX, n0 + 32, m0);
+            } else if (f32) {
+              tma_store_2d(&tmap_c, bufC, n0, m0);
+              if (n0 + 32 < p.N) tma_store_2d(&tmap_c, bufX, n0 + 32, m0);
+            } else {
+              tma_store_2d(&tmap_c, bufC, n0, m0);
+              if (has_pre) tma_store_2d(&tmap_pre, bufX, n0, m0);
+            }
+            tma_commit();
+          }
+        }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+      if (lane == 0) tma_wait_all();
+    } else {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const int m = m_blk * BM + quad * 32 + lane;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 2; cc += 32) {
+          const int col = half * (BN / 2) + cc;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col), r);
+          const int n0 = n_blk * BN + col;
+          if (m < p.M && n0 < p.N && !(p.dbg & 1)) {
+            if (p.c_is_f32) { VG_ACT_SWITCH(p.act, (epilogue_chunk<float, ACT>(p, r, m, n0))) }
+            else { VG_ACT_SWITCH(p.act, (epilogue_chunk<bf16, ACT>(p, r, m, n0))) }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+      }
     }
   }
 
@@ -332,15 +504,15 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major matrix [rows, cols] (leading dim ld elements) -> tensor map with box {box_cols, box_rows}, 128B swizzle
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+// 2-D row-major matrix [rows, cols] (leading dim ld elements, bf16 or fp32) -> tensor map with box {box_cols, box_rows}, 128B swizzle
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, bool f32 = false) {
   EncodeTiledFn enc = get_encode();
   VG_REQUIRE(enc != nullptr, VG_ERR_LAUNCH, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VG_REQUIRE(r == CUDA_SUCCESS, VG_ERR_LAUNCH, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
@@ -402,9 +574,26 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
     unsigned l = 0, sb = 0, ks = 0;
     if (sscanf(dbg, "%u,%u,%u", &l, &sb, &ks) == 3) { p.mn_lbo = l; p.mn_sbo = sb; p.mn_kstep = ks; }
   }
+  p.dbg = 0;
+  if (const char* d = getenv("VG_TC_DBG")) p.dbg = atoi(d);
+  // staged (TMA) epilogue whenever the output / side tensors are TMA-addressable and no row remap is requested
+  const bool f32 = p.c_is_f32 != 0;
+  const int esz = f32 ? 4 : 2;
+  auto tma_ok = [&](const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0; };
+  p.epi_tma = !(p.dbg & 2) && a.c_row_group == 0 && a.res_row_mod == 0 && tma_ok(a.C, a.ldc) &&
+              (!a.residual || tma_ok(a.residual, a.ldres)) && (!a.aux || tma_ok(a.aux, a.ldaux)) &&
+              (!a.c_pre || tma_ok(a.c_pre, a.ldpre)) && !(f32 && (a.aux || a.c_pre));
+  CUtensorMap mc = ma, mp = ma, mr = ma, mx = ma;     // placeholders when unused
+  if (p.epi_tma) {
+    const int bc = f32 ? 32 : 64;                      // 128-byte wide boxes, 32 rows
+    if ((rc = make_map(&mc, a.C, a.M, a.N, a.ldc, bc, 32, f32))) return rc;
+    if (a.c_pre && (rc = make_map(&mp, a.c_pre, a.M, a.N, a.ldpre, bc, 32, f32))) return rc;
+    if (a.residual && (rc = make_map(&mr, a.residual, a.M, a.N, a.ldres, bc, 32, f32))) return rc;
+    if (a.aux && (rc = make_map(&mx, a.aux, a.M, a.N, a.ldaux, bc, 32, f32))) return rc;
+  }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(total, sms);
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, p);
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, mc, mp, mr, mx, p);
   return check_launch("gemm_tc");
 }
 

@@ -54,28 +54,40 @@ __device__ __forceinline__ void row_stats(const float (&x)[NV][4], int E, int la
 }
 
 // ------------------------------------------------------------------------------------------------ LN forward
+// RPI rows per warp iteration (4 for E <= 128): all loads of the batch are issued before any math so that each
+// lane keeps RPI*NV 16-byte requests in flight (HBM latency, not the shuffle reductions, bounds this kernel).
 template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_fwd_kernel(int64_t rows, int E, const T* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, float eps) {
+  constexpr int RPI = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
   float g[NV][4], b[NV][4];
   load_vec(gamma, E, lane, g);
   load_vec(beta, E, lane, b);
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    float v[NV][4];
-    load_row<T, NV>(x + r * E, E, lane, v);
-    float mean, rstd;
-    row_stats(v, E, lane, mean, rstd, eps);
+  for (int64_t r0 = warp * RPI; r0 < rows; r0 += nwarps * RPI) {
+    float v[RPI][NV][4];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int q = 0; q < RPI; ++q) {
+      const int64_t r = min(r0 + q, rows - 1);
+      load_row<T, NV>(x + r * E, E, lane, v[q]);
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = fmaf((v[i][j] - mean) * rstd, g[i][j], b[i][j]);
-    store_row<T, NV>(y + r * E, E, lane, v);
-    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+    for (int q = 0; q < RPI; ++q) {
+      const int64_t r = r0 + q;
+      if (r >= rows) break;
+      float mean, rstd;
+      row_stats(v[q], E, lane, mean, rstd, eps);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[q][i][j] = fmaf((v[q][i][j] - mean) * rstd, g[i][j], b[i][j]);
+      store_row<T, NV>(y + r * E, E, lane, v[q]);
+      if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+    }
   }
 }
 
@@ -98,6 +110,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int RPI = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
   __shared__ float s_dg[MAXE], s_db[MAXE];
   for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
@@ -111,40 +124,45 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) { adg[i][j] = 0.f; adb[i][j] = 0.f; }
   const float invE = 1.0f / (float)E;
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    float xv[NV][4], dv[NV][4];
-    load_row<T, NV>(x + r * E, E, lane, xv);
-    load_row<T, NV>(dy + r * E, E, lane, dv);
-    const float mu = mean[r], rs = rstd[r];
-    float c1 = 0.f, c2 = 0.f;
+  for (int64_t r0 = warp * RPI; r0 < rows; r0 += nwarps * RPI) {
+    float xv[RPI][NV][4], dv[RPI][NV][4], rv[RPI][NV][4];
+    float mu[RPI], rs[RPI];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float xh = (xv[i][j] - mu) * rs;       // padded lanes: dy = 0 -> contribute nothing
-        const float gd = dv[i][j] * g[i][j];
-        adg[i][j] = fmaf(dv[i][j], xh, adg[i][j]);
-        adb[i][j] += dv[i][j];
-        c1 += gd;
-        c2 = fmaf(gd, xh, c2);
-        xv[i][j] = xh; dv[i][j] = gd;
-      }
-    c1 = warp_sum(c1) * invE;
-    c2 = warp_sum(c2) * invE;
-    if (dres != nullptr) {
-      float rv[NV][4];
-      load_row<T, NV>(dres + r * E, E, lane, rv);
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dv[i][j] = rv[i][j] + rs * (dv[i][j] - c1 - xv[i][j] * c2);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dv[i][j] = rs * (dv[i][j] - c1 - xv[i][j] * c2);
+    for (int q = 0; q < RPI; ++q) {        // issue every load of the batch first
+      const int64_t r = min(r0 + q, rows - 1);
+      load_row<T, NV>(x + r * E, E, lane, xv[q]);
+      load_row<T, NV>(dy + r * E, E, lane, dv[q]);
+      if (dres != nullptr) load_row<T, NV>(dres + r * E, E, lane, rv[q]);
+      mu[q] = mean[r]; rs[q] = rstd[r];
     }
-    store_row<T, NV>(dx + r * E, E, lane, dv);
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      const int64_t r = r0 + q;
+      if (r >= rows) break;
+      float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (xv[q][i][j] - mu[q]) * rs[q];     // padded lanes: dy = 0, gamma = 0 -> contribute nothing
+          const float gd = dv[q][i][j] * g[i][j];
+          adg[i][j] = fmaf(dv[q][i][j], xh, adg[i][j]);
+          adb[i][j] += dv[q][i][j];
+          c1 += gd;
+          c2 = fmaf(gd, xh, c2);
+          xv[q][i][j] = xh; dv[q][i][j] = gd;
+        }
+      c1 = warp_sum(c1) * invE;
+      c2 = warp_sum(c2) * invE;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float t = rs[q] * (dv[q][i][j] - c1 - xv[q][i][j] * c2);
+          dv[q][i][j] = (dres != nullptr) ? rv[q][i][j] + t : t;
+        }
+      store_row<T, NV>(dx + r * E, E, lane, dv[q]);
+    }
   }
   flush_cols(s_dg, dgamma, adg, E, lane);
   flush_cols(s_db, dbeta, adb, E, lane);
@@ -325,7 +343,7 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
                                 float* dbeta, void* stream) {
   VG_NORM_CHECK(E);
   if (rows == 0) return VG_OK;
-  const int grid = grid_for_rows(rows, 2);   // fewer CTAs -> fewer global atomics for dgamma/dbeta
+  const int grid = grid_for_rows((rows + 3) / 4, 4);   // 4 CTAs/SM: enough loads in flight, still few global atomics for dgamma/dbeta
   if (dtype == VG_F32)
     VG_NV_DISPATCH(E, (ln_bwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
                                                                       (const float*)dres, (float*)dx, dgamma, dbeta)));

@@ -63,6 +63,36 @@ extern "C" int vg_selftest_tcgen05(int M, int N, int K, int trans_a, int trans_b
   return VG_OK;
 }
 
+// average device time per launch (us) of `iters` back-to-back launches (no host work in between)
+extern "C" float vg_time_gemm(int path, int M, int N, int K, int trans_a, int trans_b, int c_f32, int act, int iters) {
+  const int64_t a_rows = trans_a ? K : M, a_cols = trans_a ? M : K;
+  const int64_t b_rows = trans_b ? N : K, b_cols = trans_b ? K : N;
+  const int64_t lda = (a_cols + 7) / 8 * 8, ldb = (b_cols + 7) / 8 * 8;
+  bf16 *A = nullptr, *B = nullptr; void *C = nullptr, *P = nullptr; float* bias = nullptr;
+  const size_t cb = (c_f32 ? 4 : 2) * (size_t)M * N;
+  cudaMalloc(&A, sizeof(bf16) * a_rows * lda); cudaMalloc(&B, sizeof(bf16) * b_rows * ldb); cudaMalloc(&C, cb); cudaMalloc(&P, cb);
+  cudaMalloc(&bias, 4 * (size_t)N);
+  fill_bf16<<<256, 256>>>(A, a_rows * lda, 17u, 2.0f);
+  fill_bf16<<<256, 256>>>(B, b_rows * ldb, 91u, 2.0f);
+  cudaMemset(C, 0, cb); cudaMemset(bias, 0, 4 * (size_t)N);
+  vg_gemm_args g = {};
+  g.path = path; g.ab_dtype = VG_BF16; g.c_dtype = c_f32 ? VG_F32 : VG_BF16; g.trans_a = trans_a; g.trans_b = trans_b;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = N;
+  g.accumulate = (trans_a && !trans_b && c_f32) ? 1 : 0;
+  if (!g.accumulate) { g.bias = bias; g.act = act % 100; if (act == VG_ACT_GELU) { g.c_pre = P; g.ldpre = N; } }
+  for (int i = 0; i < 5; ++i) vg_gemm(&g, nullptr);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  int rc = 0;
+  for (int i = 0; i < iters && !rc; ++i) rc = vg_gemm(&g, nullptr);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = -1.f;
+  if (!rc && e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(P); cudaFree(bias);
+  return ms < 0 ? -1.f : ms * 1000.f / iters;
+}
+
 #ifdef VG_SELFTEST_MAIN
 #include <string.h>
 #include <unistd.h>
@@ -82,6 +112,32 @@ int main(int argc, char** argv) {
       {200, 72, 1000, 1, 0, "wgrad ragged"},
       {128, 128, 64, 1, 1, "A MN-major, B K-major"},
   };
+  if (argc > 1 && !strcmp(argv[1], "--time")) {
+    struct T { int M, N, K, ta, tb, cf32, act; const char* name; };
+    const T ts[] = {
+        {512, 128, 128, 0, 1, 0, 0, "fwd tiny 512x128x128"},
+        {33280, 384, 128, 0, 1, 0, 0, "fwd C2 qkv"},
+        {33280, 256, 128, 0, 1, 0, 1, "fwd C2 fc1+gelu(+pre)"},
+        {33280, 256, 128, 0, 1, 0, 0, "fc1 shape, no act"},
+        {33280, 256, 128, 0, 1, 0, 101, "fc1 shape, gelu no pre"},
+        {33280, 256, 128, 0, 1, 0, 102, "fc1 shape, tanh"},
+        {33280, 256, 128, 0, 1, 0, 104, "fc1 shape, sigmoid"},
+        {33280, 128, 256, 0, 1, 0, 0, "fwd C2 fc2"},
+        {33280, 128, 384, 0, 0, 0, 0, "dgrad C2 qkv"},
+        {384, 128, 33280, 1, 0, 1, 0, "wgrad C2 qkv"},
+        {8192, 8192, 8192, 0, 1, 0, 0, "fwd 8192^3"},
+        {65792, 2304, 768, 0, 1, 0, 0, "fwd C4 qkv (B=256)"},
+    };
+    for (const T& t : ts) {
+      const int iters = (double)t.M * t.N * t.K > 1e11 ? 5 : 200;
+      const float us_tc = vg_time_gemm(VG_GEMM_TCGEN05, t.M, t.N, t.K, t.ta, t.tb, t.cf32, t.act, iters);
+      const float us_si = (double)t.M * t.N * t.K > 1e11 ? -1.f : vg_time_gemm(VG_GEMM_SIMT, t.M, t.N, t.K, t.ta, t.tb, t.cf32, t.act, 20);
+      const double fl = 2.0 * t.M * t.N * t.K;
+      printf("%-26s tcgen05 %9.2f us %8.1f TFLOP/s | simt %9.2f us\n", t.name, us_tc, fl / us_tc * 1e-6, us_si);
+      fflush(stdout);
+    }
+    return 0;
+  }
   const char* only = argc > 1 ? argv[1] : nullptr;
   int fails = 0;
   for (const Case& c : cases) {

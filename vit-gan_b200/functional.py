@@ -112,6 +112,89 @@ def _want(ctx, idx):
 
 
 # --------------------------------------------------------------------------------------------------
+# fused gradient accumulation: when a parameter already owns a contiguous fp32 .grad (train.FlatNet, or any
+# optimizer used with zero_grad(set_to_none=False)), the split-K weight-gradient GEMM / bias column-sum /
+# LayerNorm reductions ADD straight into it (they are atomic-accumulating kernels anyway) and the Function
+# returns None for that input -> no temporary, no zero-fill, no autograd add kernel per parameter.
+# Data-parallel bucketing is told through `grad_ready_hooks` since autograd hooks do not fire for None grads.
+# --------------------------------------------------------------------------------------------------
+_FUSE_GRAD_ACC = True
+grad_ready_hooks: list = []
+
+
+def set_fused_grad_accumulation(enabled: bool):
+    global _FUSE_GRAD_ACC
+    _FUSE_GRAD_ACC = enabled
+
+
+def _grad_view(params, rows, cols):
+    """A [rows, cols] fp32 view over the .grad of `params` if they exist and are laid out back to back, else None."""
+    if not _FUSE_GRAD_ACC:
+        return None
+    g0 = params[0].grad
+    if g0 is None or g0.dtype != torch.float32 or not g0.is_contiguous():
+        return None
+    ptr = g0.data_ptr()
+    for p in params:
+        g = p.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != ptr:
+            return None
+        ptr += 4 * g.numel()
+    if len(params) == 1:
+        return g0.view(rows, cols)
+    return g0.as_strided((rows, cols), (cols, 1))
+
+
+def _notify(params):
+    for hook in grad_ready_hooks:
+        for p in params:
+            hook(p)
+
+
+def acc_wgrad(dy2, x2, params):
+    """dW = dy2^T x2 for one parameter or a row-stack of parameters.  Returns the gradient tensor ([sum N, K]),
+    or None if it was accumulated in place into the parameters' .grad."""
+    n = sum(p.shape[0] for p in params)
+    view = _grad_view(params, n, x2.shape[1])
+    if view is not None:
+        ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True, out=view)
+        _notify(params)
+        return None
+    return ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True)
+
+
+def acc_colsum(dy2, params):
+    view = _grad_view(params, 1, dy2.shape[1])
+    if view is not None:
+        ops.colsum(dy2, out=view.view(-1))
+        _notify(params)
+        return None
+    return ops.colsum(dy2)
+
+
+def _split_rows(t, sizes):
+    if t is None:
+        return (None,) * len(sizes)
+    out, r = [], 0
+    for n in sizes:
+        out.append(t[r:r + n])
+        r += n
+    return tuple(out)
+
+
+def ln_bwd(dy2, x2, mean, rstd, weight, bias, dres, want_pg):
+    """LayerNorm backward; returns (dx, dweight|None, dbias|None) with in-place accumulation when possible."""
+    if want_pg:
+        gw, gb = _grad_view([weight], 1, weight.numel()), _grad_view([bias], 1, bias.numel())
+        if gw is not None and gb is not None:
+            dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, dgamma_acc=gw.view(-1), dbeta_acc=gb.view(-1))
+            _notify([weight, bias])
+            return dx, None, None
+    dx, dg, db = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres)
+    return (dx, dg, db) if want_pg else (dx, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
 # Linear (+ activation): y = act(x W^T + b)
 # --------------------------------------------------------------------------------------------------
 _ACT_BWD = {L.ACT_GELU: L.ACT_MUL_DGELU, L.ACT_TANH: L.ACT_MUL_DTANH, L.ACT_SIN: L.ACT_MUL_DSIN,
@@ -136,6 +219,7 @@ class LinearFn(Function):
         y, pre = res if need_pre else (res, None)
         ctx.save_for_backward(x2, weight, pre if need_pre else (y if act != L.ACT_NONE else None))
         ctx.meta = (act, act_param, cdt, x.shape, x.dtype, bias is not None)
+        ctx.bias_ref = bias
         ctx.skip_pg = _SKIP_PARAM_GRADS
         return y.reshape(*x.shape[:-1], weight.shape[0])
 
@@ -157,9 +241,10 @@ class LinearFn(Function):
                 dx = ops.cast(dx, xdtype)
             dx = dx.reshape(xshape)
         if _want(ctx, 1):
-            dw = ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True).reshape(weight.shape)
+            dw = acc_wgrad(dy2, x2, [weight])
+            dw = None if dw is None else dw.reshape(weight.shape)
         if has_bias and _want(ctx, 2):
-            db = ops.colsum(dy2)
+            db = acc_colsum(dy2, [ctx.bias_ref])
         return dx, dw, db, None, None, None, None
 
 
@@ -180,6 +265,7 @@ class LayerNormFn(Function):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         y, mean, rstd = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps)
         ctx.save_for_backward(x2, mean, rstd, weight)
+        ctx.bias_ref = bias
         ctx.skip_pg = _SKIP_PARAM_GRADS
         return y.reshape(x.shape)
 
@@ -188,9 +274,8 @@ class LayerNormFn(Function):
     def backward(ctx, dy):
         x2, mean, rstd, weight = ctx.saved_tensors
         dy2 = dy.reshape(x2.shape).contiguous()
-        dx, dg, db = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach())
-        keep = not ctx.skip_pg
-        return dx.reshape(dy.shape), dg if keep else None, db if keep else None, None
+        dx, dg, db = ln_bwd(dy2, x2, mean, rstd, weight, ctx.bias_ref, None, not ctx.skip_pg)
+        return dx.reshape(dy.shape), dg, db, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -210,6 +295,7 @@ class EmbedV2Fn(Function):
         ops.gemm(patches, w, bias=conv_b.detach(), residual=posd, res_row_mod=N, c_row_group=N, out=x.view(B * (N + 1), E))
         ops.fill_rows(x, 0, cls.detach().reshape(E))
         ctx.save_for_backward(patches, conv_w)
+        ctx.bias_ref = conv_b
         ctx.meta = (B, Cc, I, patch, N, E, pos.shape, cls.shape)
         ctx.skip_pg = _SKIP_PARAM_GRADS
         return x
@@ -227,8 +313,9 @@ class EmbedV2Fn(Function):
             dimg = ops.col2im(dpatches, B, Cc, I, patch)
         if ctx.skip_pg:
             return dimg, None, None, None, None, None
-        dw = ops.gemm(dtok, patches, trans_a=True, trans_b=False, accumulate=True).reshape(conv_w.shape)
-        db = ops.colsum(dtok)
+        dw = acc_wgrad(dtok, patches, [conv_w])
+        dw = None if dw is None else dw.reshape(conv_w.shape)
+        db = acc_colsum(dtok, [ctx.bias_ref])
         return dimg, dw, db, dpos.reshape(pos_shape), dcls.reshape(cls_shape), None
 
 
@@ -245,20 +332,19 @@ def _attn_fwd(xn, B, S, H, wqkv, bqkv, wo, bo, residual, scale, mode=L.ATTN_DOT)
     return y, qkv, o, lse
 
 
-def _attn_bwd(dy, xn, qkv, o, lse, B, S, H, wqkv, wo, scale, want_pg, mode=L.ATTN_DOT, has_bias=True):
+def _attn_bwd(dy, xn, qkv, o, lse, B, S, H, wqkv, wo, scale, want_pg, prm, mode=L.ATTN_DOT):
+    """prm = dict(wq, wk, wv, wo, bq, bk, bv, bo) of the nn.Parameters (targets of the in-place accumulation)."""
     hd = qkv.shape[1] // 3
     d = hd // H
-    g = {}
+    g = {"wo": None, "bo": None, "wqkv": None, "bqkv": None}
     if want_pg:
-        g["wo"] = ops.gemm(dy, o, trans_a=True, trans_b=False, accumulate=True)
-        if has_bias:
-            g["bo"] = ops.colsum(dy)
+        g["wo"] = acc_wgrad(dy, o, [prm["wo"]])
+        g["bo"] = acc_colsum(dy, [prm["bo"]])
     d_o = ops.gemm(dy, wo, trans_b=False)
     dqkv = ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, d_o, lse, B, H, S, d, scale, mode)
     if want_pg:
-        g["wqkv"] = ops.gemm(dqkv, xn, trans_a=True, trans_b=False, accumulate=True)
-        if has_bias:
-            g["bqkv"] = ops.colsum(dqkv)
+        g["wqkv"] = acc_wgrad(dqkv, xn, [prm["wq"], prm["wk"], prm["wv"]])
+        g["bqkv"] = acc_colsum(dqkv, [prm["bq"], prm["bk"], prm["bv"]])
     dxn = ops.gemm(dqkv, wqkv, trans_b=False)
     return dxn, g
 
@@ -278,6 +364,7 @@ class SelfAttentionFn(Function):
         scale = 1.0 / math.sqrt(E // n_heads)
         y, qkv, o, lse = _attn_fwd(x2.contiguous(), B, S, n_heads, wqkv, bqkv, wo_, bo.detach(), None, scale)
         ctx.save_for_backward(x2, qkv, o, lse, wq, wk, wv, wo)
+        ctx.prm = dict(wq=wq, wk=wk, wv=wv, wo=wo, bq=bq, bk=bk, bv=bv, bo=bo)
         ctx.meta = (B, S, E, n_heads, scale, x.dtype)
         ctx.skip_pg = _SKIP_PARAM_GRADS
         return y.reshape(B, S, E)
@@ -289,13 +376,14 @@ class SelfAttentionFn(Function):
         B, S, E, H, scale, xdtype = ctx.meta
         adt = x2.dtype
         dy2 = dy.reshape(B * S, E).contiguous()
+        if dy2.dtype != adt:
+            dy2 = ops.cast(dy2, adt)
         dxn, g = _attn_bwd(dy2, x2, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale,
-                           not ctx.skip_pg)
+                           not ctx.skip_pg, ctx.prm)
         dx = dxn if dxn.dtype == xdtype else ops.cast(dxn, xdtype)
-        if ctx.skip_pg:
-            return (dx.reshape(B, S, E), None) + (None,) * 8
-        dw, db = g["wqkv"], g["bqkv"]
-        return (dx.reshape(B, S, E), None, dw[:E], db[:E], dw[E:2 * E], db[E:2 * E], dw[2 * E:], db[2 * E:], g["wo"], g["bo"])
+        dwq, dwk, dwv = _split_rows(g["wqkv"], (E, E, E))
+        dbq, dbk, dbv = _split_rows(g["bqkv"], (E, E, E))
+        return (dx.reshape(B, S, E), None, dwq, dbq, dwk, dbk, dwv, dbv, g["wo"], g["bo"])
 
 
 # --------------------------------------------------------------------------------------------------
@@ -319,6 +407,7 @@ class EncoderFn(Function):
         y = ops.gemm(g, packed([w2], adt), bias=b2.detach(), residual=x1)                           # fc2 + skip
         ctx.save_for_backward(x2, mean1, rstd1, xn1, qkv, o, lse, x1, mean2, rstd2, xn2, u, g,
                               n1w, wq, wk, wv, wo, n2w, w1, w2)
+        ctx.prm = dict(wq=wq, wk=wk, wv=wv, wo=wo, bq=bq, bk=bk, bv=bv, bo=bo, n1b=n1b, n2b=n2b, b1=b1, b2=b2)
         ctx.meta = (B, S, E, n_heads, scale, x.dtype)
         ctx.skip_pg = _SKIP_PARAM_GRADS
         return y.reshape(B, S, E)
@@ -334,27 +423,26 @@ class EncoderFn(Function):
         if dy2.dtype != adt:
             dy2 = ops.cast(dy2, adt)
         # ---- MLP half
+        P = ctx.prm
         dw2 = db2 = dw1 = db1 = None
         if pg:
-            dw2 = ops.gemm(dy2, g, trans_a=True, trans_b=False, accumulate=True)
-            db2 = ops.colsum(dy2)
+            dw2 = acc_wgrad(dy2, g, [w2])
+            db2 = acc_colsum(dy2, [P["b2"]])
         du = ops.gemm(dy2, packed([w2], adt), trans_b=False, act=L.ACT_MUL_DGELU, aux=u)       # dgrad fc2 x gelu'(u)
         if pg:
-            dw1 = ops.gemm(du, xn2, trans_a=True, trans_b=False, accumulate=True)
-            db1 = ops.colsum(du)
+            dw1 = acc_wgrad(du, xn2, [w1])
+            db1 = acc_colsum(du, [P["b1"]])
         dxn2 = ops.gemm(du, packed([w1], adt), trans_b=False)
-        dx1, dn2w, dn2b = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2w.detach(), dres=dy2)
+        dx1, dn2w, dn2b = ln_bwd(dxn2, x1, mean2, rstd2, n2w, P["n2b"], dy2, pg)
         # ---- attention half
-        dxn1, ga = _attn_bwd(dx1, xn1, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale, pg)
-        dx, dn1w, dn1b = ops.layernorm_bwd(dxn1, x2, mean1, rstd1, n1w.detach(), dres=dx1)
+        dxn1, ga = _attn_bwd(dx1, xn1, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale, pg, P)
+        dx, dn1w, dn1b = ln_bwd(dxn1, x2, mean1, rstd1, n1w, P["n1b"], dx1, pg)
         if dx.dtype != xdtype:
             dx = ops.cast(dx, xdtype)
         dx = dx.reshape(B, S, E)
-        if not pg:
-            return (dx, None) + (None,) * 16
-        dw, db = ga["wqkv"], ga["bqkv"]
-        return (dx, None, dn1w, dn1b, dw[:E], db[:E], dw[E:2 * E], db[E:2 * E], dw[2 * E:], db[2 * E:], ga["wo"], ga["bo"],
-                dn2w, dn2b, dw1, db1, dw2, db2)
+        dwq, dwk, dwv = _split_rows(ga["wqkv"], (E, E, E))
+        dbq, dbk, dbv = _split_rows(ga["bqkv"], (E, E, E))
+        return (dx, None, dn1w, dn1b, dwq, dbq, dwk, dbk, dwv, dbv, ga["wo"], ga["bo"], dn2w, dn2b, dw1, db1, dw2, db2)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -131,16 +131,19 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None):
+def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbeta_acc=None):
+    """dgamma_acc / dbeta_acc: optional fp32 buffers the kernel atomically ADDS into (e.g. the parameters' .grad)."""
     _req(x2d, "x2d")
     rows, e = x2d.shape
     dx = torch.empty_like(x2d)
-    dgb = torch.zeros(2, e, dtype=torch.float32, device=x2d.device)
+    if dgamma_acc is None:
+        dgb = torch.zeros(2, e, dtype=torch.float32, device=x2d.device)
+        dgamma_acc, dbeta_acc = dgb[0], dgb[1]
     check(lib.vg_layernorm_bwd(dt(x2d), rows, e, dy2d.data_ptr(), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                               gamma.data_ptr(), _ptr(dres), dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), stream()),
+                               gamma.data_ptr(), _ptr(dres), dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(), stream()),
           "vg_layernorm_bwd")
     _count()
-    return dx, dgb[0], dgb[1]
+    return dx, dgamma_acc, dbeta_acc
 
 
 def sln_fwd(h2d, w2d, ln_g, ln_b, gamma_s, beta_s, eps=1e-5):

@@ -24,6 +24,9 @@ class FlatNet:
 
     def __init__(self, module, exclude=None):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad and not (exclude and exclude(n, p))]
+        # matrices first, vectors after (stable): q/k/v weights -- and, separately, their biases -- of one attention
+        # block then sit back to back, so the fused QKV weight gradient is ONE split-K GEMM into one flat-buffer view
+        named = [x for x in named if x[1].dim() >= 2] + [x for x in named if x[1].dim() < 2]
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
         dev = self.params[0].device
@@ -106,8 +109,10 @@ class GradBuckets:
         self.armed = False
         self.pending = [0] * self.n
         self.works = []
+        self.index = {id(p): i for i, p in enumerate(net.params)}
         for i, p in enumerate(net.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
+        Fn.grad_ready_hooks.append(self._fused_ready)      # gradients accumulated in place by the kernels
 
     def _make_hook(self, i):
         def hook(param):
@@ -118,6 +123,11 @@ class GradBuckets:
             if self.pending[b] == 0:
                 self._launch(b)
         return hook
+
+    def _fused_ready(self, param):
+        i = self.index.get(id(param))
+        if i is not None:
+            self._make_hook(i)(param)
 
     def _launch(self, b):
         s, e = self.bounds[b]
