@@ -301,3 +301,33 @@ def test_cast_scale_and_act_backward(vb):
     for act, prm in ((1, 0.0), (2, 0.0), (3, 30.0), (4, 0.0)):
         out = vb.ops.act_backward(dy.cuda(), aux.cuda(), act, prm)
         assert rel(out, act_ref(act + 4, dy, aux, prm)) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,S,d", [(3, 4, 65, 32), (300, 4, 65, 32), (2, 8, 65, 32), (4, 2, 64, 64), (3, 4, 128, 64), (5, 4, 17, 32), (2, 4, 1, 32)])
+def test_attention_tensor_core_path(vb, B, H, S, d):
+    """bf16 dot-product attention with S <= 128 and d in {32, 64} runs on tcgen05 (attention_tc.cu): forward and the
+    five-GEMM backward against the fp32 formula, and against this library's CUDA-core flash kernel (VG_ATTN_PATH=simt
+    is read once per process, so the cross-check uses the fp32 path which always takes the CUDA-core kernel)."""
+    g = gen(B + S + d)
+    hd = H * d
+    qkv = (torch.randn(B * S, 3 * hd, generator=g) * 0.8).bfloat16()
+    d_o = torch.randn(B * S, hd, generator=g).bfloat16()
+    scale = 1.0 / math.sqrt(d)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = [ref_in[:, i * hd:(i + 1) * hd].reshape(B, S, H, d).permute(0, 2, 1, 3) for i in range(3)]
+    s = (q @ k.transpose(-1, -2)) * scale
+    oref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, hd)
+    lse_ref = torch.logsumexp(s, -1).reshape(-1)
+    oref.backward(d_o.float())
+    qc = qkv.cuda()
+    o, lse = vb.ops.attention_fwd(qc[:, :hd], qc[:, hd:2 * hd], qc[:, 2 * hd:], B, H, S, d, scale, 0)
+    assert rel(o, oref) < BF16_TOL
+    assert rel(lse, lse_ref) < 1e-3
+    dqkv = vb.ops.attention_bwd(qc[:, :hd], qc[:, hd:2 * hd], qc[:, 2 * hd:], o, d_o.cuda(), lse, B, H, S, d, scale, 0)
+    assert torch.isfinite(dqkv).all()
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, i * hd:(i + 1) * hd], ref_in.grad[:, i * hd:(i + 1) * hd]) < BF16_TOL, name
+    # same inputs through the CUDA-core kernel in fp32
+    qf = qkv.float().cuda()
+    o32, lse32 = vb.ops.attention_fwd(qf[:, :hd], qf[:, hd:2 * hd], qf[:, 2 * hd:], B, H, S, d, scale, 0)
+    assert rel(o, o32) < BF16_TOL and rel(lse, lse32) < 1e-3

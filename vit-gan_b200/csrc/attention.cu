@@ -462,6 +462,15 @@ int bwd_t(int B, int H, int S, int d, const void* q, const void* k, const void* 
 }  // namespace
 }  // namespace vg
 
+namespace vg {
+bool attention_tc_supported(int dtype, int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v,
+                            int64_t ld_qkv, const void* o, int64_t ld_o);
+int attention_fwd_tc(int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                     float* lse, float scale, cudaStream_t st);
+int attention_bwd_tc(int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, const void* d_o,
+                     int64_t ldo, const float* lse, void* dq, void* dk, void* dv, int64_t ldd, float scale, cudaStream_t st);
+}  // namespace vg
+
 using namespace vg;
 
 extern "C" int vg_attention_fwd(int dtype, int mode, int B, int H, int S, int d, const void* q, const void* k,
@@ -470,6 +479,9 @@ extern "C" int vg_attention_fwd(int dtype, int mode, int B, int H, int S, int d,
   int rc = check_shape(B, H, S, d, ld_qkv, ld_o);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  // tensor-core path (attention_tc.cu) for the single-tile bf16 dot-product case; CUDA-core flash kernel otherwise
+  if (attention_tc_supported(dtype, mode, B, H, S, d, q, k, v, ld_qkv, o, ld_o))
+    return attention_fwd_tc(B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st);
   if (dtype == VG_F32)
     return mode == VG_ATTN_L2 ? fwd_t<float, VG_ATTN_L2>(B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st)
                               : fwd_t<float, VG_ATTN_DOT>(B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st);
@@ -485,6 +497,9 @@ extern "C" int vg_attention_bwd(int dtype, int mode, int B, int H, int S, int d,
   if (rc) return rc;
   VG_REQUIRE(ld_dqkv % 4 == 0, VG_ERR_ALIGN, "attention_bwd: ld_dqkv must be a multiple of 4");
   cudaStream_t st = as_stream(stream);
+  if (attention_tc_supported(dtype, mode, B, H, S, d, q, k, v, ld_qkv, d_o, ld_o) && ld_dqkv % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0)
+    return attention_bwd_tc(B, H, S, d, q, k, v, ld_qkv, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, st);
   if (dtype == VG_F32)
     return mode == VG_ATTN_L2
                ? bwd_t<float, VG_ATTN_L2>(B, H, S, d, q, k, v, ld_qkv, o, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, delta_ws, st)

@@ -1,0 +1,611 @@
+// attention_tc.cu -- dot-product multi-head self-attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA),
+// forward and backward, for the single-tile regime of the ViT-GAN configs: S <= 128 tokens, head dim 32 or 64,
+// bf16 operands, fp32 accumulation and softmax statistics.   (src/v2/modules.py:142-159 and its autograd backward.)
+//
+// Work item = (batch element b, group of 128 feature columns = 4 heads of 32 or 2 heads of 64).  All operands of
+// an item are brought in by TMA as [rows x 128 B] SWIZZLE_128B tiles straight from the fused QKV projection
+// output (3-D tensor maps [B, S, cols]: rows >= S are out of bounds -> zero filled on load, clipped on store), so
+// there is no head split/merge copy and no S x S tensor in HBM.  One smem tile serves several operand roles:
+//     forward :  S_h = Q_h K_h^T   (A = Q  K-major,  B = K  K-major)          -> TMEM, 4 heads side by side
+//                softmax rows in registers (thread = query row), P_h -> bf16 -> swizzled smem
+//                O_h = P_h V_h     (A = P  K-major,  B = V  MN-major)         -> TMEM -> * 1/l -> smem -> TMA store
+//     backward:  S_h = Q_h K_h^T, dP_h = dO_h V_h^T (B = V K-major)           -> TMEM (double buffered per head)
+//                P = exp(S*scale - lse); delta = rowsum(P*dP) (== rowsum(dO*O)); dS = P*(dP - delta)*scale
+//                dV_h = P_h^T dO_h   (A = P  MN-major, B = dO MN-major)
+//                dK_h = dS_h^T Q_h   (A = dS MN-major, B = Q  MN-major)
+//                dQ_h = dS_h K_h     (A = dS K-major,  B = K  MN-major)        -> TMEM -> smem -> TMA store into dqkv
+// Warp roles: warp 0 TMA loads, warp 1 MMA issue (+TMEM alloc), warps 2..5 softmax / drain (thread = row).
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int NTHREADS = 192;
+constexpr int ROWS = 128;                 // query rows per tile (UMMA M)
+constexpr int CHUNK_BYTES = ROWS * 128;   // one [128 rows x 64 bf16] swizzled tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ---------------------------------------------------------------- PTX helpers (same conventions as gemm_tc.cu)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("vg attention_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// SWIZZLE_128B smem descriptors (see gemm_tc.cu): K-major: SBO 1024; MN-major: LBO = stride between 64-wide blocks
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return make_desc(addr, 16u, 1024u); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) { return make_desc(addr, lbo, 1024u); }
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// address of the 16-byte chunk `c16` (0..7) of row `row` inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(uint32_t tile, int row, int c16) { return tile + (uint32_t)row * 128u + (((uint32_t)c16 ^ ((uint32_t)row & 7u)) << 4); }
+
+struct Geo {
+  int B, H, S, NK;          // NK = S rounded up to 16 (UMMA N / K granularity)
+  int groups;               // column groups of 128 per batch element (= H * D / 128)
+  float scale;              // softmax scale (applied to the raw dot products)
+  float* lse;               // [B, H, S]
+};
+
+// ================================================================================================ forward
+// smem: Q[2 chunks] K[2] V[2] (96 KB, single buffered; K/V tiles hold NK rows) + P[2 bufs][2 chunks] (64 KB; buffer 0 doubles
+// as the output staging tile)
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const Geo g) {
+  constexpr int HPC = 128 / D;                 // heads per work item
+  constexpr int S_STRIDE = 128;                // TMEM columns reserved per head for S (N <= 128)
+  constexpr int O_COL = 2 * S_STRIDE;          // S regions are double buffered by head parity; O (128 cols) behind them
+  constexpr int IN_BYTES = 6 * CHUNK_BYTES;    // Q,K,V x 2 chunks
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t in_base = base;                         // [IN_BYTES]
+  const uint32_t p_base = base + IN_BYTES;               // [2][2 chunks]
+  const uint32_t bar_base = p_base + 4 * CHUNK_BYTES;
+  const uint32_t in_full = bar_base, in_empty = bar_base + 16;
+  auto s_full = [&](int i) { return bar_base + 8u * (4 + i); };     // 2 (head parity)
+  auto s_free = [&](int i) { return bar_base + 8u * (6 + i); };     // 2
+  auto p_full = [&](int i) { return bar_base + 8u * (8 + i); };     // 2
+  auto p_empty = [&](int i) { return bar_base + 8u * (10 + i); };   // 2
+  const uint32_t o_full = bar_base + 8u * 12, o_free = bar_base + 8u * 13;
+  const uint32_t tmem_slot = bar_base + 8u * 14;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1); mbar_init(s_free(i), 128);
+      mbar_init(p_full(i), 128); mbar_init(p_empty(i), 1);
+    }
+    mbar_init(in_full, 1); mbar_init(in_empty, 1);
+    mbar_init(o_full, 1); mbar_init(o_free, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int total = g.B * g.groups;
+  const int nk_steps = g.NK / 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int b = w / g.groups, col0 = (w % g.groups) * 128;
+        mbar_wait(in_empty, ((uint32_t)it & 1u) ^ 1u);
+        const uint32_t t = in_base;
+        mbar_expect_tx(in_full, 2u * (ROWS * 128u) + 4u * ((uint32_t)g.NK * 128u));
+        for (int c = 0; c < 2; ++c) {
+          tma_load_3d(t + c * CHUNK_BYTES, &map_q, in_full, col0 + 64 * c, 0, b);
+          tma_load_3d(t + (2 + c) * CHUNK_BYTES, &map_k, in_full, col0 + 64 * c, 0, b);
+          tma_load_3d(t + (4 + c) * CHUNK_BYTES, &map_v, in_full, col0 + 64 * c, 0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(ROWS, g.NK, 0, 0);      // S = Q K^T : both K-major
+      const uint32_t idesc_o = make_idesc(ROWS, D, 0, 1);         // O = P V   : A K-major, B MN-major
+      int it = 0;
+      uint32_t hcount = 0;                                        // running head counter (parity bookkeeping)
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const uint32_t t = in_base;
+        mbar_wait(in_full, (uint32_t)it & 1u);
+        tc_fence_after();
+        // software pipeline over heads: S(h+1) is issued before PV(h) so the softmax of h overlaps the next QK^T
+        auto issue_s = [&](int h, uint32_t hc) {
+          const int r = hc & 1;
+          mbar_wait(s_free(r), ((hc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t off = (uint32_t)((h * D) / 64) * CHUNK_BYTES + (uint32_t)((h * D) % 64) * 2u;
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            tc_mma(tmem + (uint32_t)(r * S_STRIDE), desc_k(t + off + k * 32u), desc_k(t + 2 * CHUNK_BYTES + off + k * 32u), idesc_s, k > 0);
+          tc_commit(s_full(r));
+        };
+        issue_s(0, hcount);
+        for (int h = 0; h < HPC; ++h) {
+          const uint32_t hc = hcount + h;
+          if (h + 1 < HPC) issue_s(h + 1, hc + 1);
+          const int pb = hc & 1;
+          if (h == 0) { mbar_wait(o_free, ((uint32_t)it & 1u) ^ 1u); }
+          mbar_wait(p_full(pb), (hc >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t pt = p_base + pb * 2 * CHUNK_BYTES;
+          const uint32_t vt = t + 4 * CHUNK_BYTES + (uint32_t)((h * D) / 64) * CHUNK_BYTES + (uint32_t)((h * D) % 64) * 2u;
+          for (int k = 0; k < nk_steps; ++k)      // K = keys: 16 per step; P chunk (k/4), 32 B per step; V rows 16k.. (2048 B per step)
+            tc_mma(tmem + (uint32_t)(O_COL + h * D), desc_k(pt + (k >> 2) * CHUNK_BYTES + (k & 3) * 32u), desc_mn(vt + k * 2048u, CHUNK_BYTES), idesc_o, k > 0);
+          tc_commit(p_empty(pb));
+        }
+        tc_commit(o_full);
+        tc_commit(in_empty);
+        hcount += HPC;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + output drain: thread = query row
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const float sc2 = g.scale * LOG2E;
+    int it = 0;
+    uint32_t hcount = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int b = w / g.groups, grp = w % g.groups, col0 = grp * 128;
+      float inv_l[HPC];
+#pragma unroll
+      for (int h = 0; h < HPC; ++h) {
+        const uint32_t hc = hcount + h;
+        const int r = hc & 1;
+        mbar_wait(s_full(r), (hc >> 1) & 1u);
+        tc_fence_after();
+        // pass 1: row max over the valid keys
+        float m = -INFINITY;
+        for (int c = 0; c < g.NK; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)(r * S_STRIDE + c), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c + j < g.S) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        // pass 2: p = exp2((s - m) * scale * log2e), row sum, bf16 P -> swizzled smem (keys >= S are written as 0)
+        const int pb = hc & 1;
+        mbar_wait(p_empty(pb), ((hc >> 1) & 1u) ^ 1u);
+        const uint32_t pt = p_base + pb * 2 * CHUNK_BYTES;
+        float l = 0.f;
+        const float mb = m * sc2;
+        for (int c = 0; c < g.NK; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)(r * S_STRIDE + c), v);
+          tmem_ld_wait();
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            p[j] = (c + j < g.S) ? exp2f(fmaf(__uint_as_float(v[j]), sc2, -mb)) : 0.f;
+            l += p[j];
+          }
+          const uint32_t tile = pt + (uint32_t)(c >> 6) * CHUNK_BYTES;
+          const int c16 = (c & 63) >> 3;
+          sts128(swz(tile, row, c16), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+          sts128(swz(tile, row, c16 + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+        }
+        tc_fence_before();
+        mbar_arrive(s_free(r));                  // S_h fully read
+        fence_async_smem();                      // P visible to the tensor-core (async) proxy
+        mbar_arrive(p_full(pb));
+        inv_l[h] = 1.0f / l;
+        if (row < g.S) g.lse[((int64_t)b * g.H + grp * HPC + h) * g.S + row] = m * g.scale + __logf(l);
+      }
+      // ---- drain O (all heads of the item): TMEM -> *1/l -> bf16 -> swizzled staging (P buffer 0) -> TMA store
+      mbar_wait(o_full, (uint32_t)it & 1u);
+      tc_fence_after();
+      if (threadIdx.x == 64) tma_wait_read();    // previous item's store has finished reading the staging tiles
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t stg = p_base;               // P buffer 0: free, every PV MMA of this item has completed (o_full)
+#pragma unroll
+      for (int h = 0; h < HPC; ++h) {
+#pragma unroll
+        for (int c = 0; c < D; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)(O_COL + h * D + c), v);
+          tmem_ld_wait();
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * inv_l[h];
+          const int col = h * D + c;
+          const uint32_t tile = stg + (uint32_t)(col >> 6) * CHUNK_BYTES;
+          const int c16 = (col & 63) >> 3;
+          sts128(swz(tile, row, c16), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          sts128(swz(tile, row, c16 + 1), pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+      fence_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        tma_store_3d(&map_o, stg, col0, 0, b);
+        tma_store_3d(&map_o, stg + CHUNK_BYTES, col0 + 64, 0, b);
+        tma_commit();
+      }
+      hcount += HPC;
+      // NOTE: P buffer 0 is reused by the next item's first head only after p_empty/its MMA, and its softmax write is
+      // ordered behind this store's smem read by the tma_wait_read() + bar.sync at the top of the next drain ... which is
+      // too late for head 0 of the next item -> wait here instead (cheap: the store reads 32 KB of smem).
+      if (threadIdx.x == 64) tma_wait_read();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (threadIdx.x == 64) tma_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ================================================================================================ backward
+// smem: Q[2] K[2] V[2] dO[2] chunks (single buffered, 128 KB) + P[2 chunks] + dS[2 chunks] (64 KB).  The dQ/dK/dV staging
+// tiles alias P/dS: they are written after the head's last MMA has consumed P/dS and before the next head's P is produced.
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                   const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
+                   const __grid_constant__ CUtensorMap map_dv, const Geo g) {
+  constexpr int HPC = 128 / D;
+  // TMEM columns: [S | dP] double buffered by head parity (2 x 256), no room left for outputs at NK = 128 ->
+  // S and dP use 96-column slots when NK <= 96 ... keep it simple: slots of 128 for S and dP of ONE head (256),
+  // outputs dV,dK,dQ of one head behind them (3*D <= 192): 448 <= 512.  Heads are processed one at a time.
+  constexpr int DP_COL = 128, DV_COL = 256, DK_COL = 256 + D, DQ_COL = 256 + 2 * D;
+  constexpr int STG_BYTES = ROWS * D * 2;      // one [128 x D] bf16 staging tile, plain row-major
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t q_t = base, k_t = base + 2 * CHUNK_BYTES, v_t = base + 4 * CHUNK_BYTES, do_t = base + 6 * CHUNK_BYTES;
+  const uint32_t p_t = base + 8 * CHUNK_BYTES, ds_t = base + 10 * CHUNK_BYTES;
+  const uint32_t stg = p_t;                                // 3 tiles of STG_BYTES (<= 48 KB) over P | dS
+  const uint32_t bar_base = base + 12 * CHUNK_BYTES;
+  const uint32_t in_full = bar_base, in_empty = bar_base + 8, sdp_full = bar_base + 16, sdp_free = bar_base + 24,
+                 pds_full = bar_base + 32, pds_empty = bar_base + 40, out_full = bar_base + 48, out_free = bar_base + 56;
+  const uint32_t tmem_slot = bar_base + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(in_full, 1); mbar_init(in_empty, 1); mbar_init(sdp_full, 1); mbar_init(sdp_free, 128);
+    mbar_init(pds_full, 128); mbar_init(pds_empty, 1); mbar_init(out_full, 1); mbar_init(out_free, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int total = g.B * g.groups;
+  const int nk_steps = g.NK / 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int b = w / g.groups, col0 = (w % g.groups) * 128;
+        mbar_wait(in_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_expect_tx(in_full, 4u * (ROWS * 128u) + 4u * ((uint32_t)g.NK * 128u));
+        for (int c = 0; c < 2; ++c) {
+          tma_load_3d(q_t + c * CHUNK_BYTES, &map_q, in_full, col0 + 64 * c, 0, b);
+          tma_load_3d(do_t + c * CHUNK_BYTES, &map_do, in_full, col0 + 64 * c, 0, b);
+          tma_load_3d(k_t + c * CHUNK_BYTES, &map_k, in_full, col0 + 64 * c, 0, b);
+          tma_load_3d(v_t + c * CHUNK_BYTES, &map_v, in_full, col0 + 64 * c, 0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(ROWS, g.NK, 0, 0);     // S, dP: [q x keys], A,B K-major
+      const uint32_t idesc_kv = make_idesc(ROWS, D, 1, 1);       // dV, dK: [keys(128) x D], A MN-major (P/dS), B MN-major (dO/Q)
+      const uint32_t idesc_q = make_idesc(ROWS, D, 0, 1);        // dQ: [q x D], A K-major (dS), B MN-major (K)
+      int it = 0;
+      uint32_t hc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        mbar_wait(in_full, (uint32_t)it & 1u);
+        tc_fence_after();
+        for (int h = 0; h < HPC; ++h, ++hc) {
+          const uint32_t off = (uint32_t)((h * D) / 64) * CHUNK_BYTES + (uint32_t)((h * D) % 64) * 2u;
+          mbar_wait(sdp_free, (hc & 1u) ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) tc_mma(tmem, desc_k(q_t + off + k * 32u), desc_k(k_t + off + k * 32u), idesc_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) tc_mma(tmem + DP_COL, desc_k(do_t + off + k * 32u), desc_k(v_t + off + k * 32u), idesc_s, k > 0);
+          tc_commit(sdp_full);
+          mbar_wait(pds_full, hc & 1u);
+          mbar_wait(out_free, (hc & 1u) ^ 1u);
+          tc_fence_after();
+          // dV = P^T dO, dK = dS^T Q : K dimension = query rows (8 steps of 16 rows = 2048 B in both operands)
+#pragma unroll
+          for (int k = 0; k < ROWS / 16; ++k) tc_mma(tmem + DV_COL, desc_mn(p_t + k * 2048u, CHUNK_BYTES), desc_mn(do_t + off + k * 2048u, CHUNK_BYTES), idesc_kv, k > 0);
+#pragma unroll
+          for (int k = 0; k < ROWS / 16; ++k) tc_mma(tmem + DK_COL, desc_mn(ds_t + k * 2048u, CHUNK_BYTES), desc_mn(q_t + off + k * 2048u, CHUNK_BYTES), idesc_kv, k > 0);
+          // dQ = dS K : K dimension = keys
+          for (int k = 0; k < nk_steps; ++k)
+            tc_mma(tmem + DQ_COL, desc_k(ds_t + (k >> 2) * CHUNK_BYTES + (k & 3) * 32u), desc_mn(k_t + off + k * 2048u, CHUNK_BYTES), idesc_q, k > 0);
+          tc_commit(out_full);
+          tc_commit(pds_empty);
+        }
+        tc_commit(in_empty);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const float sc2 = g.scale * LOG2E;
+    uint32_t hc = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int b = w / g.groups, grp = w % g.groups, col0 = grp * 128;
+      for (int h = 0; h < HPC; ++h, ++hc) {
+        const bool valid_row = row < g.S;
+        const float lse2 = valid_row ? g.lse[((int64_t)b * g.H + grp * HPC + h) * g.S + row] * LOG2E : 0.f;
+        mbar_wait(sdp_full, hc & 1u);
+        tc_fence_after();
+        mbar_wait(pds_empty, (hc & 1u) ^ 1u);        // previous head's dV/dK/dQ MMAs have finished reading P / dS
+        if (threadIdx.x == 64) tma_wait_read();      // ... and the previous head's output stores have read the aliased staging
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // pass 1: P = exp2(s*scale*log2e - lse*log2e) -> smem (bf16); delta = sum_j P_ij dP_ij
+        float delta = 0.f;
+        for (int c = 0; c < g.NK; c += 16) {
+          uint32_t sv[16], dv[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)c, sv);
+          tmem_ld16(tmem + lane_addr + (uint32_t)(DP_COL + c), dv);
+          tmem_ld_wait();
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            p[j] = (valid_row && c + j < g.S) ? exp2f(fmaf(__uint_as_float(sv[j]), sc2, -lse2)) : 0.f;
+            delta = fmaf(p[j], __uint_as_float(dv[j]), delta);
+          }
+          const uint32_t tile = p_t + (uint32_t)(c >> 6) * CHUNK_BYTES;
+          const int c16 = (c & 63) >> 3;
+          sts128(swz(tile, row, c16), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+          sts128(swz(tile, row, c16 + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+        }
+        // pass 2: dS = P * (dP - delta) * scale   (P re-read from this thread's own smem row, dP from TMEM)
+        for (int c = 0; c < g.NK; c += 16) {
+          uint32_t dv[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)(DP_COL + c), dv);
+          tmem_ld_wait();
+          const uint32_t tile_p = p_t + (uint32_t)(c >> 6) * CHUNK_BYTES, tile_d = ds_t + (uint32_t)(c >> 6) * CHUNK_BYTES;
+          const int c16 = (c & 63) >> 3;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t a0, a1, a2, a3;
+            lds128(swz(tile_p, row, c16 + hh), a0, a1, a2, a3);
+            const float p[8] = {bf16_lo(a0), bf16_hi(a0), bf16_lo(a1), bf16_hi(a1), bf16_lo(a2), bf16_hi(a2), bf16_lo(a3), bf16_hi(a3)};
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = p[j] * (__uint_as_float(dv[hh * 8 + j]) - delta) * g.scale;
+            sts128(swz(tile_d, row, c16 + hh), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+          }
+        }
+        // key columns NK..127 of P / dS feed the M dimension of dV / dK (rows that are never stored) but must be finite
+        for (int c = g.NK; c < 128; c += 8) {
+          sts128(swz(p_t + (uint32_t)(c >> 6) * CHUNK_BYTES, row, (c & 63) >> 3), 0u, 0u, 0u, 0u);
+          sts128(swz(ds_t + (uint32_t)(c >> 6) * CHUNK_BYTES, row, (c & 63) >> 3), 0u, 0u, 0u, 0u);
+        }
+        tc_fence_before();
+        mbar_arrive(sdp_free);
+        fence_async_smem();
+        mbar_arrive(pds_full);
+        // ---- drain dV, dK, dQ of this head: TMEM -> bf16 -> plain row-major staging -> TMA stores (rows >= S clipped)
+        mbar_wait(out_full, hc & 1u);              // dV/dK/dQ complete => P/dS (== staging) no longer read by the tensor core
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t tcol = (t == 0) ? DQ_COL : (t == 1 ? DK_COL : DV_COL);
+          const uint32_t dst = stg + t * STG_BYTES + (uint32_t)row * (D * 2);
+#pragma unroll
+          for (int c = 0; c < D; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem + lane_addr + tcol + (uint32_t)c, v);
+            tmem_ld_wait();
+            sts128(dst + c * 2, pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                   pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
+            sts128(dst + c * 2 + 16, pack_bf16(__uint_as_float(v[8]), __uint_as_float(v[9])), pack_bf16(__uint_as_float(v[10]), __uint_as_float(v[11])),
+                   pack_bf16(__uint_as_float(v[12]), __uint_as_float(v[13])), pack_bf16(__uint_as_float(v[14]), __uint_as_float(v[15])));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(out_free);
+        fence_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int c = col0 + h * D;
+          tma_store_3d(&map_dq, stg, c, 0, b);
+          tma_store_3d(&map_dk, stg + STG_BYTES, c, 0, b);
+          tma_store_3d(&map_dv, stg + 2 * STG_BYTES, c, 0, b);
+          tma_commit();
+        }
+      }
+    }
+    if (threadIdx.x == 64) tma_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ================================================================================================ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// bf16 tensor viewed as [B, S, cols] with row pitch ld elements; box {box_cols, box_rows, 1}
+int make_map3(CUtensorMap* map, const void* ptr, int B, int S, int cols, int64_t ld, int box_cols, int box_rows, bool swizzle) {
+  EncodeTiledFn enc = get_encode();
+  VG_REQUIRE(enc != nullptr, VG_ERR_LAUNCH, "attention_tc: cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)S * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_REQUIRE(r == CUDA_SUCCESS, VG_ERR_LAUNCH, "attention_tc: cuTensorMapEncodeTiled failed (%d) B=%d S=%d cols=%d ld=%lld box=%dx%d", (int)r, B, S,
+             cols, (long long)ld, box_cols, box_rows);
+  return VG_OK;
+}
+
+constexpr int FWD_SMEM = 6 * CHUNK_BYTES + 4 * CHUNK_BYTES + 1024 + 256;
+template <int D> constexpr int bwd_smem() { return 12 * CHUNK_BYTES + 1024 + 256; }
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool attention_tc_supported(int dtype, int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v,
+                            int64_t ld_qkv, const void* o, int64_t ld_o) {
+  static int sm100 = -1, forced_off = -1;
+  if (sm100 < 0) sm100 = vg_device_is_sm100();
+  if (forced_off < 0) { const char* e = getenv("VG_ATTN_PATH"); forced_off = (e && !strcmp(e, "simt")) ? 1 : 0; }
+  if (!sm100 || forced_off) return false;
+  if (dtype != VG_BF16 || mode != VG_ATTN_DOT) return false;
+  if (!(d == 32 || d == 64) || (H * d) % 128 != 0 || S < 1 || S > 128) return false;
+  if (ld_qkv % 8 || ld_o % 8) return false;
+  return aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o);
+}
+
+int attention_fwd_tc(int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                     float* lse, float scale, cudaStream_t st) {
+  const int cols = H * d, NK = (S + 15) / 16 * 16;
+  CUtensorMap mq, mk, mv, mo;
+  int rc;
+  if ((rc = make_map3(&mq, q, B, S, cols, ld, 64, ROWS, true))) return rc;
+  if ((rc = make_map3(&mk, k, B, S, cols, ld, 64, NK, true))) return rc;
+  if ((rc = make_map3(&mv, v, B, S, cols, ld, 64, NK, true))) return rc;
+  if ((rc = make_map3(&mo, o, B, S, cols, ldo, 64, ROWS, true))) return rc;
+  Geo g; g.B = B; g.H = H; g.S = S; g.NK = NK; g.groups = cols / 128; g.scale = scale; g.lse = lse;
+  const int total = B * g.groups, grid = min(total, num_sms());
+  if (d == 32) {
+    static bool set = false;
+    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    attn_fwd_tc_kernel<32><<<grid, NTHREADS, FWD_SMEM, st>>>(mq, mk, mv, mo, g);
+  } else {
+    static bool set = false;
+    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    attn_fwd_tc_kernel<64><<<grid, NTHREADS, FWD_SMEM, st>>>(mq, mk, mv, mo, g);
+  }
+  return check_launch("attention_fwd_tc");
+}
+
+int attention_bwd_tc(int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, const void* d_o,
+                     int64_t ldo, const float* lse, void* dq, void* dk, void* dv, int64_t ldd, float scale, cudaStream_t st) {
+  const int cols = H * d, NK = (S + 15) / 16 * 16;
+  CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
+  int rc;
+  if ((rc = make_map3(&mq, q, B, S, cols, ld, 64, ROWS, true))) return rc;
+  if ((rc = make_map3(&mk, k, B, S, cols, ld, 64, NK, true))) return rc;
+  if ((rc = make_map3(&mv, v, B, S, cols, ld, 64, NK, true))) return rc;
+  if ((rc = make_map3(&mdo, d_o, B, S, cols, ldo, 64, ROWS, true))) return rc;
+  if ((rc = make_map3(&mdq, dq, B, S, cols, ldd, d, ROWS, false))) return rc;
+  if ((rc = make_map3(&mdk, dk, B, S, cols, ldd, d, ROWS, false))) return rc;
+  if ((rc = make_map3(&mdv, dv, B, S, cols, ldd, d, ROWS, false))) return rc;
+  Geo g; g.B = B; g.H = H; g.S = S; g.NK = NK; g.groups = cols / 128; g.scale = scale; g.lse = const_cast<float*>(lse);
+  const int total = B * g.groups, grid = min(total, num_sms());
+  if (d == 32) {
+    static bool set = false;
+    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<32>()) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    attn_bwd_tc_kernel<32><<<grid, NTHREADS, bwd_smem<32>(), st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, g);
+  } else {
+    static bool set = false;
+    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<64>()) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    attn_bwd_tc_kernel<64><<<grid, NTHREADS, bwd_smem<64>(), st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, g);
+  }
+  return check_launch("attention_bwd_tc");
+}
+
+}  // namespace vg
