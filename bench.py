@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a whole-step CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing section (used for ncu launch lists)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW instead of the fused flat Adam kernel")
     ap.add_argument("--keep-unused-d-grads", action="store_true",
                     help="also compute D's parameter gradients in the G pass (the reference computes, then discards them)")
@@ -188,18 +189,32 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ kernel roofline (dominant kernel, timed alone)
-def time_kernel(fn, iters, flush):
-    for _ in range(3):
-        fn()
+def time_graph(make_call, n_sets, iters=48):
+    """Average device time per launch: `iters` launches round-robin over `n_sets` disjoint buffer sets (footprint > L2,
+    so every launch streams from HBM) captured into ONE CUDA graph -> no host launch overhead inside the event pair."""
+    calls = [make_call(i) for i in range(n_sets)]
+    for c in calls:
+        c()
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        flush.zero_()                         # > L2 (126 MB): next launch starts cold in L2
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for c in calls:
+            c()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            calls[i % n_sets]()
+    g.replay()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(3):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); fn(); e.record()
+        s.record(); g.replay(); e.record()
         e.synchronize()
-        ts.append(s.elapsed_time(e))
-    return statistics.mean(ts)
+        best = min(best, s.elapsed_time(e) / iters)
+    return best
 
 
 def kernel_rooflines(vb, spec, pk):
@@ -210,50 +225,72 @@ def kernel_rooflines(vb, spec, pk):
     cfg = o2.V2Config(**spec["over"])
     B, S, E, H, m = spec["per_gpu_batch"], cfg.seq_len, cfg.embeddings_dimension, cfg.attention_heads_count, cfg.mlp_ratio
     M, d = B * S, cfg.embeddings_dimension // cfg.attention_heads_count
-    dev = "cuda"
-    bf = torch.bfloat16
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    x = torch.randn(M, E, device=dev).to(bf)
-    wqkv = torch.randn(3 * E, E, device=dev).to(bf)
-    bq = torch.randn(3 * E, device=dev)
-    qkv = torch.randn(M, 3 * E, device=dev).to(bf)
-    w1 = torch.randn(m * E, E, device=dev).to(bf)
-    b1 = torch.randn(m * E, device=dev)
+    dev, bf, L = "cuda", torch.bfloat16, vb.lib
+    mk = lambda *shape: torch.randn(*shape, device=dev).to(bf)
+    wqkv, w1 = mk(3 * E, E), mk(m * E, E)
+    bq, b1 = torch.randn(3 * E, device=dev), torch.randn(m * E, device=dev)
+    gam, bet = torch.ones(E, device=dev), torch.zeros(E, device=dev)
+    scale = d ** -0.5
     out = []
 
-    def entry(name, fn, flops, bytes_, iters=20):
-        t = time_kernel(fn, iters, flush) * 1e-3
+    def entry(name, make_call, set_bytes, flops, bytes_):
+        n_sets = max(2, int(300e6 // max(set_bytes, 1)) + 1)
+        t = time_graph(make_call, n_sets) * 1e-3
         tf, gb = flops / t / 1e12, bytes_ / t / 1e9
         bound = "tensor" if flops / bytes_ > pk["tf_burst"] * 1e3 / pk["hbm"] else "hbm"
-        out.append({"kernel": name, "bound": bound, "us": t * 1e6, "tflops": tf, "gbs": gb,
-                    "frac_tensor": tf / pk["tf_burst"], "frac_hbm": gb / pk["hbm"], "alg_flops": flops, "alg_bytes": bytes_})
+        out.append({"kernel": name, "bound": bound, "us": t * 1e6, "tflops": tf, "gbs": gb, "frac_tensor": tf / pk["tf_burst"],
+                    "frac_hbm": gb / pk["hbm"], "alg_flops": flops, "alg_bytes": bytes_, "buffer_sets": n_sets})
 
-    L = vb.lib
-    entry("gemm_tc fwd qkv [M,E]x[E,3E]+bias", lambda: vb.ops.gemm(x, wqkv, bias=bq, path=L.GEMM_TCGEN05),
-          2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E))
-    entry("gemm_tc fwd fc1+gelu [M,E]x[E,mE]", lambda: vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05),
-          2.0 * M * m * E * E, 2.0 * (M * E + m * E * E + 2 * M * m * E))
-    entry("gemm_tc dgrad qkv [M,3E]x[3E,E]", lambda: vb.ops.gemm(qkv, wqkv, trans_b=False, path=L.GEMM_TCGEN05),
-          2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + 3 * E * E + M * E))
-    entry("gemm_tc wgrad qkv [3E,M]x[M,E] split-K", lambda: vb.ops.gemm(qkv, x, trans_a=True, trans_b=False, accumulate=True, path=L.GEMM_TCGEN05),
-          2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + M * E) + 4.0 * 3 * E * E)
-    hd = E
-    scale = d ** -0.5
-    o, lse = vb.ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale)
-    entry("attention fwd (flash, CUDA cores)", lambda: vb.ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale),
-          4.0 * B * H * S * S * d, 2.0 * (4 * M * E), iters=5)
-    entry("attention bwd (flash, CUDA cores)", lambda: vb.ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, o, lse, B, H, S, d, scale),
-          8.0 * B * H * S * S * d, 2.0 * (8 * M * E), iters=5)
-    g, b_ = torch.ones(E, device=dev), torch.zeros(E, device=dev)
-    entry("layernorm fwd", lambda: vb.ops.layernorm_fwd(x, g, b_), 8.0 * M * E, 2.0 * 2 * M * E)
-    del flush
+    def mk_qkv(i):
+        x, o = mk(M, E), torch.empty(M, 3 * E, device=dev, dtype=bf)
+        return lambda: vb.ops.gemm(x, wqkv, bias=bq, out=o, path=L.GEMM_TCGEN05)
+    entry("gemm_tc fwd qkv [M,E]x[E,3E]+bias", mk_qkv, 2 * (M * E + M * 3 * E), 2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E))
+
+    def mk_fc1(i):
+        x = mk(M, E)
+        return lambda: vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)
+    entry("gemm_tc fwd fc1+gelu(+pre) [M,E]x[E,mE]", mk_fc1, 2 * (M * E + 2 * M * m * E), 2.0 * M * m * E * E, 2.0 * (M * E + m * E * E + 2 * M * m * E))
+
+    def mk_dgrad(i):
+        dy, o = mk(M, 3 * E), torch.empty(M, E, device=dev, dtype=bf)
+        return lambda: vb.ops.gemm(dy, wqkv, trans_b=False, out=o, path=L.GEMM_TCGEN05)
+    entry("gemm_tc dgrad qkv [M,3E]x[3E,E]", mk_dgrad, 2 * (M * 3 * E + M * E), 2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + 3 * E * E + M * E))
+
+    def mk_wgrad(i):
+        dy, x, o = mk(M, 3 * E), mk(M, E), torch.zeros(3 * E, E, device=dev)
+        return lambda: vb.ops.gemm(dy, x, trans_a=True, trans_b=False, accumulate=True, out=o, path=L.GEMM_TCGEN05)
+    entry("gemm_tc wgrad qkv [3E,M]x[M,E] split-K", mk_wgrad, 2 * (M * 3 * E + M * E), 2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + M * E) + 4.0 * 3 * E * E)
+
+    def mk_attn_f(i):
+        qkv = mk(M, 3 * E)
+        return lambda: vb.ops.attention_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, H, S, d, scale)
+    entry("attention fwd", mk_attn_f, 2 * 4 * M * E, 4.0 * B * H * S * S * d, 2.0 * 4 * M * E)
+
+    def mk_attn_b(i):
+        qkv, d_o = mk(M, 3 * E), mk(M, E)
+        o, lse = vb.ops.attention_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, H, S, d, scale)
+        return lambda: vb.ops.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], o, d_o, lse, B, H, S, d, scale)
+    entry("attention bwd", mk_attn_b, 2 * 8 * M * E, 8.0 * B * H * S * S * d, 2.0 * 7 * M * E)
+
+    def mk_ln(i):
+        x = mk(M, E)
+        return lambda: vb.ops.layernorm_fwd(x, gam, bet)
+    entry("layernorm fwd", mk_ln, 2 * 2 * M * E, 8.0 * M * E, 2.0 * 2 * M * E)
+
+    def mk_lnb(i):
+        x, dy, dr = mk(M, E), mk(M, E), mk(M, E)
+        _, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)
+        return lambda: vb.ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dr)
+    entry("layernorm bwd (+residual grad)", mk_lnb, 2 * 4 * M * E, 12.0 * M * E, 2.0 * 4 * M * E)
+
     dom = out[0]
     key = "frac_tensor" if dom["bound"] == "tensor" else "frac_hbm"
     roof = {"kernel": dom["kernel"], "bound": dom["bound"],
             "achieved": dom["tflops"] if dom["bound"] == "tensor" else dom["gbs"],
             "peak": pk["tf_burst"] if dom["bound"] == "tensor" else pk["hbm"],
             "unit": "TFLOP/s" if dom["bound"] == "tensor" else "GB/s", "frac": dom[key], "traffic": None,
-            "peak_source": pk["src"], "us_per_launch": dom["us"]}
+            "peak_source": pk["src"], "us_per_launch": dom["us"],
+            "note": "timed alone inside one CUDA graph over rotating >L2 buffer sets (burst peak); traffic from profiles/ ncu --set full"}
     return roof, out
 
 
@@ -402,7 +439,7 @@ def run_ours(args):
         value, e2e_value = imgs / (ms * 1e-3), imgs / (ms_e2e * 1e-3)
         fl = step_flops_per_image(spec, skip_unused)
         step_tf = value * fl / world / 1e12          # per GPU
-        roof, all_k = kernel_rooflines(vb, spec, pk) if world == 1 else (None, [])
+        roof, all_k = kernel_rooflines(vb, spec, pk) if (world == 1 and not args.no_roofline) else (None, [])
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_oracle_rate(spec, seconds_budget=25.0, steps=2, warmup=1)

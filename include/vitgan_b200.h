@@ -96,10 +96,12 @@ int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* ou
  * src/v1/transformer.py:18-19.  Saves mean / rstd per row for the backward. */
 int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, const float* gamma, const float* beta,
                      void* y, float* mean, float* rstd, float eps, void* stream);
-/* dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta are atomically accumulated (zero them first). */
+/* dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta are atomically accumulated (zero them first).
+ * dres_colsum / dx_colsum (optional, fp32 [E], accumulated): column sums of the skip-path gradient `dres` and of the
+ * produced `dx` -- the bias gradients of the Linear layers on either side of the norm, computed here for free. */
 int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
                      const float* rstd, const float* gamma, const void* dres, void* dx,
-                     float* dgamma, float* dbeta, void* stream);
+                     float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum, void* stream);
 
 /* Self-modulated LayerNorm  y = w * (gamma_s * (LN(h)*g + b) + beta_s)  (src/v1/spectral_layer_norm.py:19-20).
  * h has h_rows rows (h_rows == rows, or rows % h_rows == 0 for the first G layer where h is (S,F) and

@@ -336,3 +336,29 @@ def test_v1_full_grads_vs_oracle_64px(vb):
     for name, mod in (("generator.", G), ("discriminator.", D)):
         cmp_grads({k: p.grad for k, p in mod.named_parameters()}, {k: orc.p[name + k].grad for k, _ in mod.named_parameters()}, 5e-4, name)
     vb.set_precision("bf16")
+
+
+def test_v2_200_step_loss_curve(vb):
+    """BASELINE.json: loss curves over 200 synthetic steps.  Default v2 model (E128 L6 H4 S65) at B=8, fp32 path, the
+    reference's own step sequence with torch AdamW, against the live CPU oracle (bit-exact to the reference).
+    GAN training is a chaotic map: rounding differences are amplified by Adam, so the curves are compared (a) tightly
+    over the first 20 steps and (b) on the smoothed trajectory over all 200."""
+    vb.set_precision("fp32")
+    steps, B = 200, 8
+    ocfg = o2.V2Config(batch_size=3 * 32 * 32)
+    orc = harness.OracleV2(ocfg, seed=0)
+    torch.manual_seed(0)
+    gan = vb.v2.ViTGAN(vb.v2.Config(batch_size=3 * 32 * 32)).cuda()
+    go = torch.optim.AdamW(gan.generator.parameters(), lr=5e-4, weight_decay=1e-3)
+    do = torch.optim.AdamW(gan.discriminator.parameters(), lr=5e-4, weight_decay=1e-3)
+    ref, got = [], []
+    for real, noise in harness.synthetic_batches_v2(ocfg, B, steps):
+        ref.append(torch.stack(orc.step(real, noise)))
+        got.append(torch.stack(vb.train.gan_step(gan.generator, gan.discriminator, go, do, real.cuda(), noise.cuda(), "ce")).cpu())
+    ref, got = torch.stack(ref), torch.stack(got)
+    assert torch.isfinite(got).all()
+    assert rel(got[:20], ref[:20]) < 1e-3
+    k = 20
+    smooth = lambda t: t.unfold(0, k, k).mean(-1)
+    assert rel(smooth(got), smooth(ref)) < 5e-2
+    vb.set_precision("bf16")

@@ -138,9 +138,12 @@ def test_layernorm(vb, dt, tol, rows, E):
     y, mean, rstd = vb.ops.layernorm_fwd(x.cuda(), gam.cuda(), bet.cuda())
     assert rel(y, yr) < tol
     assert rel(mean, x.float().mean(1)) < 1e-5
-    dx, dg, db = vb.ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dres=dres.cuda())
+    cr, cx = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
+    dx, dg, db = vb.ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dres=dres.cuda(), dres_colsum=cr, dx_colsum=cx)
     assert rel(dx, xr.grad + dres.float()) < tol
     assert rel(dg, gr.grad) < max(tol, 1e-4) and rel(db, br.grad) < max(tol, 1e-4)
+    # fused column sums (bias gradients of the neighbouring Linear layers): fp32 sums of the un-rounded values
+    assert rel(cr, dres.float().sum(0)) < 1e-4 and rel(cx, (xr.grad + dres.float()).sum(0)) < max(tol, 1e-3)
 
 
 @pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])

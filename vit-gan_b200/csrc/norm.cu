@@ -109,7 +109,10 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-              const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dres_colsum, float* __restrict__ dx_colsum) {
+  // dres_colsum / dx_colsum (optional): column sums of the skip-path gradient and of the produced dx -- these are the
+  // bias gradients of the Linear layers on either side of the norm (fc2 / out-proj), obtained here for free.
   constexpr int RPI = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
   __shared__ float s_dg[MAXE], s_db[MAXE];
   for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
@@ -117,12 +120,12 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
-  float g[NV][4], adg[NV][4], adb[NV][4];
+  float g[NV][4], adg[NV][4], adb[NV][4], adr[NV][4], adx[NV][4];
   load_vec(gamma, E, lane, g);
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { adg[i][j] = 0.f; adb[i][j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { adg[i][j] = 0.f; adb[i][j] = 0.f; adr[i][j] = 0.f; adx[i][j] = 0.f; }
   const float invE = 1.0f / (float)E;
   for (int64_t r0 = warp * RPI; r0 < rows; r0 += nwarps * RPI) {
     float xv[RPI][NV][4], dv[RPI][NV][4], rv[RPI][NV][4];
@@ -159,7 +162,9 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float t = rs[q] * (dv[q][i][j] - c1 - xv[q][i][j] * c2);
+          if (dres != nullptr) adr[i][j] += rv[q][i][j];
           dv[q][i][j] = (dres != nullptr) ? rv[q][i][j] + t : t;
+          adx[i][j] += dv[q][i][j];
         }
       store_row<T, NV>(dx + r * E, E, lane, dv[q]);
     }
@@ -168,6 +173,18 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
   flush_cols(s_db, dbeta, adb, E, lane);
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += blockDim.x) { atomicAdd(&dgamma[i], s_dg[i]); atomicAdd(&dbeta[i], s_db[i]); }
+  if (dres_colsum != nullptr || dx_colsum != nullptr) {      // second round through the same smem accumulators
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+    __syncthreads();
+    flush_cols(s_dg, dres_colsum, adr, E, lane);
+    flush_cols(s_db, dx_colsum, adx, E, lane);
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+      if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_dg[i]);
+      if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_db[i]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ SLN forward
@@ -340,16 +357,17 @@ extern "C" int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, c
 
 extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
                                 const float* rstd, const float* gamma, const void* dres, void* dx, float* dgamma,
-                                float* dbeta, void* stream) {
+                                float* dbeta, float* dres_colsum, float* dx_colsum, void* stream) {
   VG_NORM_CHECK(E);
+  VG_REQUIRE(!(dres_colsum && !dres), VG_ERR_ARG, "layernorm_bwd: dres_colsum without dres");
   if (rows == 0) return VG_OK;
-  const int grid = grid_for_rows((rows + 3) / 4, 4);   // 4 CTAs/SM: enough loads in flight, still few global atomics for dgamma/dbeta
+  const int grid = grid_for_rows((rows + 3) / 4, 2);   // 2 CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
   if (dtype == VG_F32)
     VG_NV_DISPATCH(E, (ln_bwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
-                                                                      (const float*)dres, (float*)dx, dgamma, dbeta)));
+                                                                      (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum)));
   else
     VG_NV_DISPATCH(E, (ln_bwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
-                                                                     (const bf16*)dres, (bf16*)dx, dgamma, dbeta)));
+                                                                     (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum)));
   return check_launch("layernorm_bwd");
 }
 

@@ -182,16 +182,30 @@ def _split_rows(t, sizes):
     return tuple(out)
 
 
-def ln_bwd(dy2, x2, mean, rstd, weight, bias, dres, want_pg):
-    """LayerNorm backward; returns (dx, dweight|None, dbias|None) with in-place accumulation when possible."""
-    if want_pg:
-        gw, gb = _grad_view([weight], 1, weight.numel()), _grad_view([bias], 1, bias.numel())
-        if gw is not None and gb is not None:
-            dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, dgamma_acc=gw.view(-1), dbeta_acc=gb.view(-1))
-            _notify([weight, bias])
-            return dx, None, None
-    dx, dg, db = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres)
-    return (dx, dg, db) if want_pg else (dx, None, None)
+def _acc_target(params):
+    """-> (buffer to accumulate a bias gradient into, in_place?)"""
+    n = sum(p.numel() for p in params)
+    view = _grad_view(params, 1, n)
+    if view is not None:
+        return view.view(-1), True
+    return torch.zeros(n, dtype=torch.float32, device=params[0].device), False
+
+
+def ln_bwd(dy2, x2, mean, rstd, weight, bias, dres, want_pg, bias_of_dres=None, bias_of_dx=None):
+    """LayerNorm backward; returns (dx, dweight|None, dbias|None, d_bias_of_dres|None, d_bias_of_dx|None).
+    bias_of_dres / bias_of_dx: bias parameters whose gradient is colsum(dres) / colsum(dx) (fused into this kernel).
+    Gradients are accumulated in place into .grad when possible (then None is returned for them)."""
+    if not want_pg:
+        dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres)
+        return dx, None, None, None, None
+    gw, w_in = _acc_target([weight])
+    gb, b_in = _acc_target([bias])
+    cr, cr_in = _acc_target([bias_of_dres]) if bias_of_dres is not None else (None, True)
+    cx, cx_in = _acc_target([bias_of_dx]) if bias_of_dx is not None else (None, True)
+    dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, dgamma_acc=gw, dbeta_acc=gb,
+                                 dres_colsum=cr, dx_colsum=cx)
+    _notify([p for p, flag in ((weight, w_in), (bias, b_in), (bias_of_dres, cr_in), (bias_of_dx, cx_in)) if p is not None and flag])
+    return (dx, None if w_in else gw, None if b_in else gb, None if cr_in else cr, None if cx_in else cx)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -274,7 +288,7 @@ class LayerNormFn(Function):
     def backward(ctx, dy):
         x2, mean, rstd, weight = ctx.saved_tensors
         dy2 = dy.reshape(x2.shape).contiguous()
-        dx, dg, db = ln_bwd(dy2, x2, mean, rstd, weight, ctx.bias_ref, None, not ctx.skip_pg)
+        dx, dg, db, _, _ = ln_bwd(dy2, x2, mean, rstd, weight, ctx.bias_ref, None, not ctx.skip_pg)
         return dx.reshape(dy.shape), dg, db, None
 
 
@@ -332,14 +346,16 @@ def _attn_fwd(xn, B, S, H, wqkv, bqkv, wo, bo, residual, scale, mode=L.ATTN_DOT)
     return y, qkv, o, lse
 
 
-def _attn_bwd(dy, xn, qkv, o, lse, B, S, H, wqkv, wo, scale, want_pg, prm, mode=L.ATTN_DOT):
-    """prm = dict(wq, wk, wv, wo, bq, bk, bv, bo) of the nn.Parameters (targets of the in-place accumulation)."""
+def _attn_bwd(dy, xn, qkv, o, lse, B, S, H, wqkv, wo, scale, want_pg, prm, mode=L.ATTN_DOT, bo_done=False):
+    """prm = dict(wq, wk, wv, wo, bq, bk, bv, bo) of the nn.Parameters (targets of the in-place accumulation).
+    bo_done: the out-proj bias gradient colsum(dy) was already produced by the LayerNorm backward that made dy."""
     hd = qkv.shape[1] // 3
     d = hd // H
     g = {"wo": None, "bo": None, "wqkv": None, "bqkv": None}
     if want_pg:
         g["wo"] = acc_wgrad(dy, o, [prm["wo"]])
-        g["bo"] = acc_colsum(dy, [prm["bo"]])
+        if not bo_done:
+            g["bo"] = acc_colsum(dy, [prm["bo"]])
     d_o = ops.gemm(dy, wo, trans_b=False)
     dqkv = ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, d_o, lse, B, H, S, d, scale, mode)
     if want_pg:
@@ -427,16 +443,17 @@ class EncoderFn(Function):
         dw2 = db2 = dw1 = db1 = None
         if pg:
             dw2 = acc_wgrad(dy2, g, [w2])
-            db2 = acc_colsum(dy2, [P["b2"]])
         du = ops.gemm(dy2, packed([w2], adt), trans_b=False, act=L.ACT_MUL_DGELU, aux=u)       # dgrad fc2 x gelu'(u)
         if pg:
             dw1 = acc_wgrad(du, xn2, [w1])
             db1 = acc_colsum(du, [P["b1"]])
         dxn2 = ops.gemm(du, packed([w1], adt), trans_b=False)
-        dx1, dn2w, dn2b = ln_bwd(dxn2, x1, mean2, rstd2, n2w, P["n2b"], dy2, pg)
+        # LN2 backward also yields db2 = colsum(dy2) (its skip input) and dbo = colsum(dx1) (its output)
+        dx1, dn2w, dn2b, db2, dbo = ln_bwd(dxn2, x1, mean2, rstd2, n2w, P["n2b"], dy2, pg, bias_of_dres=P["b2"], bias_of_dx=P["bo"])
         # ---- attention half
-        dxn1, ga = _attn_bwd(dx1, xn1, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale, pg, P)
-        dx, dn1w, dn1b = ln_bwd(dxn1, x2, mean1, rstd1, n1w, P["n1b"], dx1, pg)
+        dxn1, ga = _attn_bwd(dx1, xn1, qkv, o, lse, B, S, H, packed([wq, wk, wv], adt), packed([wo], adt), scale, pg, P, bo_done=True)
+        ga["bo"] = dbo
+        dx, dn1w, dn1b, _, _ = ln_bwd(dxn1, x2, mean1, rstd1, n1w, P["n1b"], dx1, pg)
         if dx.dtype != xdtype:
             dx = ops.cast(dx, xdtype)
         dx = dx.reshape(B, S, E)

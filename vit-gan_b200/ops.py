@@ -131,8 +131,9 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbeta_acc=None):
-    """dgamma_acc / dbeta_acc: optional fp32 buffers the kernel atomically ADDS into (e.g. the parameters' .grad)."""
+def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbeta_acc=None, dres_colsum=None, dx_colsum=None):
+    """dgamma_acc / dbeta_acc: optional fp32 buffers the kernel atomically ADDS into (e.g. the parameters' .grad).
+    dres_colsum / dx_colsum: optional fp32 [E] buffers accumulating the column sums of `dres` / of the returned dx."""
     _req(x2d, "x2d")
     rows, e = x2d.shape
     dx = torch.empty_like(x2d)
@@ -140,7 +141,8 @@ def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbet
         dgb = torch.zeros(2, e, dtype=torch.float32, device=x2d.device)
         dgamma_acc, dbeta_acc = dgb[0], dgb[1]
     check(lib.vg_layernorm_bwd(dt(x2d), rows, e, dy2d.data_ptr(), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                               gamma.data_ptr(), _ptr(dres), dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(), stream()),
+                               gamma.data_ptr(), _ptr(dres), dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(), _ptr(dres_colsum),
+                               _ptr(dx_colsum), stream()),
           "vg_layernorm_bwd")
     _count()
     return dx, dgamma_acc, dbeta_acc
