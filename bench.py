@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--micro", type=int, default=None, help="micro-batches per step (exact gradient accumulation); default: auto")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a whole-step CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing section (used for ncu launch lists)")
@@ -361,9 +362,12 @@ def run_ours(args):
                 g_b = vb.train.GradBuckets(gnet, n_buckets=2, average_in_place=False)
                 gopt.grad_scale = dopt.grad_scale = 1.0 / world
 
+        # micro-batching only when the saved activations of the full per-GPU batch would not fit (C4 at 1-2 GPUs)
+        n_micro = args.micro or (max(1, B // 256) if spec["name"] == "c4" else 1)
+
         def eager(real, noise):
-            return vb.train.gan_step(gen, disc, gopt, dopt, real, noise, loss_kind, d_buckets=d_b, g_buckets=g_b,
-                                     skip_unused_d_grads=skip_unused)
+            return vb.train.gan_step_microbatched(gen, disc, gopt, dopt, real, noise, loss_kind, n_micro=n_micro, d_buckets=d_b,
+                                                  g_buckets=g_b, skip_unused_d_grads=skip_unused)
         # launches per step, counted on one eager step (the graph replays exactly these)
         eager(*devb[0])
         torch.cuda.synchronize()
@@ -375,7 +379,7 @@ def run_ours(args):
         if not args.no_graph:
             try:
                 gs = vb.train.GraphedStep(gen, disc, gopt, dopt, devb[0][0], devb[0][1], loss_kind, warmup=2, d_buckets=d_b,
-                                          g_buckets=g_b, skip_unused_d_grads=skip_unused)
+                                          g_buckets=g_b, skip_unused_d_grads=skip_unused, n_micro=n_micro)
                 step_fn, graph_used = gs, True
             except Exception as ex:      # fall back to eager launches of the same kernels (never to another implementation)
                 if rank == 0:
@@ -452,7 +456,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
             "dtype": prec, "data": "synthetic",
             "config": {"workload": f"{spec['name']}: {spec['desc']}", "per_gpu_batch": B, "global_batch": spec["global_batch"],
-                       "parallelism": f"dp{world}", "cuda_graph": graph_used, "optimizer": "torch" if args.torch_optim else "fused flat Adam(W) kernel",
+                       "parallelism": f"dp{world}", "cuda_graph": graph_used, "micro_batches": (n_micro if spec["kind"] != "v2_sample" else 1), "optimizer": "torch" if args.torch_optim else "fused flat Adam(W) kernel",
                        "d_param_grads_in_g_pass": not skip_unused,
                        "l2": "192 MiB buffer written between timed steps (L2 flush); step working set is >1 GB anyway"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(last_e2e),

@@ -339,26 +339,57 @@ def test_v1_full_grads_vs_oracle_64px(vb):
 
 
 def test_v2_200_step_loss_curve(vb):
-    """BASELINE.json: loss curves over 200 synthetic steps.  Default v2 model (E128 L6 H4 S65) at B=8, fp32 path, the
-    reference's own step sequence with torch AdamW, against the live CPU oracle (bit-exact to the reference).
-    GAN training is a chaotic map: rounding differences are amplified by Adam, so the curves are compared (a) tightly
-    over the first 20 steps and (b) on the smoothed trajectory over all 200."""
-    vb.set_precision("fp32")
+    """BASELINE.json: loss curves over 200 synthetic steps.  Default v2 model (E128 L6 H4 S65) at B=8, the reference's own
+    step sequence with torch AdamW.  Adversarial training + Adam is a chaotic map: ANY rounding difference grows
+    exponentially (the fp32 reference itself drifts from an fp64 run of the same code by 1e-3 after ~60 steps), so a fixed
+    1e-4 band over 200 steps is not a meaningful criterion.  Calibrated check, three trajectories:
+    CUDA fp32 path, CPU oracle fp32 (bit-exact to the reference), CPU oracle fp64:
+      (a) first 30 steps: CUDA within 1e-4 of the fp32 reference;
+      (b) all 200 steps: |CUDA - fp64| <= 10 x running-max |fp32 reference - fp64|  (we are as close to the exact
+          trajectory as the reference's own arithmetic is);
+      (c) bf16 path: finite, first 10 steps within 2e-2."""
     steps, B = 200, 8
     ocfg = o2.V2Config(batch_size=3 * 32 * 32)
-    orc = harness.OracleV2(ocfg, seed=0)
-    torch.manual_seed(0)
-    gan = vb.v2.ViTGAN(vb.v2.Config(batch_size=3 * 32 * 32)).cuda()
-    go = torch.optim.AdamW(gan.generator.parameters(), lr=5e-4, weight_decay=1e-3)
-    do = torch.optim.AdamW(gan.discriminator.parameters(), lr=5e-4, weight_decay=1e-3)
-    ref, got = [], []
-    for real, noise in harness.synthetic_batches_v2(ocfg, B, steps):
-        ref.append(torch.stack(orc.step(real, noise)))
-        got.append(torch.stack(vb.train.gan_step(gan.generator, gan.discriminator, go, do, real.cuda(), noise.cuda(), "ce")).cpu())
-    ref, got = torch.stack(ref), torch.stack(got)
-    assert torch.isfinite(got).all()
-    assert rel(got[:20], ref[:20]) < 1e-3
-    k = 20
-    smooth = lambda t: t.unfold(0, k, k).mean(-1)
-    assert rel(smooth(got), smooth(ref)) < 5e-2
+    batches = harness.synthetic_batches_v2(ocfg, B, steps)
+    orc32 = harness.OracleV2(ocfg, seed=0)
+    orc64 = harness.OracleV2(ocfg, seed=0, dtype=torch.float64)
+
+    def run_cuda(prec, n):
+        vb.set_precision(prec)
+        torch.manual_seed(0)
+        gan = vb.v2.ViTGAN(vb.v2.Config(batch_size=3 * 32 * 32)).cuda()
+        go = torch.optim.AdamW(gan.generator.parameters(), lr=5e-4, weight_decay=1e-3)
+        do = torch.optim.AdamW(gan.discriminator.parameters(), lr=5e-4, weight_decay=1e-3)
+        return torch.stack([torch.stack(vb.train.gan_step(gan.generator, gan.discriminator, go, do, r.cuda(), n_.cuda(), "ce")).cpu()
+                            for r, n_ in batches[:n]]).double()
+
+    f32 = torch.stack([torch.stack(orc32.step(r, n)) for r, n in batches]).double()
+    f64 = torch.stack([torch.stack(orc64.step(r.double(), n.double())) for r, n in batches])
+    gpu = run_cuda("fp32", steps)
+    assert torch.isfinite(gpu).all()
+    assert rel(gpu[:30], f32[:30]) < 1e-4
+    ref_dev = (f32 - f64).abs().amax(1).cummax(0).values          # running-max deviation of the fp32 reference from fp64
+    gpu_dev = (gpu - f64).abs().amax(1)
+    assert (gpu_dev <= 10 * ref_dev + 1e-5).all(), (gpu_dev / (ref_dev + 1e-12)).max()
+    bf = run_cuda("bf16", 40)
+    assert torch.isfinite(bf).all() and rel(bf[:10], f32[:10]) < 2e-2
+    vb.set_precision("bf16")
+
+
+def test_microbatched_step_equals_full_batch(vb, golden):
+    """Exact mean-gradient accumulation: 3 micro-batches of 1 == one batch of 3 (fp32 path, up to summation order)."""
+    vb.set_precision("fp32")
+    fx = golden("v2_tiny")
+    cfg = vb.v2.Config(**fx["config"])
+    ocfg = o2.V2Config(**fx["config"])
+    losses = {}
+    for n_micro in (1, 3):
+        gan = vb.v2.ViTGAN(cfg)
+        gan.load_state_dict(fx["params"])
+        gan = gan.cuda()
+        go = torch.optim.AdamW(gan.generator.parameters(), lr=5e-4, weight_decay=1e-3)
+        do = torch.optim.AdamW(gan.discriminator.parameters(), lr=5e-4, weight_decay=1e-3)
+        losses[n_micro] = torch.stack([torch.stack([t.reshape(()) for t in vb.train.gan_step_microbatched(
+            gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", n_micro=n_micro)]) for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
+    assert rel(losses[3], losses[1]) < 1e-4 and rel(losses[1], fx["losses"]) < 1e-4
     vb.set_precision("bf16")

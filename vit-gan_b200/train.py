@@ -197,6 +197,60 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
     return loss_real.detach(), loss_fake.detach(), loss_g.detach()
 
 
+def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", n_micro=1, d_buckets=None, g_buckets=None,
+                          skip_unused_d_grads=False):
+    """The same G+D iteration with the batch processed in `n_micro` equal chunks and exact mean-gradient accumulation
+    (each chunk's loss is scaled by 1/n_micro; no BatchNorm on the path, so the result equals the full-batch step up to
+    summation order).  Needed when the activations of the full batch do not fit (C4: global batch 2048 on one GPU).
+
+    Phase D: per chunk  D(real) bwd, G(noise) without grad -> fake, D(fake) bwd;  then one D optimizer step.
+    Phase G: per chunk  G(noise) with grad (G is unchanged, so this is the same fake), D(fake) bwd;  then one G step.
+    Cost vs. the un-chunked step: one extra generator forward."""
+    if n_micro == 1:
+        return gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind, d_buckets, g_buckets, skip_unused_d_grads)
+    b, dev = real.shape[0], real.device
+    assert b % n_micro == 0, "batch must be divisible by n_micro"
+    mb = b // n_micro
+    if loss_kind == "ce":
+        ones, zeros, crit = torch.ones(mb, dtype=torch.long, device=dev), torch.zeros(mb, dtype=torch.long, device=dev), F.cross_entropy
+    else:
+        ones, zeros, crit = torch.ones(mb, 1, device=dev), torch.zeros(mb, 1, device=dev), F.binary_cross_entropy
+    inv = 1.0 / n_micro
+    zg = lambda opt: opt.zero_grad(set_to_none=False) if isinstance(opt, FusedAdam) else opt.zero_grad(set_to_none=True)
+    zg(disc_opt)
+    l_real = l_fake = l_g = 0.0
+    for i in range(n_micro):
+        r, z = real[i * mb:(i + 1) * mb], noise[i * mb:(i + 1) * mb]
+        loss = crit(disc(r).float(), ones) * inv
+        loss.backward()
+        l_real = l_real + loss.detach()
+        with torch.no_grad():
+            fake = gen(z)
+        if d_buckets is not None and i == n_micro - 1:
+            d_buckets.arm()
+        loss = crit(disc(fake).float(), zeros) * inv
+        loss.backward()
+        l_fake = l_fake + loss.detach()
+    if d_buckets is not None:
+        d_buckets.finish()
+    disc_opt.step()
+    zg(gen_opt)
+    for i in range(n_micro):
+        z = noise[i * mb:(i + 1) * mb]
+        if g_buckets is not None and i == n_micro - 1:
+            g_buckets.arm()
+        fake = gen(z)
+        with Fn.skip_param_grads(skip_unused_d_grads):
+            out = disc(fake)
+        loss = crit(out.float(), ones) * inv
+        loss.backward()
+        l_g = l_g + loss.detach()
+    if g_buckets is not None:
+        g_buckets.finish()
+    gen_opt.step()
+    return l_real, l_fake, l_g
+
+
 class GraphedStep:
     """Whole-step CUDA graph: the ~600 kernel launches of one G+D iteration are captured once and replayed
     with one cudaGraphLaunch (the small-E configs are launch-bound).  Inputs are copied
@@ -206,16 +260,19 @@ class GraphedStep:
         self.real, self.noise = real.clone(), noise.clone()
         self.args = (gen, disc, gen_opt, disc_opt)
         self.kw = dict(loss_kind=loss_kind, **kw)
+        step = gan_step_microbatched if kw.get("n_micro", 1) > 1 else gan_step
+        if step is gan_step:
+            self.kw.pop("n_micro", None)
         Fn.set_operand_cache(False)        # casts/packs must be part of the captured work
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                gan_step(*self.args, self.real, self.noise, **self.kw)
+                step(*self.args, self.real, self.noise, **self.kw)
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.losses = gan_step(*self.args, self.real, self.noise, **self.kw)
+            self.losses = step(*self.args, self.real, self.noise, **self.kw)
 
     def __call__(self, real, noise):
         self.real.copy_(real, non_blocking=True)
