@@ -468,10 +468,18 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured CUDA graphs hold NCCL work objects; tearing the communicator down underneath them deadlocks
+        # (observed at N=2).  Everything has been synchronised and printed: leave without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
+    import faulthandler
+    if os.environ.get("VG_BENCH_WATCHDOG"):      # debugging aid: dump all Python stacks if the run stalls
+        faulthandler.dump_traceback_later(int(os.environ["VG_BENCH_WATCHDOG"]), repeat=False, exit=True)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
