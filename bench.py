@@ -301,6 +301,8 @@ def run_ours(args):
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("WARN", "VERSION"):
+            os.environ.pop("NCCL_DEBUG")          # NCCL would print its version banner on stdout, ahead of the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import vitgan_b200 as vb
     from oracle import harness, v1 as o1, v2 as o2      # synthetic data generator + FLOP formulas + cpu_baseline leg only
@@ -443,7 +445,7 @@ def run_ours(args):
         value, e2e_value = imgs / (ms * 1e-3), imgs / (ms_e2e * 1e-3)
         fl = step_flops_per_image(spec, skip_unused)
         step_tf = value * fl / world / 1e12          # per GPU
-        roof, all_k = kernel_rooflines(vb, spec, pk) if (world == 1 and not args.no_roofline) else (None, [])
+        roof, all_k = kernel_rooflines(vb, spec, pk) if not args.no_roofline else (None, [])   # rank 0; the others wait at the barrier
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_oracle_rate(spec, seconds_budget=25.0, steps=2, warmup=1)

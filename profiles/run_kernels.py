@@ -1,0 +1,29 @@
+"""Launch each hot kernel ONCE at the C2 shapes (B=512, S=65, E=128, H=4) so that `ncu --set full` can capture them:
+   ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|attn_.*_tc|ln_' -o gpurun_out/prof python profiles/run_kernels.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vitgan_b200 as vb  # noqa: E402
+
+B, S, E, H, m = 512, 65, 128, 4, 2
+M, d = B * S, E // H
+L, bf, dev = vb.lib, torch.bfloat16, "cuda"
+mk = lambda *s: torch.randn(*s, device=dev).to(bf)
+x, qkv, wqkv, w1 = mk(M, E), mk(M, 3 * E), mk(3 * E, E), mk(m * E, E)
+bq, b1 = torch.randn(3 * E, device=dev), torch.randn(m * E, device=dev)
+gam, bet = torch.ones(E, device=dev), torch.zeros(E, device=dev)
+for rep in range(2):      # first pass warms caches/lazy init; ncu is told to skip it (-s) or simply profiles both
+    vb.ops.gemm(x, wqkv, bias=bq, path=L.GEMM_TCGEN05)                                        # fwd qkv
+    vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)           # fwd fc1 + gelu
+    vb.ops.gemm(qkv, wqkv, trans_b=False, path=L.GEMM_TCGEN05)                                # dgrad qkv
+    vb.ops.gemm(qkv, x, trans_a=True, trans_b=False, accumulate=True, path=L.GEMM_TCGEN05)    # wgrad qkv
+    o, lse = vb.ops.attention_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, H, S, d, d ** -0.5)
+    vb.ops.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], o, o, lse, B, H, S, d, d ** -0.5)
+    y, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)
+    vb.ops.layernorm_bwd(x, x, mean, rstd, gam, dres=x)
+torch.cuda.synchronize()
+print("ok")
