@@ -89,8 +89,11 @@ int vg_gemm(const vg_gemm_args* args, void* stream);
 int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
                   const float* num, const float* den, void* stream);
 
-/* out[n] (+)= sum_m x[m,n]   (bias gradients; fp32 out, atomically accumulated: zero it first) */
-int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, void* stream);
+/* out[n] += sum_m x[m,n]   (bias gradients; fp32 out, accumulated: zero it first).
+ * workspace (optional): [ws_rows, N] fp32 scratch + a zero-initialised `counter`: CTA partial sums are combined by the last
+ * CTA (deterministic, no same-address atomics); without it the kernel falls back to global atomics. */
+int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, float* workspace, int ws_rows,
+              unsigned* counter, void* stream);
 
 /* LayerNorm over the last dim (eps 1e-5, biased variance, affine): src/v2/modules.py:168,172,225;
  * src/v1/transformer.py:18-19.  Saves mean / rstd per row for the backward. */
@@ -101,7 +104,8 @@ int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, const float*
  * produced `dx` -- the bias gradients of the Linear layers on either side of the norm, computed here for free. */
 int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
                      const float* rstd, const float* gamma, const void* dres, void* dx,
-                     float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum, void* stream);
+                     float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
+                     float* workspace /* [ws_rows, 4*E] fp32 or NULL */, int ws_rows, unsigned* counter, void* stream);
 
 /* Self-modulated LayerNorm  y = w * (gamma_s * (LN(h)*g + b) + beta_s)  (src/v1/spectral_layer_norm.py:19-20).
  * h has h_rows rows (h_rows == rows, or rows % h_rows == 0 for the first G layer where h is (S,F) and

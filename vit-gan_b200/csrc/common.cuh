@@ -138,6 +138,33 @@ __device__ __forceinline__ int64_t res_row(int m, int mod, int off) {
   return mod > 0 ? (int64_t)(m % mod) + off : (int64_t)m;
 }
 
+// ---------------------------------------------------------------- cross-CTA column reduction without atomics
+// Each CTA deposits `ncols` partial sums in its row of a workspace; the last CTA to finish (ticket counter) adds all
+// rows, in a fixed order, into `out` (+=).  Replaces gridDim same-address atomics per column (measured ~70 ns each when
+// serialised at one L2 address: 20 us for 296 CTAs) by one coalesced pass, and makes the result deterministic.
+// `counter` must be 0 on entry and is reset to 0 by the last CTA.  Call with all threads of the CTA.
+__device__ __forceinline__ void cta_partials_reduce(float* __restrict__ ws, unsigned* __restrict__ counter,
+                                                    const float* __restrict__ smem_vals, int ncols, float* const* outs,
+                                                    const int* out_offsets, int n_outs) {
+  __shared__ unsigned s_ticket;
+  float* mine = ws + (size_t)blockIdx.x * ncols;
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) mine[i] = smem_vals[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+    float acc = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(ws + (size_t)b * ncols + i);
+    int o = 0;
+    while (o + 1 < n_outs && i >= out_offsets[o + 1]) ++o;       // which output array this column belongs to
+    if (outs[o] != nullptr) outs[o][i - out_offsets[o]] += acc;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
 // launchers implemented per translation unit
 int gemm_simt_launch(const vg_gemm_args& a, cudaStream_t st);
 int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st);

@@ -37,13 +37,15 @@ __global__ void cast_scale_kernel(const TS* __restrict__ src, TD* __restrict__ d
 // and the rows m0+ty, m0+ty+8, ...; a warp reads 512 contiguous bytes per row; 4 rows in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_vec_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* __restrict__ out, int64_t rows_per_cta) {
+colsum_vec_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* __restrict__ out, int64_t rows_per_cta,
+                  float* __restrict__ ws, unsigned* __restrict__ counter) {
   constexpr int V = 16 / sizeof(T);
   __shared__ float red[8][32][V + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int cg = blockIdx.x * 32 + tx;                 // column group
+  const bool wsmode = ws != nullptr;                   // workspace mode: 1-D grid over row slices, one 32-group column slab
+  const int cg = (wsmode ? 0 : blockIdx.x * 32) + tx;  // column group
   const int n0 = cg * V;
-  const int64_t m0 = (int64_t)blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  const int64_t m0 = (int64_t)(wsmode ? blockIdx.x : blockIdx.y) * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
   float acc[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.f;
@@ -70,6 +72,23 @@ colsum_vec_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* 
 #pragma unroll
   for (int j = 0; j < V; ++j) red[ty][tx][j] = acc[j];
   __syncthreads();
+  if (ws != nullptr) {      // 1-D grid over row slices, all N columns per CTA (N <= 32*V): partials + last-CTA reduction
+    __shared__ float s_cols[32 * V];
+    if (ty == 0) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][tx][j];
+        s_cols[tx * V + j] = s;
+      }
+    }
+    __syncthreads();
+    float* outs[1] = {out};
+    const int offs[1] = {0};
+    cta_partials_reduce(ws, counter, s_cols, N, outs, offs, 1);
+    return;
+  }
   if (ty == 0 && n0 < N) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -191,19 +210,29 @@ extern "C" int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_
   return check_launch("cast_scale");
 }
 
-extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, void* stream) {
+extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, float* workspace, int ws_rows,
+                         unsigned* counter, void* stream) {
   if (M == 0 || N == 0) return VG_OK;
   const int V = dtype == VG_F32 ? 4 : 8;
   const bool vec = (N % V == 0) && (ldx % V == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  cudaStream_t st = as_stream(stream);
+  if (vec && workspace && counter && ws_rows >= 1 && N <= 32 * V) {
+    // contention-free path: blockIdx.x = row slice; workspace = [ws_rows][N] floats
+    int ys = (int)max((int64_t)1, min((int64_t)min(ws_rows, 2 * num_sms()), (M + 63) / 64));
+    const int64_t rows_per_cta = (M + ys - 1) / ys;
+    ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
+    if (dtype == VG_F32) colsum_vec_kernel<float><<<dim3(ys, 1), 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, workspace, counter);
+    else colsum_vec_kernel<bf16><<<dim3(ys, 1), 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, workspace, counter);
+    return check_launch("colsum");
+  }
   const int xs = vec ? (N / V + 31) / 32 : (N + 31) / 32;
   int ys = (int)max((int64_t)1, min((M + 127) / 128, (int64_t)(4 * num_sms() + xs - 1) / xs));
   const int64_t rows_per_cta = (M + ys - 1) / ys;
   ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
   dim3 grid(xs, ys);
-  cudaStream_t st = as_stream(stream);
   if (vec) {
-    if (dtype == VG_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta);
-    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta);
+    if (dtype == VG_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, nullptr, nullptr);
+    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, nullptr, nullptr);
   } else {
     if (dtype == VG_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta);
     else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta);

@@ -30,7 +30,8 @@ constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STG_BYTES = 8192;         // per epilogue warp: two 4 KB swizzled staging tiles (32 rows x 128 B each)
-constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int BIAS_BYTES = EPI_WARPS * 64 * 4;   // per epilogue warp: the 64 bias values of its column slab
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int TMEM_COLS = NACC * BN;   // 256: power of two >= 32
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -158,7 +159,7 @@ struct Params {
   int epi_tma;                         // 1: smem-staged epilogue with TMA loads (residual/aux) and TMA stores / reduce-add
 };
 
-template <typename TC, int ACT>
+template <typename TC>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&r)[32], int m, int n0) {
   // one thread = one output row m, 32 consecutive columns n0..n0+31
   const int64_t orow = out_row(m, p.c_row_group);
@@ -193,11 +194,11 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
     }
     if (vec_ok) {
       if (cpre) Vec4<TC>::store(cpre + c, v);
-      if (ACT != VG_ACT_NONE) {
+      if (p.act != VG_ACT_NONE) {
         float a[4] = {0.f, 0.f, 0.f, 0.f};
         if (aux) Vec4<TC>::load(aux + c, a);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = act_t<ACT, true>(v[j], a[j], p.act_param);
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(p.act, v[j], a[j], p.act_param);
       }
       if (res) {
         float t[4];
@@ -213,7 +214,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
           float x = v[j];
           if (cpre) cpre[c + j] = from_f<TC>(x);
           const float a = aux ? to_f<TC>(aux[c + j]) : 0.f;
-          x = act_t<ACT, true>(x, a, p.act_param);
+          x = apply_act(p.act, x, a, p.act_param);
           if (res) x += to_f<TC>(res[c + j]);
           C[c + j] = from_f<TC>(x);
         }
@@ -229,7 +230,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 // bufC holds the residual tile on entry (if any) and the output on exit; bufX holds aux on entry or c_pre on exit.
 template <bool F32, int ACT>
 __device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r)[32], int lane, int cc, int n0,
-                                             uint32_t bufC, uint32_t bufX) {
+                                             uint32_t bufC, uint32_t bufX, const float* __restrict__ bias_s) {
   const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
   if (F32) {
@@ -241,9 +242,9 @@ __device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r
       for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[g * 4 + j]);
       const uint32_t addr = base + (((uint32_t)g ^ sw) << 4);
       if (!p.accumulate) {
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { const int n = n0 + g * 4 + j; v[j] += (n < p.N) ? __ldg(p.bias + n) : 0.f; }
+        if (p.bias) {      // bias_s: this warp's 64 bias values, staged in smem at the start of the tile (broadcast reads)
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + cc * 32 + g * 4);
+          v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
         }
         if (ACT != VG_ACT_NONE) {
 #pragma unroll
@@ -265,8 +266,9 @@ __device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r
       for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
       const uint32_t off = row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4);
       if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const int n = n0 + h * 8 + j; v[j] += (n < p.N) ? __ldg(p.bias + n) : 0.f; }
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + h * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + h * 8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
       float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (has_aux) {
@@ -291,6 +293,10 @@ __device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r
   }
 }
 
+// MODE 0: direct epilogue (row remaps / unaligned outputs; activation switched at run time)
+// MODE 1: staged TMA epilogue, bf16 output, activation ACT fixed at compile time
+// MODE 2: staged TMA epilogue, fp32 output (plain or split-K reduce-add), no activation
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
@@ -299,7 +305,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + NSTAGES * STAGE_BYTES;          // 1024-aligned (stage bytes are multiples of 1024)
-  const uint32_t bar_base = stg_base + EPI_WARPS * STG_BYTES;
+  const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;
+  const uint32_t bar_base = bias_base + BIAS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + a); };
@@ -399,11 +406,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access (warp id % 4)
     const int half = ew >> 2;              // which 64-column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
-    if (p.epi_tma) {
+    if (MODE != 0) {
       const uint32_t bufC = stg_base + (uint32_t)ew * STG_BYTES, bufX = bufC + 4096u;
       const uint32_t wbar = warp_bar(ew);
       uint32_t wphase = 0;
-      const bool f32 = p.c_is_f32 != 0;
+      constexpr bool f32 = MODE == 2;
+      float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
       const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
@@ -411,6 +419,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // staging tiles are free once the previous tile's bulk stores have READ them
         if (lane == 0) tma_wait_read();
         __syncwarp();
+        if (p.bias) {                               // stage this warp's 64 bias values (previous tile's readers are past them)
+          const int c0 = n0 + lane, c1 = n0 + 32 + lane;
+          bias_s[lane] = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
+          bias_s[32 + lane] = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
+          __syncwarp();
+        }
         if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
           mbar_expect_tx(wbar, (has_res ? (f32 ? 8192u : 4096u) : 0u) + (has_aux ? 4096u : 0u));
           if (has_res) {
@@ -431,11 +445,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator is in registers: release TMEM to the MMA warp
         if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
         if (!(p.dbg & 1)) {
-          if (f32) {
-            VG_ACT_SWITCH(p.act, (staged_chunk<true, ACT>(p, r0, lane, 0, n0, bufC, bufX), staged_chunk<true, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX)))
-          } else {
-            VG_ACT_SWITCH(p.act, (staged_chunk<false, ACT>(p, r0, lane, 0, n0, bufC, bufX), staged_chunk<false, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX)))
-          }
+          staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
+          staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
           fence_async_smem();                  // generic-proxy smem writes -> visible to the async (TMA) proxy
           __syncwarp();
           if (lane == 0 && m0 < p.M && n0 < p.N) {
@@ -468,8 +479,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col), r);
           const int n0 = n_blk * BN + col;
           if (m < p.M && n0 < p.N && !(p.dbg & 1)) {
-            if (p.c_is_f32) { VG_ACT_SWITCH(p.act, (epilogue_chunk<float, ACT>(p, r, m, n0))) }
-            else { VG_ACT_SWITCH(p.act, (epilogue_chunk<bf16, ACT>(p, r, m, n0))) }
+            if (p.c_is_f32) epilogue_chunk<float>(p, r, m, n0);
+            else epilogue_chunk<bf16>(p, r, m, n0);
           }
         }
         tc_fence_before();
@@ -537,12 +548,6 @@ bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
 }
 
 int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   CUtensorMap ma, mb;
   int rc;
   // A: trans_a=0 stored [M,K] -> box {64 k, 128 m};  trans_a=1 stored [K,M] -> box {64 m, 64 k}
@@ -582,7 +587,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   auto tma_ok = [&](const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0; };
   p.epi_tma = !(p.dbg & 2) && a.c_row_group == 0 && a.res_row_mod == 0 && tma_ok(a.C, a.ldc) &&
               (!a.residual || tma_ok(a.residual, a.ldres)) && (!a.aux || tma_ok(a.aux, a.ldaux)) &&
-              (!a.c_pre || tma_ok(a.c_pre, a.ldpre)) && !(f32 && (a.aux || a.c_pre));
+              (!a.c_pre || tma_ok(a.c_pre, a.ldpre)) && !(f32 && (a.aux || a.c_pre || a.act != VG_ACT_NONE));
   CUtensorMap mc = ma, mp = ma, mr = ma, mx = ma;     // placeholders when unused
   if (p.epi_tma) {
     const int bc = f32 ? 32 : 64;                      // 128-byte wide boxes, 32 rows
@@ -593,7 +598,21 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(total, sms);
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, mc, mp, mr, mx, p);
+  const int mode = !p.epi_tma ? 0 : (f32 ? 2 : 1);
+#define VG_TC_LAUNCH(MODE_, ACT_)                                                                                              \
+  do {                                                                                                                         \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
+      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                 \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    gemm_tc_kernel<MODE_, ACT_><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, mc, mp, mr, mx, p);                                \
+  } while (0)
+  if (mode == 0) VG_TC_LAUNCH(0, 0);
+  else if (mode == 2) VG_TC_LAUNCH(2, 0);
+  else { VG_ACT_SWITCH(a.act, VG_TC_LAUNCH(1, ACT)) }
+#undef VG_TC_LAUNCH
   return check_launch("gemm_tc");
 }
 

@@ -250,7 +250,11 @@ class LinearFn(Function):
         w = packed([weight], cdt)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm(dy2, w, trans_b=False, out_dtype=cdt)
+            if cdt == torch.float32 and w.shape[1] * 16 <= w.shape[0]:
+                # tiny fan-in (G head 10 -> 3072): dX[M,10] = dY[M,3072] W has 8 output tiles and a long K: split-K
+                dx = ops.gemm(dy2, w, trans_b=False, accumulate=True)
+            else:
+                dx = ops.gemm(dy2, w, trans_b=False, out_dtype=cdt)
             if dx.dtype != xdtype:
                 dx = ops.cast(dx, xdtype)
             dx = dx.reshape(xshape)

@@ -38,9 +38,9 @@ SIGNATURES = {
     "vg_device_is_sm100": [],
     "vg_gemm": [C.POINTER(GemmArgs), vp],
     "vg_cast_scale": [vp, i32, vp, i32, i64, vp, vp, vp],
-    "vg_colsum": [vp, i32, i64, i32, i64, vp, vp],
+    "vg_colsum": [vp, i32, i64, i32, i64, vp, vp, i32, vp, vp],
     "vg_layernorm_fwd": [i32, i64, i32, vp, vp, vp, vp, vp, vp, f32, vp],
-    "vg_layernorm_bwd": [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "vg_layernorm_bwd": [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
     "vg_sln_fwd": [i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp],
     "vg_sln_bwd": [i32, i64, i64, i32] + [vp] * 17,
     "vg_attention_fwd": [i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, i64, vp, f32, vp],
