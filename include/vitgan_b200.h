@@ -90,8 +90,9 @@ int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int6
                   const float* num, const float* den, void* stream);
 
 /* out[n] += sum_m x[m,n]   (bias gradients; fp32 out, accumulated: zero it first).
- * workspace (optional): [ws_rows, N] fp32 scratch + a zero-initialised `counter`: CTA partial sums are combined by the last
- * CTA (deterministic, no same-address atomics); without it the kernel falls back to global atomics. */
+ * workspace (optional): persistent ZERO-INITIALISED [ws_rows = R, N] fp32 replicated accumulators + a zero-initialised
+ * ticket `counter`: CTA partial sums go to row blockIdx %% R (same-address atomic contention / R), the last CTA folds the R
+ * rows into `out` and re-zeroes them and the counter.  Without it the kernel falls back to direct global atomics. */
 int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, float* workspace, int ws_rows,
               unsigned* counter, void* stream);
 
@@ -105,7 +106,7 @@ int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, const float*
 int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
                      const float* rstd, const float* gamma, const void* dres, void* dx,
                      float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
-                     float* workspace /* [ws_rows, 4*E] fp32 or NULL */, int ws_rows, unsigned* counter, void* stream);
+                     float* workspace /* persistent zeroed [ws_rows = R, 4*E] fp32 or NULL */, int ws_rows, unsigned* counter, void* stream);
 
 /* Self-modulated LayerNorm  y = w * (gamma_s * (LN(h)*g + b) + beta_s)  (src/v1/spectral_layer_norm.py:19-20).
  * h has h_rows rows (h_rows == rows, or rows % h_rows == 0 for the first G layer where h is (S,F) and

@@ -138,17 +138,21 @@ __device__ __forceinline__ int64_t res_row(int m, int mod, int off) {
   return mod > 0 ? (int64_t)(m % mod) + off : (int64_t)m;
 }
 
-// ---------------------------------------------------------------- cross-CTA column reduction without atomics
-// Each CTA deposits `ncols` partial sums in its row of a workspace; the last CTA to finish (ticket counter) adds all
-// rows, in a fixed order, into `out` (+=).  Replaces gridDim same-address atomics per column (measured ~70 ns each when
-// serialised at one L2 address: 20 us for 296 CTAs) by one coalesced pass, and makes the result deterministic.
-// `counter` must be 0 on entry and is reset to 0 by the last CTA.  Call with all threads of the CTA.
-__device__ __forceinline__ void cta_partials_reduce(float* __restrict__ ws, unsigned* __restrict__ counter,
-                                                    const float* __restrict__ smem_vals, int ncols, float* const* outs,
-                                                    const int* out_offsets, int n_outs) {
+// ---------------------------------------------------------------- cross-CTA column reduction with bounded contention
+// gridDim CTAs each hold `ncols` partial sums in smem.  Same-address global atomics serialise at the L2 (~70 ns each,
+// measured: 296 CTAs on one address = 20 us), so the partials go to one of R replicated accumulator rows
+// (row = blockIdx % R -> contention gridDim/R), and the LAST CTA to finish (ticket counter) folds the R rows into
+// `out` (+=) in a fixed order and re-zeroes them.  ws = persistent zero-initialised [R][ncols] scratch, `counter`
+// a zero-initialised ticket; both are left zeroed for the next call.  Call with all threads of the CTA.
+__device__ __forceinline__ void cta_replica_reduce(float* __restrict__ ws, int R, unsigned* __restrict__ counter,
+                                                   const float* __restrict__ smem_vals, int ncols, float* const* outs,
+                                                   const int* out_offsets, int n_outs) {
   __shared__ unsigned s_ticket;
-  float* mine = ws + (size_t)blockIdx.x * ncols;
-  for (int i = threadIdx.x; i < ncols; i += blockDim.x) mine[i] = smem_vals[i];
+  float* mine = ws + (size_t)(blockIdx.x % R) * ncols;
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+    const float v = smem_vals[i];
+    if (v != 0.f) atomicAdd(mine + i, v);
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
@@ -157,7 +161,7 @@ __device__ __forceinline__ void cta_partials_reduce(float* __restrict__ ws, unsi
   __threadfence();
   for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
     float acc = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(ws + (size_t)b * ncols + i);
+    for (int r = 0; r < R; ++r) { acc += __ldcg(ws + (size_t)r * ncols + i); ws[(size_t)r * ncols + i] = 0.f; }
     int o = 0;
     while (o + 1 < n_outs && i >= out_offsets[o + 1]) ++o;       // which output array this column belongs to
     if (outs[o] != nullptr) outs[o][i - out_offsets[o]] += acc;

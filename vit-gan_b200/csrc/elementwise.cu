@@ -38,7 +38,7 @@ __global__ void cast_scale_kernel(const TS* __restrict__ src, TD* __restrict__ d
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* __restrict__ out, int64_t rows_per_cta,
-                  float* __restrict__ ws, unsigned* __restrict__ counter) {
+                  float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
   constexpr int V = 16 / sizeof(T);
   __shared__ float red[8][32][V + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -86,7 +86,7 @@ colsum_vec_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* 
     __syncthreads();
     float* outs[1] = {out};
     const int offs[1] = {0};
-    cta_partials_reduce(ws, counter, s_cols, N, outs, offs, 1);
+    cta_replica_reduce(ws, ws_rows, counter, s_cols, N, outs, offs, 1);
     return;
   }
   if (ty == 0 && n0 < N) {
@@ -217,12 +217,12 @@ extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx
   const bool vec = (N % V == 0) && (ldx % V == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   cudaStream_t st = as_stream(stream);
   if (vec && workspace && counter && ws_rows >= 1 && N <= 32 * V) {
-    // contention-free path: blockIdx.x = row slice; workspace = [ws_rows][N] floats
-    int ys = (int)max((int64_t)1, min((int64_t)min(ws_rows, 2 * num_sms()), (M + 63) / 64));
+    // low-contention path: blockIdx.x = row slice; workspace = persistent zeroed [ws_rows = R][N] replicated accumulators
+    int ys = (int)max((int64_t)1, min((int64_t)(2 * num_sms()), (M + 63) / 64));
     const int64_t rows_per_cta = (M + ys - 1) / ys;
     ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
-    if (dtype == VG_F32) colsum_vec_kernel<float><<<dim3(ys, 1), 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, workspace, counter);
-    else colsum_vec_kernel<bf16><<<dim3(ys, 1), 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, workspace, counter);
+    if (dtype == VG_F32) colsum_vec_kernel<float><<<dim3(ys, 1), 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, workspace, ws_rows, counter);
+    else colsum_vec_kernel<bf16><<<dim3(ys, 1), 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, workspace, ws_rows, counter);
     return check_launch("colsum");
   }
   const int xs = vec ? (N / V + 31) / 32 : (N + 31) / 32;
@@ -231,8 +231,8 @@ extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx
   ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
   dim3 grid(xs, ys);
   if (vec) {
-    if (dtype == VG_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, nullptr, nullptr);
-    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, nullptr, nullptr);
+    if (dtype == VG_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, nullptr, 0, nullptr);
+    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, nullptr, 0, nullptr);
   } else {
     if (dtype == VG_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta);
     else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta);

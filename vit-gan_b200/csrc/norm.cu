@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dres_colsum, float* __restrict__ dx_colsum, float* __restrict__ ws, unsigned* __restrict__ counter) {
+              float* __restrict__ dres_colsum, float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
   // dres_colsum / dx_colsum (optional): column sums of the skip-path gradient and of the produced dx -- these are the
   // bias gradients of the Linear layers on either side of the norm (fc2 / out-proj), obtained here for free.
   constexpr int RPI = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
@@ -170,7 +170,7 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
     }
   }
   if (ws != nullptr) {
-    // workspace path: CTA partials for [dgamma | dbeta | colsum(dres) | colsum(dx)] -> last CTA reduces (no global atomics)
+    // workspace path: [dgamma | dbeta | colsum(dres) | colsum(dx)] -> replicated accumulators, folded by the last CTA
     __shared__ float s_all[4 * MAXE];
     for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) s_all[i] = 0.f;
     __syncthreads();
@@ -181,7 +181,7 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
     __syncthreads();
     float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
     const int offs[4] = {0, E, 2 * E, 3 * E};
-    cta_partials_reduce(ws, counter, s_all, 4 * E, outs, offs, 4);
+    cta_replica_reduce(ws, ws_rows, counter, s_all, 4 * E, outs, offs, 4);
     return;
   }
   flush_cols(s_dg, dgamma, adg, E, lane);
@@ -379,13 +379,12 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
   VG_REQUIRE(!(workspace && (!counter || ws_rows < 1)), VG_ERR_ARG, "layernorm_bwd: workspace needs a counter and ws_rows >= 1");
   if (rows == 0) return VG_OK;
   int grid = grid_for_rows((rows + 3) / 4, 2);   // 2 CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
-  if (workspace) grid = min(grid, ws_rows);        // workspace = [ws_rows][4*E] floats
   if (dtype == VG_F32)
     VG_NV_DISPATCH(E, (ln_bwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
-                                                                      (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, counter)));
+                                                                      (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)));
   else
     VG_NV_DISPATCH(E, (ln_bwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
-                                                                     (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, counter)));
+                                                                     (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)));
   return check_launch("layernorm_bwd");
 }
 

@@ -29,19 +29,22 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# scratch for the contention-free column reductions (CTA partials + last-CTA combine): a persistent zeroed ticket
-# counter per device (kernels reset it themselves) and a per-call partials buffer from torch's caching allocator
-_counters: dict = {}
-_ws_rows: dict = {}
+# scratch for the low-contention column reductions (see cta_replica_reduce in csrc/common.cuh): per device one
+# persistent ZEROED buffer of R replicated accumulator rows and a zeroed ticket counter; kernels leave both zeroed.
+_REPLICAS = 16
+_MAX_COLS = 4 * 1024
+_scratch: dict = {}
 
 
 def _reduce_scratch(device, ncols):
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    if idx not in _counters:
-        _counters[idx] = torch.zeros(16, dtype=torch.int32, device=device)
-        _ws_rows[idx] = 2 * torch.cuda.get_device_properties(idx).multi_processor_count
-    rows = _ws_rows[idx]
-    return torch.empty(rows * ncols, dtype=torch.float32, device=device), rows, _counters[idx]
+    sc = _scratch.get(idx)
+    if sc is None:
+        sc = (torch.zeros(_REPLICAS * _MAX_COLS, dtype=torch.float32, device=device), torch.zeros(16, dtype=torch.int32, device=device))
+        _scratch[idx] = sc
+    if ncols > _MAX_COLS:
+        return None, 0, sc[1]
+    return sc[0], _REPLICAS, sc[1]
 
 
 def dt(t: torch.Tensor) -> int:
@@ -130,7 +133,7 @@ def colsum(x2d: torch.Tensor, out=None):
     if out is None:
         out = torch.zeros(x2d.shape[1], dtype=torch.float32, device=x2d.device)
     ws, ws_rows, counter = _reduce_scratch(x2d.device, x2d.shape[1])
-    check(lib.vg_colsum(x2d.data_ptr(), dt(x2d), x2d.shape[0], x2d.shape[1], ld, out.data_ptr(), ws.data_ptr(), ws_rows,
+    check(lib.vg_colsum(x2d.data_ptr(), dt(x2d), x2d.shape[0], x2d.shape[1], ld, out.data_ptr(), _ptr(ws), ws_rows,
                         counter.data_ptr(), stream()), "vg_colsum")
     _count()
     return out
@@ -160,7 +163,7 @@ def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbet
     ws, ws_rows, counter = _reduce_scratch(x2d.device, 4 * e)
     check(lib.vg_layernorm_bwd(dt(x2d), rows, e, dy2d.data_ptr(), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                gamma.data_ptr(), _ptr(dres), dx.data_ptr(), dgamma_acc.data_ptr(), dbeta_acc.data_ptr(), _ptr(dres_colsum),
-                               _ptr(dx_colsum), ws.data_ptr(), ws_rows, counter[4:].data_ptr(), stream()),
+                               _ptr(dx_colsum), _ptr(ws), ws_rows, counter[4:].data_ptr(), stream()),
           "vg_layernorm_bwd")
     _count()
     return dx, dgamma_acc, dbeta_acc
