@@ -1,5 +1,6 @@
 // api.cu -- C-ABI glue: error state, device queries, vg_gemm dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +24,12 @@ int check_launch(const char* what) {
     return VG_ERR_LAUNCH;
   }
   return VG_OK;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VG_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
 }
 
 int num_sms() {

@@ -153,6 +153,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
   const int total = g.B * g.groups;
   const int nk_steps = g.NK / 16;
 
@@ -304,7 +306,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (threadIdx.x == 64) tma_wait_read();
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    if (threadIdx.x == 64) tma_wait_all();
+    if (threadIdx.x == 64) tma_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -354,6 +356,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
   const int total = g.B * g.groups;
   const int nk_steps = g.NK / 16;
 
@@ -500,7 +504,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
       }
     }
-    if (threadIdx.x == 64) tma_wait_all();
+    if (threadIdx.x == 64) tma_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -573,11 +577,11 @@ int attention_fwd_tc(int B, int H, int S, int d, const void* q, const void* k, c
   if (d == 32) {
     static bool set = false;
     if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
-    attn_fwd_tc_kernel<32><<<grid, NTHREADS, FWD_SMEM, st>>>(mq, mk, mv, mo, g);
+    launch_pdl(attn_fwd_tc_kernel<32>, dim3(grid), dim3(NTHREADS), FWD_SMEM, st, mq, mk, mv, mo, g);
   } else {
     static bool set = false;
     if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
-    attn_fwd_tc_kernel<64><<<grid, NTHREADS, FWD_SMEM, st>>>(mq, mk, mv, mo, g);
+    launch_pdl(attn_fwd_tc_kernel<64>, dim3(grid), dim3(NTHREADS), FWD_SMEM, st, mq, mk, mv, mo, g);
   }
   return check_launch("attention_fwd_tc");
 }
@@ -599,11 +603,11 @@ int attention_bwd_tc(int B, int H, int S, int d, const void* q, const void* k, c
   if (d == 32) {
     static bool set = false;
     if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<32>()) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
-    attn_bwd_tc_kernel<32><<<grid, NTHREADS, bwd_smem<32>(), st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, g);
+    launch_pdl(attn_bwd_tc_kernel<32>, dim3(grid), dim3(NTHREADS), bwd_smem<32>(), st, mq, mk, mv, mdo, mdq, mdk, mdv, g);
   } else {
     static bool set = false;
     if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<64>()) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
-    attn_bwd_tc_kernel<64><<<grid, NTHREADS, bwd_smem<64>(), st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, g);
+    launch_pdl(attn_bwd_tc_kernel<64>, dim3(grid), dim3(NTHREADS), bwd_smem<64>(), st, mq, mk, mv, mdo, mdq, mdk, mdv, g);
   }
   return check_launch("attention_bwd_tc");
 }

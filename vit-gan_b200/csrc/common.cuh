@@ -24,6 +24,26 @@ int check_launch(const char* what);   // cudaPeekAtLastError -> vg_status
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int num_sms();
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Kernels launched through launch_pdl() may begin (prologue: barrier init, TMEM alloc, descriptor prefetch) while the
+// previous kernel of the stream is still draining.  Contract: every such kernel executes pdl_wait() before its first
+// access to global memory and pdl_trigger() as early as it likes.  Launching a kernel WITHOUT the attribute after one
+// that triggered early is always safe (plain stream order).  VG_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------- dtype helpers
 typedef __nv_bfloat16 bf16;
 

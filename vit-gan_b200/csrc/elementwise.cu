@@ -13,6 +13,8 @@ int grid1d(int64_t total, int block, int per_sm = 16) {
 template <typename TS, typename TD>
 __global__ void cast_scale_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n,
                                   const float* __restrict__ num, const float* __restrict__ den) {
+  pdl_trigger();
+  pdl_wait();
   float sc = 1.f;
   if (num) sc = *num;
   if (den) sc = sc / *den;
@@ -41,6 +43,8 @@ colsum_vec_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ld, float* 
                   float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
   constexpr int V = 16 / sizeof(T);
   __shared__ float red[8][32][V + 1];
+  pdl_trigger();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bool wsmode = ws != nullptr;                   // workspace mode: 1-D grid over row slices, one 32-group column slab
   const int cg = (wsmode ? 0 : blockIdx.x * 32) + tx;  // column group
@@ -198,13 +202,13 @@ extern "C" int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_
   cudaStream_t st = as_stream(stream);
   const int grid = grid1d((n + 3) / 4, 256);
   if (src_dtype == VG_F32 && dst_dtype == VG_BF16)
-    cast_scale_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, n, num, den);
+    launch_pdl(cast_scale_kernel<float, bf16>, dim3(grid), dim3(256), 0, st, (const float*)src, (bf16*)dst, n, num, den);
   else if (src_dtype == VG_F32 && dst_dtype == VG_F32)
-    cast_scale_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n, num, den);
+    launch_pdl(cast_scale_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, n, num, den);
   else if (src_dtype == VG_BF16 && dst_dtype == VG_F32)
-    cast_scale_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, n, num, den);
+    launch_pdl(cast_scale_kernel<bf16, float>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (float*)dst, n, num, den);
   else if (src_dtype == VG_BF16 && dst_dtype == VG_BF16)
-    cast_scale_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n, num, den);
+    launch_pdl(cast_scale_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, n, num, den);
   else
     VG_REQUIRE(false, VG_ERR_ARG, "cast_scale: bad dtypes %d -> %d", src_dtype, dst_dtype);
   return check_launch("cast_scale");
@@ -221,8 +225,8 @@ extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx
     int ys = (int)max((int64_t)1, min((int64_t)(2 * num_sms()), (M + 63) / 64));
     const int64_t rows_per_cta = (M + ys - 1) / ys;
     ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
-    if (dtype == VG_F32) colsum_vec_kernel<float><<<dim3(ys, 1), 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, workspace, ws_rows, counter);
-    else colsum_vec_kernel<bf16><<<dim3(ys, 1), 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, workspace, ws_rows, counter);
+    if (dtype == VG_F32) launch_pdl(colsum_vec_kernel<float>, dim3(dim3(ys, 1)), dim3(256), 0, st, (const float*)x, M, N, ldx, out, rows_per_cta, workspace, ws_rows, counter);
+    else launch_pdl(colsum_vec_kernel<bf16>, dim3(dim3(ys, 1)), dim3(256), 0, st, (const bf16*)x, M, N, ldx, out, rows_per_cta, workspace, ws_rows, counter);
     return check_launch("colsum");
   }
   const int xs = vec ? (N / V + 31) / 32 : (N + 31) / 32;
@@ -231,8 +235,8 @@ extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx
   ys = (int)((M + rows_per_cta - 1) / rows_per_cta);
   dim3 grid(xs, ys);
   if (vec) {
-    if (dtype == VG_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta, nullptr, 0, nullptr);
-    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta, nullptr, 0, nullptr);
+    if (dtype == VG_F32) launch_pdl(colsum_vec_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)x, M, N, ldx, out, rows_per_cta, nullptr, 0, nullptr);
+    else launch_pdl(colsum_vec_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)x, M, N, ldx, out, rows_per_cta, nullptr, 0, nullptr);
   } else {
     if (dtype == VG_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, out, rows_per_cta);
     else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, M, N, ldx, out, rows_per_cta);

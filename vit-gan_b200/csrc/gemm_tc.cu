@@ -157,6 +157,7 @@ struct Params {
   uint32_t mn_lbo, mn_sbo, mn_kstep;   // MN-major smem descriptor geometry (debug-overridable, see gemm_tc_launch)
   int dbg;                             // bring-up switches (VG_TC_DBG): 1 = epilogue skips global memory, 2 = force direct epilogue
   int epi_tma;                         // 1: smem-staged epilogue with TMA loads (residual/aux) and TMA stores / reduce-add
+  int na_stages;                       // weight-stationary kernel: depth of the A k-block ring
 };
 
 template <typename TC>
@@ -293,6 +294,64 @@ __device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r
   }
 }
 
+// One epilogue warp's share ([32 rows x 64 columns]) of one accumulator tile, staged (TMA) epilogue:
+//   wait for the staging tiles -> stage bias -> prefetch residual/aux by TMA -> wait accumulator -> TMEM -> registers ->
+//   release TMEM -> math -> swizzled smem -> TMA store / reduce-add.
+template <int MODE, int ACT>
+__device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_pre,
+                                            const CUtensorMap* tmap_res, const CUtensorMap* tmap_aux, uint32_t taddr,
+                                            uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
+                                            uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane) {
+  constexpr bool f32 = MODE == 2;
+  const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
+  // staging tiles are free once the previous tile's bulk stores have READ them
+  if (lane == 0) tma_wait_read();
+  __syncwarp();
+  if (p.bias) {                               // stage this warp's 64 bias values (previous tile's readers are past them)
+    const int c0 = n0 + lane, c1 = n0 + 32 + lane;
+    bias_s[lane] = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
+    bias_s[32 + lane] = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
+    __syncwarp();
+  }
+  if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
+    mbar_expect_tx(wbar, (has_res ? (f32 ? 8192u : 4096u) : 0u) + (has_aux ? 4096u : 0u));
+    if (has_res) {
+      tma_load_2d(bufC, tmap_res, wbar, n0, m0);
+      if (f32) tma_load_2d(bufX, tmap_res, wbar, n0 + 32, m0);
+    }
+    if (has_aux) tma_load_2d(bufX, tmap_aux, wbar, n0, m0);
+  }
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  uint32_t r0[32], r1[32];
+  tmem_ld32_nowait(taddr, r0);
+  tmem_ld32_nowait(taddr + 32u, r1);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty);         // accumulator is in registers: release TMEM to the MMA warp
+  if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
+  if (!(p.dbg & 1)) {
+    staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
+    staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
+    fence_async_smem();                       // generic-proxy smem writes -> visible to the async (TMA) proxy
+    __syncwarp();
+    if (lane == 0 && m0 < p.M && n0 < p.N) {
+      if (p.accumulate) {
+        tma_reduce_add_2d(tmap_c, bufC, n0, m0);
+        if (n0 + 32 < p.N) tma_reduce_add_2d(tmap_c, bufX, n0 + 32, m0);
+      } else if (f32) {
+        tma_store_2d(tmap_c, bufC, n0, m0);
+        if (n0 + 32 < p.N) tma_store_2d(tmap_c, bufX, n0 + 32, m0);
+      } else {
+        tma_store_2d(tmap_c, bufC, n0, m0);
+        if (has_pre) tma_store_2d(tmap_pre, bufX, n0, m0);
+      }
+      tma_commit();
+    }
+  }
+}
+
 // MODE 0: direct epilogue (row remaps / unaligned outputs; activation switched at run time)
 // MODE 1: staged TMA epilogue, bf16 output, activation ACT fixed at compile time
 // MODE 2: staged TMA epilogue, fp32 output (plain or split-K reduce-add), no activation
@@ -333,6 +392,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();   // dependents may start their prologue; they wait for our completion before touching memory
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
   // smem tile geometry per operand
@@ -410,62 +471,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t bufC = stg_base + (uint32_t)ew * STG_BYTES, bufX = bufC + 4096u;
       const uint32_t wbar = warp_bar(ew);
       uint32_t wphase = 0;
-      constexpr bool f32 = MODE == 2;
       float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
-      const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
         const int m0 = m_blk * BM + quad * 32, n0 = n_blk * BN + half * 64;
-        // staging tiles are free once the previous tile's bulk stores have READ them
-        if (lane == 0) tma_wait_read();
-        __syncwarp();
-        if (p.bias) {                               // stage this warp's 64 bias values (previous tile's readers are past them)
-          const int c0 = n0 + lane, c1 = n0 + 32 + lane;
-          bias_s[lane] = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
-          bias_s[32 + lane] = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
-          __syncwarp();
-        }
-        if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
-          mbar_expect_tx(wbar, (has_res ? (f32 ? 8192u : 4096u) : 0u) + (has_aux ? 4096u : 0u));
-          if (has_res) {
-            tma_load_2d(bufC, &tmap_res, wbar, n0, m0);
-            if (f32) tma_load_2d(bufX, &tmap_res, wbar, n0 + 32, m0);
-          }
-          if (has_aux) tma_load_2d(bufX, &tmap_aux, wbar, n0, m0);
-        }
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 64);
-        tmem_ld32_nowait(taddr, r0);
-        tmem_ld32_nowait(taddr + 32u, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator is in registers: release TMEM to the MMA warp
-        if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
-        if (!(p.dbg & 1)) {
-          staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
-          staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
-          fence_async_smem();                  // generic-proxy smem writes -> visible to the async (TMA) proxy
-          __syncwarp();
-          if (lane == 0 && m0 < p.M && n0 < p.N) {
-            if (p.accumulate) {
-              tma_reduce_add_2d(&tmap_c, bufC, n0, m0);
-              if (n0 + 32 < p.N) tma_reduce_add_2d(&tmap_c, bufX, n0 + 32, m0);
-            } else if (f32) {
-              tma_store_2d(&tmap_c, bufC, n0, m0);
-              if (n0 + 32 < p.N) tma_store_2d(&tmap_c, bufX, n0 + 32, m0);
-            } else {
-              tma_store_2d(&tmap_c, bufC, n0, m0);
-              if (has_pre) tma_store_2d(&tmap_pre, bufX, n0, m0);
-            }
-            tma_commit();
-          }
-        }
+        staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 64),
+                               tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n0, bufC, bufX, wbar, wphase, bias_s, lane);
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
-      if (lane == 0) tma_wait_all();
+      if (lane == 0) tma_wait_read();   // smem may not be released while bulk stores still read it; visibility comes with grid completion
     } else {
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
@@ -496,6 +510,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+
+// ================================================================================================ weight-stationary variant
+// For the skinny Linear layers of the small ViT configs (K <= 384, N <= 384: the whole weight matrix is <= 96 KB of bf16)
+// the generic kernel re-fetches the B tile for every output tile (QKV at C2: 50 MB of L2->SM traffic for 8.6 MB of unique
+// operands).  Here B is loaded ONCE per CTA and stays resident; A is streamed once per 128-row m-tile through a ring of
+// k-block stages and multiplied against every n-tile (up to 3 accumulators side by side in TMEM, 4 rotating slots).
+//   smem: [B: n_tiles*kb_total tiles of 16 KB][A ring: na_stages x 16 KB][staging 64 KB][bias][barriers]
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
+                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
+  constexpr int NSLOT = 4;                       // TMEM accumulator slots of 128 columns
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int nb_tiles = p.n_tiles * p.kb_total;
+  const uint32_t b_base = smem_base;
+  const uint32_t a_base = b_base + (uint32_t)nb_tiles * B_BYTES;
+  const uint32_t stg_base = a_base + (uint32_t)p.na_stages * A_BYTES;
+  const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;
+  const uint32_t bar_base = bias_base + BIAS_BYTES;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };              // 8
+  auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };       // 8
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };    // 4
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (20 + a); };   // 4
+  auto warp_bar = [&](int w) { return bar_base + 8u * (24 + w); };     // 8
+  const uint32_t b_full = bar_base + 8u * 32;
+  const uint32_t tmem_slot = bar_base + 8u * 33;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < 8; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(warp_bar(w), 1);
+    mbar_init(b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();   // dependents may start their prologue; they wait for our completion before touching memory
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  const uint32_t b_lbo = p.trans_b ? 16u : p.mn_lbo, b_sbo = p.trans_b ? 1024u : p.mn_sbo, b_kstep = p.trans_b ? 32u : p.mn_kstep;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // B: every (n-tile, k-block) tile once
+      mbar_expect_tx(b_full, (uint32_t)nb_tiles * B_BYTES);
+      for (int n = 0; n < p.n_tiles; ++n)
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          const uint32_t sb = b_base + (uint32_t)(n * p.kb_total + kb) * B_BYTES;
+          if (p.trans_b) {
+            tma_load_2d(sb, &tmap_b, b_full, kb * BK, n * BN);
+          } else {
+            tma_load_2d(sb, &tmap_b, b_full, n * BN, kb * BK);
+            tma_load_2d(sb + 8192, &tmap_b, b_full, n * BN + 64, kb * BK);
+          }
+        }
+      // A: one pass per m-tile
+      int stage = 0; uint32_t phase = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(a_empty(stage), phase ^ 1u);
+          mbar_expect_tx(a_full(stage), A_BYTES);
+          tma_load_2d(a_base + stage * A_BYTES, &tmap_a, a_full(stage), kb * BK, mt * BM);
+          if (++stage == p.na_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.trans_b ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      mbar_wait(b_full, 0);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t unit = 0;                              // running (m-tile, n-tile) counter -> TMEM slot = unit % 4
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(a_full(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = a_base + stage * A_BYTES;
+          for (int n = 0; n < p.n_tiles; ++n) {
+            if (kb == 0) {                            // first touch of this slot for this m-tile: the epilogue must have drained it
+              const uint32_t u = unit + n;
+              mbar_wait(tempty_bar(u % NSLOT), ((u / NSLOT) & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            const uint32_t sb = b_base + (uint32_t)(n * p.kb_total + kb) * B_BYTES;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(((unit + n) % NSLOT) * BN);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              tc_mma(d_tmem, make_desc(sa + k * 32u, 16u, 1024u), make_desc(sb + k * b_kstep, b_lbo, b_sbo), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(a_empty(stage));
+          if (++stage == p.na_stages) { stage = 0; phase ^= 1u; }
+        }
+        for (int n = 0; n < p.n_tiles; ++n) tc_commit(tfull_bar((unit + n) % NSLOT));
+        unit += p.n_tiles;
+      }
+    }
+  } else {
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    const uint32_t bufC = stg_base + (uint32_t)ew * STG_BYTES, bufX = bufC + 4096u;
+    const uint32_t wbar = warp_bar(ew);
+    uint32_t wphase = 0;
+    float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
+    uint32_t unit = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      for (int n = 0; n < p.n_tiles; ++n, ++unit) {
+        const int slot = unit % NSLOT;
+        staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BN + half * 64),
+                               tfull_bar(slot), (unit / NSLOT) & 1u, tempty_bar(slot), mt * BM + quad * 32, n * BN + half * 64, bufC, bufX, wbar,
+                               wphase, bias_s, lane);
+      }
+    }
+    if (lane == 0) tma_wait_read();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -599,6 +746,31 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(total, sms);
   const int mode = !p.epi_tma ? 0 : (f32 ? 2 : 1);
+  // weight-stationary variant: staged epilogue, A K-major, no split-K, whole B (+ >= 2 A stages) fits next to the staging tiles
+  const int nb_tiles = p.n_tiles * p.kb_total;
+  const int ws_budget = 227 * 1024 - (EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512);
+  int na = (ws_budget - nb_tiles * B_BYTES) / A_BYTES;
+  na = min(na, min(8, 2 * p.kb_total));
+  const bool ws_ok = mode != 0 && !a.trans_a && !a.accumulate && p.n_tiles <= 3 && na >= 2 && p.m_tiles >= 2 && (p.dbg & 8);   // opt-in (VG_TC_DBG=8): measured no faster than the generic kernel at C2 shapes
+  if (ws_ok) {
+    p.na_stages = na;
+    const int ws_smem = nb_tiles * B_BYTES + na * A_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512;
+    const int ws_grid = min(p.m_tiles, sms);
+#define VG_WS_LAUNCH(MODE_, ACT_)                                                                                                 \
+  do {                                                                                                                            \
+    static int attr_smem = 0;                                                                                                     \
+    if (attr_smem < ws_smem) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_ws_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc(ws): cudaFuncSetAttribute: %s", cudaGetErrorString(e));                \
+      attr_smem = 227 * 1024;                                                                                                     \
+    }                                                                                                                             \
+    launch_pdl(gemm_tc_ws_kernel<MODE_, ACT_>, dim3(ws_grid), dim3(NTHREADS), ws_smem, st, ma, mb, mc, mp, mr, mx, p);                                \
+  } while (0)
+    if (mode == 2) VG_WS_LAUNCH(2, 0);
+    else { VG_ACT_SWITCH(a.act, VG_WS_LAUNCH(1, ACT)) }
+#undef VG_WS_LAUNCH
+    return check_launch("gemm_tc_ws");
+  }
 #define VG_TC_LAUNCH(MODE_, ACT_)                                                                                              \
   do {                                                                                                                         \
     static bool attr_set = false;                                                                                              \
@@ -607,7 +779,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
       VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                 \
       attr_set = true;                                                                                                         \
     }                                                                                                                          \
-    gemm_tc_kernel<MODE_, ACT_><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, mc, mp, mr, mx, p);                                \
+    launch_pdl(gemm_tc_kernel<MODE_, ACT_>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, ma, mb, mc, mp, mr, mx, p);                                \
   } while (0)
   if (mode == 0) VG_TC_LAUNCH(0, 0);
   else if (mode == 2) VG_TC_LAUNCH(2, 0);

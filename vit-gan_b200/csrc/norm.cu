@@ -62,6 +62,8 @@ ln_fwd_kernel(int64_t rows, int E, const T* __restrict__ x, const float* __restr
               const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, float eps) {
   constexpr int RPI = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
@@ -115,8 +117,10 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
   // bias gradients of the Linear layers on either side of the norm (fc2 / out-proj), obtained here for free.
   constexpr int RPI = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
   __shared__ float s_dg[MAXE], s_db[MAXE];
+  pdl_trigger();
   for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
@@ -364,9 +368,9 @@ extern "C" int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, c
   if (rows == 0) return VG_OK;
   const int grid = grid_for_rows(rows, 8);
   if (dtype == VG_F32)
-    VG_NV_DISPATCH(E, (ln_fwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)x, gamma, beta, (float*)y, mean, rstd, eps)));
+    VG_NV_DISPATCH(E, (launch_pdl(ln_fwd_kernel<float, NV>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)x, gamma, beta, (float*)y, mean, rstd, eps)));
   else
-    VG_NV_DISPATCH(E, (ln_fwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, eps)));
+    VG_NV_DISPATCH(E, (launch_pdl(ln_fwd_kernel<bf16, NV>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, eps)));
   return check_launch("layernorm_fwd");
 }
 
@@ -380,10 +384,10 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
   if (rows == 0) return VG_OK;
   int grid = grid_for_rows((rows + 3) / 4, 2);   // 2 CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
   if (dtype == VG_F32)
-    VG_NV_DISPATCH(E, (ln_bwd_kernel<float, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
+    VG_NV_DISPATCH(E, (launch_pdl(ln_bwd_kernel<float, NV>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
                                                                       (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)));
   else
-    VG_NV_DISPATCH(E, (ln_bwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, E, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+    VG_NV_DISPATCH(E, (launch_pdl(ln_bwd_kernel<bf16, NV>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
                                                                      (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)));
   return check_launch("layernorm_bwd");
 }
