@@ -13,7 +13,7 @@ namespace {
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, NTHREADS = 256;
 
 template <typename TC, int ACT>
-__device__ __forceinline__ void simt_epilogue(const vg_gemm_args& g, const float (&acc)[TM][TN], int mbase, int nbase) {
+__device__ __noinline__ void simt_epilogue(const vg_gemm_args& g, const float (&acc)[TM][TN], int mbase, int nbase) {
   TC* __restrict__ C = static_cast<TC*>(g.C);
   const TC* __restrict__ aux = static_cast<const TC*>(g.aux);
   const TC* __restrict__ res = static_cast<const TC*>(g.residual);
