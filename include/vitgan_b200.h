@@ -178,7 +178,7 @@ int vg_copy_rows(int dtype, int64_t rows, int cols, const void* src, int64_t ld_
  * by the kernel so the update is graph-capturable.  decoupled != 0 -> AdamW weight decay. */
 int vg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                  float beta1, float beta2, float eps, float weight_decay, int decoupled, float grad_scale,
-                 int* step_count, void* stream);
+                 int* step_count, void* bf16_shadow /* optional [n] bf16 copy of the updated parameters */, void* stream);
 
 /* self test of the tcgen05 GEMM against an in-kernel SIMT reference; returns 0 if max rel err < tol */
 int vg_selftest_tcgen05(int M, int N, int K, int trans_a, int trans_b, float tol, float* max_err_out);

@@ -173,7 +173,7 @@ __global__ void act_bwd_kernel(int64_t n, const T* __restrict__ dy, const T* __r
 //   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
-                            int decoupled, float grad_scale, const int* __restrict__ step_count) {
+                            int decoupled, float grad_scale, const int* __restrict__ step_count, bf16* __restrict__ shadow) {
   const int t = *step_count + 1;     // the counter is bumped by a separate 1-thread kernel after all tensors
   const float bc1 = 1.f - powf(b1, (float)t);
   const float bc2s = sqrtf(1.f - powf(b2, (float)t));
@@ -187,6 +187,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float denom = sqrtf(vi) / bc2s + eps;
     pi -= step_size * (mi / denom);
     p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pi);   // bf16 operand copy for the tensor-core GEMMs, kept in sync here
   }
 }
 __global__ void bump_kernel(int* c) { *c += 1; }
@@ -264,12 +265,12 @@ extern "C" int vg_broadcast_rows(int dtype, const void* src, int64_t src_rows, i
 
 extern "C" int vg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                             float beta1, float beta2, float eps, float weight_decay, int decoupled, float grad_scale,
-                            int* step_count, void* stream) {
+                            int* step_count, void* bf16_shadow, void* stream) {
   VG_REQUIRE(step_count != nullptr, VG_ERR_ARG, "adam_step: step_count is NULL");
   cudaStream_t st = as_stream(stream);
   if (n > 0)
     adam_kernel<<<grid1d(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                decoupled, grad_scale, step_count);
+                                                decoupled, grad_scale, step_count, (bf16*)bf16_shadow);
   bump_kernel<<<1, 1, 0, st>>>(step_count);
   return check_launch("adam_step");
 }

@@ -74,12 +74,40 @@ def invalidate_operands(param_ids):
         del _cache[key]
 
 
+# parameters re-homed by train.FlatNet: id(param) -> (flatnet, element offset).  When the parameters asked for sit back to
+# back in the flat buffer, the packed operand is a VIEW of the flat fp32 buffer or of its bf16 shadow (kept in sync by the
+# fused Adam kernel): no cast, no copy, no launch -- also under CUDA-graph capture, where the version-keyed cache is off.
+flat_registry: dict = {}
+
+
+def _flat_view(params, dtype):
+    ent = flat_registry.get(id(params[0]))
+    if ent is None:
+        return None
+    net, off0 = ent
+    buf = net.flat_param if dtype == torch.float32 else (net.flat_shadow if dtype == torch.bfloat16 else None)
+    if buf is None or not net.shadow_valid(params):
+        return None
+    off = off0
+    for p in params:
+        e = flat_registry.get(id(p))
+        if e is None or e[0] is not net or e[1] != off:
+            return None
+        off += p.numel()
+    rows = sum(p.shape[0] if p.dim() > 1 else p.numel() for p in params)
+    return buf[off0:off].view(rows, -1)
+
+
 def packed(params, dtype, cols=None, scales=None):
     """Stack 2-D (or flattenable) fp32 parameters along dim 0 into one [sum(rows), cols] tensor of `dtype`.
     scales: optional list of (num, den) 1-element device tensors (spectral rescale) per parameter."""
     if len(params) == 1 and params[0].dtype == dtype and scales is None:
         p = params[0].detach()
         return p if p.dim() == 2 else p.reshape(p.shape[0], -1)
+    if scales is None:
+        v = _flat_view(params, dtype)
+        if v is not None:
+            return v if params[0].dim() != 1 else v
     key = (tuple(id(p) for p in params), dtype)
     ver = tuple((p._version, p.data_ptr()) for p in params)
     if _cache_enabled and scales is None:
@@ -104,6 +132,9 @@ def packed_vec(params):
     """Concatenate fp32 bias vectors (stay fp32)."""
     if len(params) == 1:
         return params[0].detach()
+    v = _flat_view(params, torch.float32)
+    if v is not None:
+        return v.reshape(-1)
     return packed(params, torch.float32).reshape(-1)
 
 
@@ -308,7 +339,7 @@ class EmbedV2Fn(Function):
         N = (I // patch) ** 2
         patches = ops.im2col(img, patch, adt)                        # [B*N, C*P*P]
         w = packed([conv_w], adt)                                     # [E, C*P*P]
-        posd = packed([pos.reshape(N, E)], adt)
+        posd = packed([pos], adt).reshape(N, E)
         x = torch.empty(B, N + 1, E, dtype=adt, device=img.device)
         ops.gemm(patches, w, bias=conv_b.detach(), residual=posd, res_row_mod=N, c_row_group=N, out=x.view(B * (N + 1), E))
         ops.fill_rows(x, 0, cls.detach().reshape(E))

@@ -56,7 +56,7 @@ SIGNATURES = {
     "vg_broadcast_rows": [i32, vp, i64, i64, vp, i64, vp],
     "vg_act_backward": [i32, i64, vp, vp, i32, f32, vp, vp],
     "vg_copy_rows": [i32, i64, i32, vp, i64, vp, i64, vp],
-    "vg_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp],
+    "vg_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp, vp],
     "vg_selftest_tcgen05": [i32, i32, i32, i32, i32, f32, C.POINTER(f32)],
 }
 _OTHER_RESTYPE = {"vg_last_error": C.c_char_p}

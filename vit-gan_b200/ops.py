@@ -324,7 +324,7 @@ def sigma_max(mat_ptrs: torch.Tensor, n_mats, rows, cols, u_state, n_iters, out=
     return out
 
 
-def adam_step(p, g, m, v, step_count, lr, b1, b2, eps, wd, decoupled, grad_scale=1.0):
+def adam_step(p, g, m, v, step_count, lr, b1, b2, eps, wd, decoupled, grad_scale=1.0, shadow=None):
     check(lib.vg_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd,
-                           int(decoupled), grad_scale, step_count.data_ptr(), stream()), "vg_adam_step")
+                           int(decoupled), grad_scale, step_count.data_ptr(), _ptr(shadow), stream()), "vg_adam_step")
     _count(2)

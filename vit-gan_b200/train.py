@@ -45,6 +45,29 @@ class FlatNet:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        # bf16 shadow of the whole flat buffer (operands of the tensor-core GEMMs); FusedAdam keeps it in sync
+        self.flat_shadow = None
+        self._versions = None
+        if dev.type == "cuda":
+            self.flat_shadow = torch.empty(off, dtype=torch.bfloat16, device=dev)
+            self.sync_shadow()
+            for p, o in zip(self.params, self.offsets):
+                Fn.flat_registry[id(p)] = (self, o)
+
+    def sync_shadow(self):
+        """Re-derive the bf16 shadow from the fp32 parameters (after construction / load_state_dict)."""
+        if self.flat_shadow is not None:
+            with torch.no_grad():
+                ops.cast(self.flat_param, torch.bfloat16, out=self.flat_shadow)
+            self._versions = [p._version for p in self.params]
+            self._vmap = {id(p): i for i, p in enumerate(self.params)}
+
+    def shadow_valid(self, params):
+        """False if any of `params` was modified through autograd-visible in-place ops since the last sync
+        (e.g. load_state_dict, a torch optimizer): callers then fall back to the cast path."""
+        if self._versions is None:
+            return True
+        return all(self._versions[self._vmap[id(p)]] == p._version for p in params)
 
     def zero_grad(self):
         """Keeps .grad as views of the flat buffer (autograd then accumulates in place)."""
@@ -73,7 +96,8 @@ class FusedAdam:
     def step(self):
         with torch.no_grad():
             ops.adam_step(self.net.flat_param, self.net.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
-                          self.betas[0], self.betas[1], self.eps, self.wd, self.decoupled, self.grad_scale)
+                          self.betas[0], self.betas[1], self.eps, self.wd, self.decoupled, self.grad_scale,
+                          shadow=self.net.flat_shadow)
         Fn.invalidate_operands(self.net.param_ids)   # the kernel wrote parameter memory behind autograd's back
 
 

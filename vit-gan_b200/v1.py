@@ -218,7 +218,7 @@ class PatchEncoderFn(Function):
         n = n_side * n_side
         F_ = proj_w.shape[0]
         tok = ops.v1_tokens_fwd(img, win, stride, n_side, adt)                       # [B*n, C*win*win]
-        posd = packed([pos], adt)
+        posd = packed([pos], adt).reshape(pos.shape)
         x = torch.empty(B, n + 1, F_, dtype=adt, device=img.device)
         ops.gemm(tok, packed([proj_w], adt), residual=posd, res_row_mod=n, res_row_off=1, c_row_group=n,
                  out=x.view(B * (n + 1), F_))
