@@ -3,6 +3,8 @@
 // Algorithmic bytes: fwd 2*rows*E*sizeof(T); bwd 4*rows*E*sizeof(T) (dy, x, [dres], dx).
 //   LayerNorm : src/v2/modules.py:168,172,225 ; src/v1/transformer.py:18-19 (eps 1e-5, biased var, affine)
 //   SLN       : src/v1/spectral_layer_norm.py:19-20  y = gamma_s * w * LN(h) + beta_s * w
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vg {
@@ -206,6 +208,107 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LN backward, E <= 128
+// Same math as ln_bwd_kernel<T, 1>, restructured for memory-level parallelism: a warp keeps RPI = 8 (bf16) / 4 (fp32) rows
+// of all three inputs in flight as PACKED registers (one 8/16-byte load per lane per tensor per row) before any conversion
+// or shuffle, i.e. 6 KB per warp instead of 3 KB -- the generic kernel is latency-bound at ~1.4 TB/s.
+template <typename T> struct Packed4;
+template <> struct Packed4<float> {
+  typedef float4 raw;
+  static __device__ __forceinline__ void unpack(const raw& r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+template <> struct Packed4<bf16> {
+  typedef uint2 raw;
+  static __device__ __forceinline__ void unpack(const raw& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xFFFF0000u);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_bwd_e128_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
+                   T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_colsum,
+                   float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
+  typedef typename Packed4<T>::raw raw_t;
+  constexpr int RPI = sizeof(T) == 2 ? 8 : 4;
+  __shared__ float s_all[4 * 128];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) s_all[i] = 0.f;
+  __syncthreads();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  const bool on = c < E;
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (on) Vec4<float>::load(gamma + c, g);
+  float adg[4] = {0.f, 0.f, 0.f, 0.f}, adb[4] = {0.f, 0.f, 0.f, 0.f}, adr[4] = {0.f, 0.f, 0.f, 0.f}, adx[4] = {0.f, 0.f, 0.f, 0.f};
+  const float invE = 1.0f / (float)E;
+  const raw_t zero = {};
+  for (int64_t r0 = warp * RPI; r0 < rows; r0 += nwarps * RPI) {
+    raw_t rx[RPI], rdy[RPI], rdr[RPI];
+    float mu[RPI], rs[RPI];
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {        // all loads of the batch first (packed: 2 registers per bf16 load)
+      const int64_t r = min(r0 + q, rows - 1);
+      rx[q] = on ? *reinterpret_cast<const raw_t*>(x + r * E + c) : zero;
+      rdy[q] = on ? *reinterpret_cast<const raw_t*>(dy + r * E + c) : zero;
+      rdr[q] = (on && dres != nullptr) ? *reinterpret_cast<const raw_t*>(dres + r * E + c) : zero;
+      mu[q] = __ldg(mean + r); rs[q] = __ldg(rstd + r);
+    }
+#pragma unroll
+    for (int q = 0; q < RPI; ++q) {
+      const int64_t r = r0 + q;
+      if (r >= rows) break;
+      float xv[4], dv[4], rv[4];
+      Packed4<T>::unpack(rx[q], xv); Packed4<T>::unpack(rdy[q], dv); Packed4<T>::unpack(rdr[q], rv);
+      float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = on ? (xv[j] - mu[q]) * rs[q] : 0.f;
+        const float gd = dv[j] * g[j];
+        adg[j] = fmaf(dv[j], xh, adg[j]);
+        adb[j] += dv[j];
+        c1 += gd;
+        c2 = fmaf(gd, xh, c2);
+        xv[j] = xh; dv[j] = gd;
+      }
+      c1 = warp_sum(c1) * invE;
+      c2 = warp_sum(c2) * invE;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = rs[q] * (dv[j] - c1 - xv[j] * c2);
+        adr[j] += rv[j];
+        dv[j] = rv[j] + t;           // rv is zero when there is no skip-path gradient
+        adx[j] += dv[j];
+      }
+      if (on) Vec4<T>::store(dx + r * E + c, dv);
+    }
+  }
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&s_all[c + j], adg[j]); atomicAdd(&s_all[128 + c + j], adb[j]);
+      atomicAdd(&s_all[256 + c + j], adr[j]); atomicAdd(&s_all[384 + c + j], adx[j]);
+    }
+  }
+  __syncthreads();
+  if (ws != nullptr) {
+    float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
+    const int offs[4] = {0, 128, 256, 384};
+    cta_replica_reduce(ws, ws_rows, counter, s_all, 512, outs, offs, 4);     // columns >= E of each 128-slab stay zero
+  } else {
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+      atomicAdd(&dgamma[i], s_all[i]); atomicAdd(&dbeta[i], s_all[128 + i]);
+      if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[256 + i]);
+      if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[384 + i]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ SLN forward
 template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -382,7 +485,21 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
   VG_REQUIRE(!(dres_colsum && !dres), VG_ERR_ARG, "layernorm_bwd: dres_colsum without dres");
   VG_REQUIRE(!(workspace && (!counter || ws_rows < 1)), VG_ERR_ARG, "layernorm_bwd: workspace needs a counter and ws_rows >= 1");
   if (rows == 0) return VG_OK;
-  int grid = grid_for_rows((rows + 3) / 4, 2);   // 2 CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
+  static int per_sm = 0;
+  if (per_sm == 0) { const char* e = getenv("VG_LN_BWD_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 2; }
+  if (E <= 128) {      // specialised kernel: 8 (bf16) / 4 (fp32) rows per warp in flight
+    const int rpi = dtype == VG_F32 ? 4 : 8;
+    const int grid = grid_for_rows((rows + rpi - 1) / rpi, per_sm);
+    // replica layout is [R][512] (four 128-column slabs); requires outputs sized >= E, workspace sized R*512
+    if (dtype == VG_F32)
+      launch_pdl(ln_bwd_e128_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
+                 rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+    else
+      launch_pdl(ln_bwd_e128_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
+                 rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+    return check_launch("layernorm_bwd");
+  }
+  int grid = grid_for_rows((rows + 3) / 4, per_sm);   // CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
   if (dtype == VG_F32)
     VG_NV_DISPATCH(E, (launch_pdl(ln_bwd_kernel<float, NV>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean, rstd, gamma,
                                                                       (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)));
