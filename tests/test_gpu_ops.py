@@ -306,7 +306,8 @@ def test_cast_scale_and_act_backward(vb):
         assert rel(out, act_ref(act + 4, dy, aux, prm)) < 1e-5
 
 
-@pytest.mark.parametrize("B,H,S,d", [(3, 4, 65, 32), (300, 4, 65, 32), (2, 8, 65, 32), (4, 2, 64, 64), (3, 4, 128, 64), (5, 4, 17, 32), (2, 4, 1, 32)])
+@pytest.mark.parametrize("B,H,S,d", [(3, 4, 65, 32), (300, 4, 65, 32), (2, 8, 65, 32), (4, 2, 64, 64), (3, 4, 128, 64), (5, 4, 17, 32), (2, 4, 1, 32),
+                                     (7, 2, 96, 32), (3, 1, 80, 64), (2, 6, 33, 32), (3, 4, 100, 32), (600, 2, 48, 32)])
 def test_attention_tensor_core_path(vb, B, H, S, d):
     """bf16 dot-product attention with S <= 128 and d in {32, 64} runs on tcgen05 (attention_tc.cu): forward and the
     five-GEMM backward against the fp32 formula, and against this library's CUDA-core flash kernel (VG_ATTN_PATH=simt

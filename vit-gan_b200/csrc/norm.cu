@@ -291,20 +291,20 @@ ln_bwd_e128_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __res
   if (on) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&s_all[c + j], adg[j]); atomicAdd(&s_all[128 + c + j], adb[j]);
-      atomicAdd(&s_all[256 + c + j], adr[j]); atomicAdd(&s_all[384 + c + j], adx[j]);
+      atomicAdd(&s_all[c + j], adg[j]); atomicAdd(&s_all[E + c + j], adb[j]);
+      atomicAdd(&s_all[2 * E + c + j], adr[j]); atomicAdd(&s_all[3 * E + c + j], adx[j]);
     }
   }
   __syncthreads();
-  if (ws != nullptr) {
+  if (ws != nullptr) {       // same [dgamma | dbeta | colsum(dres) | colsum(dx)] x E replica layout as ln_bwd_kernel
     float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
-    const int offs[4] = {0, 128, 256, 384};
-    cta_replica_reduce(ws, ws_rows, counter, s_all, 512, outs, offs, 4);     // columns >= E of each 128-slab stay zero
+    const int offs[4] = {0, E, 2 * E, 3 * E};
+    cta_replica_reduce(ws, ws_rows, counter, s_all, 4 * E, outs, offs, 4);
   } else {
     for (int i = threadIdx.x; i < E; i += blockDim.x) {
-      atomicAdd(&dgamma[i], s_all[i]); atomicAdd(&dbeta[i], s_all[128 + i]);
-      if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[256 + i]);
-      if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[384 + i]);
+      atomicAdd(&dgamma[i], s_all[i]); atomicAdd(&dbeta[i], s_all[E + i]);
+      if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[2 * E + i]);
+      if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[3 * E + i]);
     }
   }
 }
@@ -490,7 +490,6 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
   if (E <= 128) {      // specialised kernel: 8 (bf16) / 4 (fp32) rows per warp in flight
     const int rpi = dtype == VG_F32 ? 4 : 8;
     const int grid = grid_for_rows((rows + rpi - 1) / rpi, per_sm);
-    // replica layout is [R][512] (four 128-column slabs); requires outputs sized >= E, workspace sized R*512
     if (dtype == VG_F32)
       launch_pdl(ln_bwd_e128_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
                  rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
