@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing section (used for ncu launch lists)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW instead of the fused flat Adam kernel")
+    ap.add_argument("--separate-d-passes", action="store_true",
+                    help="run D(real) and D(fake) of the discriminator update as two passes (reference call order) instead of one concatenated pass")
     ap.add_argument("--keep-unused-d-grads", action="store_true",
                     help="also compute D's parameter gradients in the G pass (the reference computes, then discards them)")
     return ap.parse_args()
@@ -313,6 +315,7 @@ def run_ours(args):
     pk = peaks()
     B = spec["per_gpu_batch"]
     skip_unused = not args.keep_unused_d_grads
+    merge_d = not args.separate_d_passes
     torch.manual_seed(0)
     if spec["kind"].startswith("v2"):
         I = spec["over"].get("image_size", 32)
@@ -369,7 +372,7 @@ def run_ours(args):
 
         def eager(real, noise):
             return vb.train.gan_step_microbatched(gen, disc, gopt, dopt, real, noise, loss_kind, n_micro=n_micro, d_buckets=d_b,
-                                                  g_buckets=g_b, skip_unused_d_grads=skip_unused)
+                                                  g_buckets=g_b, skip_unused_d_grads=skip_unused, merge_d_passes=merge_d)
         # launches per step, counted on one eager step (the graph replays exactly these)
         eager(*devb[0])
         torch.cuda.synchronize()
@@ -381,7 +384,7 @@ def run_ours(args):
         if not args.no_graph:
             try:
                 gs = vb.train.GraphedStep(gen, disc, gopt, dopt, devb[0][0], devb[0][1], loss_kind, warmup=2, d_buckets=d_b,
-                                          g_buckets=g_b, skip_unused_d_grads=skip_unused, n_micro=n_micro)
+                                          g_buckets=g_b, skip_unused_d_grads=skip_unused, n_micro=n_micro, merge_d_passes=merge_d)
                 step_fn, graph_used = gs, True
             except Exception as ex:      # fall back to eager launches of the same kernels (never to another implementation)
                 if rank == 0:
@@ -460,6 +463,7 @@ def run_ours(args):
             "config": {"workload": f"{spec['name']}: {spec['desc']}", "per_gpu_batch": B, "global_batch": spec["global_batch"],
                        "parallelism": f"dp{world}", "cuda_graph": graph_used, "micro_batches": (n_micro if spec["kind"] != "v2_sample" else 1), "optimizer": "torch" if args.torch_optim else "fused flat Adam(W) kernel",
                        "d_param_grads_in_g_pass": not skip_unused,
+                       "d_update_passes": "D(real) and D(fake) as one concatenated pass (same gradient sum)" if (merge_d and spec["kind"] != "v2_sample" and n_micro == 1) else "separate",
                        "l2": "192 MiB buffer written between timed steps (L2 flush); step working set is >1 GB anyway"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(last_e2e),
                     "ms_per_step": ms_e2e / args.steps},

@@ -400,3 +400,24 @@ def test_microbatched_step_equals_full_batch(vb, golden):
             gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", n_micro=n_micro)]) for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
     assert rel(losses[3], losses[1]) < 1e-4 and rel(losses[1], fx["losses"]) < 1e-4
     vb.set_precision("bf16")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_merged_d_passes_equal_reference_call_order(vb, prec, golden):
+    """gan_step(merge_d_passes=True) runs D(real) and D(fake.detach()) as one concatenated pass: the three losses of three
+    consecutive steps must match the reference-generated golden curve (src/v2/training.py:177-211 call order) at the
+    same tolerance as the two-pass step."""
+    vb.set_precision(prec)
+    fx = golden("v2_tiny")
+    cfg = vb.v2.Config(**fx["config"])
+    ocfg = o2.V2Config(**fx["config"])
+    gan = vb.v2.ViTGAN(cfg)
+    gan.load_state_dict(fx["params"])
+    gan = gan.cuda()
+    go = torch.optim.AdamW(gan.generator.parameters(), lr=cfg.generator_learning_rate, weight_decay=1e-3)
+    do = torch.optim.AdamW(gan.discriminator.parameters(), lr=cfg.discriminator_learning_rate, weight_decay=1e-3)
+    losses = torch.stack([torch.stack([t.reshape(()) for t in vb.train.gan_step(
+        gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", merge_d_passes=True)]) for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
+    assert rel(losses, fx["losses"]) < TOL[prec]
+    vb.set_precision("bf16")

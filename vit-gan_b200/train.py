@@ -180,13 +180,17 @@ class GradBuckets:
 # the step
 # --------------------------------------------------------------------------------------------------
 def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_buckets=None, g_buckets=None,
-             skip_unused_d_grads=False):
+             skip_unused_d_grads=False, merge_d_passes=False):
     """One adversarial iteration: D(real), G(noise), D(fake.detach()) -> D step; D(fake) -> G step.
 
     loss_kind 'ce'  : nn.CrossEntropyLoss with class-index targets (v2; shim Q2)
     loss_kind 'bce' : nn.BCELoss with float (B,1) targets (v1)
     skip_unused_d_grads: do not produce D's parameter gradients in the third pass (the reference computes
     and then discards them, training.py:177 / gan.py:222); dgrad still flows to G.  Off by default.
+    merge_d_passes: run the two discriminator-update passes D(real), D(fake.detach()) as ONE pass over the
+    concatenated batch with loss = mean_real + mean_fake.  No op on the path couples samples (no BatchNorm), so the
+    accumulated gradient is the same sum up to fp32 summation order; every kernel sees 2x the rows, which halves the
+    per-launch fixed cost of these passes (the E=128 configs are launch/latency bound).  Off by default.
     """
     b, dev = real.shape[0], real.device
     if loss_kind == "ce":
@@ -198,13 +202,22 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
         zeros = torch.zeros(b, 1, device=dev)
         crit = F.binary_cross_entropy
     disc_opt.zero_grad(set_to_none=False) if isinstance(disc_opt, FusedAdam) else disc_opt.zero_grad(set_to_none=True)
-    loss_real = crit(disc(real).float(), ones)
-    loss_real.backward()
-    fake = gen(noise)
-    if d_buckets is not None:
-        d_buckets.arm()
-    loss_fake = crit(disc(fake.detach()).float(), zeros)
-    loss_fake.backward()
+    if merge_d_passes:
+        fake = gen(noise)
+        if d_buckets is not None:
+            d_buckets.arm()
+        out = disc(torch.cat([real, fake.detach().to(real.dtype)], 0)).float()
+        per = crit(out, torch.cat([ones, zeros], 0), reduction="none").view(2, -1)
+        loss_real, loss_fake = per[0].mean(), per[1].mean()
+        (loss_real + loss_fake).backward()
+    else:
+        loss_real = crit(disc(real).float(), ones)
+        loss_real.backward()
+        fake = gen(noise)
+        if d_buckets is not None:
+            d_buckets.arm()
+        loss_fake = crit(disc(fake.detach()).float(), zeros)
+        loss_fake.backward()
     if d_buckets is not None:
         d_buckets.finish()
     disc_opt.step()
@@ -222,7 +235,7 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
 
 
 def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", n_micro=1, d_buckets=None, g_buckets=None,
-                          skip_unused_d_grads=False):
+                          skip_unused_d_grads=False, merge_d_passes=False):
     """The same G+D iteration with the batch processed in `n_micro` equal chunks and exact mean-gradient accumulation
     (each chunk's loss is scaled by 1/n_micro; no BatchNorm on the path, so the result equals the full-batch step up to
     summation order).  Needed when the activations of the full batch do not fit (C4: global batch 2048 on one GPU).
@@ -231,7 +244,7 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
     Phase G: per chunk  G(noise) with grad (G is unchanged, so this is the same fake), D(fake) bwd;  then one G step.
     Cost vs. the un-chunked step: one extra generator forward."""
     if n_micro == 1:
-        return gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind, d_buckets, g_buckets, skip_unused_d_grads)
+        return gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind, d_buckets, g_buckets, skip_unused_d_grads, merge_d_passes)
     b, dev = real.shape[0], real.device
     assert b % n_micro == 0, "batch must be divisible by n_micro"
     mb = b // n_micro
