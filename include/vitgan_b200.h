@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VG_ABI_VERSION 1
+#define VG_ABI_VERSION 2
 
 typedef enum { VG_F32 = 0, VG_BF16 = 1 } vg_dtype;
 typedef enum {
@@ -75,6 +75,10 @@ typedef struct {
   int c_row_group;
   int res_row_mod, res_row_off;
   int accumulate;
+  float* a_rowsum;          /* optional [M] fp32, accumulated: a_rowsum[m] += sum_k opA(A)[m,k].  With the wgrad form
+                             * (trans_a=1, A = dY) this is the bias gradient colsum(dY), obtained on the tensor cores from an
+                             * extra N=16 MMA against a tile of ones.  tcgen05 path in accumulate mode only
+                             * (VG_ERR_UNSUPPORTED otherwise, nothing launched). */
 } vg_gemm_args;
 
 int vg_version(void);

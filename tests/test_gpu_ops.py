@@ -72,6 +72,23 @@ def test_gemm_split_k_accumulate(vb, path):
     assert out.dtype == torch.float32 and rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("rows,N,K", [(33280 // 4, 384, 128), (1000, 256, 128), (70, 128, 256), (4096, 136, 64)])
+def test_gemm_wgrad_fused_bias_gradient(vb, rows, N, K):
+    """a_rowsum: the weight-gradient GEMM dW += dY^T X also accumulates db += colsum(dY) from an N=16 MMA against ones
+    (tcgen05 accumulate mode); both outputs ADD into their buffers; the CUDA-core path rejects it before launching."""
+    L = vb.lib
+    g = gen(rows + N)
+    dy = torch.randn(rows, N, generator=g).bfloat16()
+    x = torch.randn(rows, K, generator=g).bfloat16()
+    dw0, db0 = torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    dw, db = dw0.cuda(), db0.cuda()
+    vb.ops.gemm(dy.cuda(), x.cuda(), trans_a=True, trans_b=False, accumulate=True, out=dw, rowsum_out=db, path=L.GEMM_TCGEN05)
+    assert rel(dw, dw0 + dy.float().t() @ x.float()) < 2e-5
+    assert rel(db, db0 + dy.float().sum(0)) < 2e-5
+    with pytest.raises(L.VitganError, match="a_rowsum"):
+        vb.ops.gemm(dy.cuda(), x.cuda(), trans_a=True, trans_b=False, accumulate=True, out=dw, rowsum_out=db, path=L.GEMM_SIMT)
+
+
 @pytest.mark.parametrize("path", ["simt_f32", "simt_bf16", "tc"])
 @pytest.mark.parametrize("act", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_gemm_epilogue(vb, path, act):

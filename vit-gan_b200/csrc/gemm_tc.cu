@@ -31,8 +31,10 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STG_BYTES = 8192;         // per epilogue warp: two 4 KB swizzled staging tiles (32 rows x 128 B each)
 constexpr int BIAS_BYTES = EPI_WARPS * 64 * 4;   // per epilogue warp: the 64 bias values of its column slab
-constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int ONES_BYTES = 2048;        // [16 n x 64 k] bf16 tile of 1.0: B operand of the row-sum MMA (layout-agnostic)
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int TMEM_COLS = NACC * BN;   // 256: power of two >= 32
+constexpr int RS_COL = TMEM_COLS, RS_N = 16;   // row-sum accumulators (a_rowsum): 16 columns per stage behind the tile accumulators
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,6 +131,15 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tmem_ld1_nowait(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  return r;
+}
+// fp32 vector reduce-add smem -> global through the bulk-copy engine (joins the thread's current bulk group)
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+}
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, sm_100 version 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -158,6 +169,7 @@ struct Params {
   int dbg;                             // bring-up switches (VG_TC_DBG): 1 = epilogue skips global memory, 2 = force direct epilogue
   int epi_tma;                         // 1: smem-staged epilogue with TMA loads (residual/aux) and TMA stores / reduce-add
   int na_stages;                       // weight-stationary kernel: depth of the A k-block ring
+  float* rowsum;                       // a_rowsum: rowsum[m] += sum_k opA(A)[m,k] (bias gradient of a wgrad GEMM) or NULL
 };
 
 template <typename TC>
@@ -301,7 +313,9 @@ template <int MODE, int ACT>
 __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_pre,
                                             const CUtensorMap* tmap_res, const CUtensorMap* tmap_aux, uint32_t taddr,
                                             uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
-                                            uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane) {
+                                            uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane,
+                                            uint32_t rs_taddr = 0u) {
+  // rs_taddr != 0: this warp also drains one row-sum column (a_rowsum) of its 32 rows and reduce-adds it into p.rowsum
   constexpr bool f32 = MODE == 2;
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
   // staging tiles are free once the previous tile's bulk stores have READ them
@@ -326,10 +340,13 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   uint32_t r0[32], r1[32];
   tmem_ld32_nowait(taddr, r0);
   tmem_ld32_nowait(taddr + 32u, r1);
+  uint32_t rs = 0u;
+  if (MODE == 2 && rs_taddr != 0u) rs = tmem_ld1_nowait(rs_taddr);
   tmem_ld_wait();
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tempty);         // accumulator is in registers: release TMEM to the MMA warp
+  if (MODE == 2 && rs_taddr != 0u) bias_s[lane] = __uint_as_float(rs);   // bias staging is idle in accumulate mode
   if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
   if (!(p.dbg & 1)) {
     staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
@@ -340,6 +357,8 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
       if (p.accumulate) {
         tma_reduce_add_2d(tmap_c, bufC, n0, m0);
         if (n0 + 32 < p.N) tma_reduce_add_2d(tmap_c, bufX, n0 + 32, m0);
+        if (MODE == 2 && rs_taddr != 0u)
+          bulk_reduce_add_f32(p.rowsum + m0, smem_u32(bias_s), (uint32_t)min(32, p.M - m0) * 4u);
       } else if (f32) {
         tma_store_2d(tmap_c, bufC, n0, m0);
         if (n0 + 32 < p.N) tma_store_2d(tmap_c, bufX, n0 + 32, m0);
@@ -365,7 +384,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + NSTAGES * STAGE_BYTES;          // 1024-aligned (stage bytes are multiples of 1024)
   const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;
-  const uint32_t bar_base = bias_base + BIAS_BYTES;
+  const uint32_t ones_base = bias_base + BIAS_BYTES;                    // 1024-aligned (all regions above are multiples of 1024)
+  const uint32_t bar_base = ones_base + ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + a); };
@@ -375,7 +395,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool do_rs = MODE == 2 && p.rowsum != nullptr;
+  const uint32_t tmem_cols = do_rs ? 512u : (uint32_t)TMEM_COLS;
 
+  if (do_rs && warp == 2) {        // B operand of the row-sum MMA: bf16 ones (any swizzle / major reads ones)
+#pragma unroll
+    for (int i = 0; i < ONES_BYTES / 512; ++i) sts128(ones_base + (uint32_t)(i * 32 + lane) * 16u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_async_smem();
+  }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
@@ -385,7 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // whole warp: allocate TMEM columns, publish base address through smem
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -436,10 +463,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.trans_a ? 1u : 0u) << 15) |
                              ((p.trans_b ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // row-sum MMA (a_rowsum): same A, B = ones [16 n x 16 k] K-major -> every column of D2 is sum_k opA(A)[m, k]
+      const uint32_t idesc_rs = (1u << 4) | (1u << 7) | (1u << 10) | ((p.trans_a ? 1u : 0u) << 15) | ((uint32_t)(RS_N >> 3) << 17) |
+                                ((uint32_t)(BM >> 4) << 24);
+      const uint64_t ones_desc = make_desc(ones_base, 16u, 1024u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w / (p.n_tiles * p.m_tiles);
+        const bool rs_tile = do_rs && (w % p.n_tiles) == 0;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -453,6 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t ad = make_desc(sa + k * a_kstep, a_lbo, a_sbo);
             const uint64_t bd = make_desc(sb + k * b_kstep, b_lbo, b_sbo);
             tc_mma(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (rs_tile) tc_mma(tmem_base + (uint32_t)(RS_COL + acc * RS_N), ad, ones_desc, idesc_rs, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));                       // frees the smem slot when these MMAs retire
           if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
@@ -475,8 +508,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
         const int m0 = m_blk * BM + quad * 32, n0 = n_blk * BN + half * 64;
+        const uint32_t rs_taddr = (do_rs && n_blk == 0 && half == 0 && m0 < p.M) ? tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(RS_COL + acc * RS_N) : 0u;
         staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 64),
-                               tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n0, bufC, bufX, wbar, wphase, bias_s, lane);
+                               tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n0, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr);
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
       if (lane == 0) tma_wait_read();   // smem may not be released while bulk stores still read it; visibility comes with grid completion
@@ -509,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -691,6 +725,11 @@ bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
   if (a.accumulate && a.c_dtype != VG_F32) { *why = "accumulate needs fp32 C"; return false; }
   if (a.accumulate && (a.act != VG_ACT_NONE || a.c_pre || a.bias || a.residual)) { *why = "accumulate supports a plain epilogue only"; return false; }
   if (act_needs_aux(a.act) && !a.aux) { *why = "activation needs aux"; return false; }
+  if (a.a_rowsum) {
+    const bool c_tma = (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * 4) % 16 == 0 && a.c_row_group == 0 && a.res_row_mod == 0;
+    if (!a.accumulate || !c_tma) { *why = "a_rowsum needs the split-K accumulate mode with a TMA-addressable fp32 C"; return false; }
+    if (a.M % 4 || (reinterpret_cast<uintptr_t>(a.a_rowsum) & 15)) { *why = "a_rowsum needs M % 4 == 0 and a 16 B aligned vector"; return false; }
+  }
   return true;
 }
 
@@ -728,6 +767,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   }
   p.dbg = 0;
   if (const char* d = getenv("VG_TC_DBG")) p.dbg = atoi(d);
+  p.rowsum = a.a_rowsum;
   // staged (TMA) epilogue whenever the output / side tensors are TMA-addressable and no row remap is requested
   const bool f32 = p.c_is_f32 != 0;
   const int esz = f32 ? 4 : 2;
@@ -746,6 +786,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(total, sms);
   const int mode = !p.epi_tma ? 0 : (f32 ? 2 : 1);
+  VG_REQUIRE(!a.a_rowsum || mode == 2, VG_ERR_UNSUPPORTED, "gemm_tc: a_rowsum needs the staged fp32 epilogue");
   // weight-stationary variant: staged epilogue, A K-major, no split-K, whole B (+ >= 2 A stages) fits next to the staging tiles
   const int nb_tiles = p.n_tiles * p.kb_total;
   const int ws_budget = 227 * 1024 - (EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512);

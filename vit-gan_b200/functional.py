@@ -182,16 +182,35 @@ def _notify(params):
             hook(p)
 
 
-def acc_wgrad(dy2, x2, params):
+_FUSE_BIAS_IN_WGRAD = True     # bias gradient as an extra N=16 MMA against ones inside the wgrad GEMM (vg_gemm a_rowsum)
+_wgrad_bias_unsupported: set = set()
+
+
+def acc_wgrad(dy2, x2, params, bias_params=None):
     """dW = dy2^T x2 for one parameter or a row-stack of parameters.  Returns the gradient tensor ([sum N, K]),
-    or None if it was accumulated in place into the parameters' .grad."""
+    or None if it was accumulated in place into the parameters' .grad.
+    bias_params: the matching bias parameter(s); their gradient colsum(dy2) is then produced by the same GEMM when both
+    gradients accumulate in place on the tcgen05 path -- returns (dW, db) with db == "fused" in that case, else db is
+    whatever acc_colsum returns."""
     n = sum(p.shape[0] for p in params)
     view = _grad_view(params, n, x2.shape[1])
-    if view is not None:
-        ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True, out=view)
-        _notify(params)
-        return None
-    return ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True)
+    if bias_params is None:
+        if view is not None:
+            ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True, out=view)
+            _notify(params)
+            return None
+        return ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True)
+    bview = _grad_view(bias_params, 1, dy2.shape[1]) if view is not None else None
+    key = (dy2.dtype, dy2.shape[1], x2.shape[1])
+    if _FUSE_BIAS_IN_WGRAD and bview is not None and dy2.dtype == torch.bfloat16 and key not in _wgrad_bias_unsupported:
+        try:
+            ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True, out=view, rowsum_out=bview.view(-1))
+            _notify(params)
+            _notify(bias_params)
+            return None, None
+        except L.VitganError:          # rejected before any launch (shape / alignment): separate column-sum kernel
+            _wgrad_bias_unsupported.add(key)
+    return acc_wgrad(dy2, x2, params), acc_colsum(dy2, bias_params)
 
 
 def acc_colsum(dy2, params):
@@ -394,8 +413,7 @@ def _attn_bwd(dy, xn, qkv, o, lse, B, S, H, wqkv, wo, scale, want_pg, prm, mode=
     d_o = ops.gemm(dy, wo, trans_b=False)
     dqkv = ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, d_o, lse, B, H, S, d, scale, mode)
     if want_pg:
-        g["wqkv"] = acc_wgrad(dqkv, xn, [prm["wq"], prm["wk"], prm["wv"]])
-        g["bqkv"] = acc_colsum(dqkv, [prm["bq"], prm["bk"], prm["bv"]])
+        g["wqkv"], g["bqkv"] = acc_wgrad(dqkv, xn, [prm["wq"], prm["wk"], prm["wv"]], [prm["bq"], prm["bk"], prm["bv"]])
     dxn = ops.gemm(dqkv, wqkv, trans_b=False)
     return dxn, g
 
@@ -480,8 +498,7 @@ class EncoderFn(Function):
             dw2 = acc_wgrad(dy2, g, [w2])
         du = ops.gemm(dy2, packed([w2], adt), trans_b=False, act=L.ACT_MUL_DGELU, aux=u)       # dgrad fc2 x gelu'(u)
         if pg:
-            dw1 = acc_wgrad(du, xn2, [w1])
-            db1 = acc_colsum(du, [P["b1"]])
+            dw1, db1 = acc_wgrad(du, xn2, [w1], [P["b1"]])
         dxn2 = ops.gemm(du, packed([w1], adt), trans_b=False)
         # LN2 backward also yields db2 = colsum(dy2) (its skip input) and dbo = colsum(dx1) (its output)
         dx1, dn2w, dn2b, db2, dbo = ln_bwd(dxn2, x1, mean2, rstd2, n2w, P["n2b"], dy2, pg, bias_of_dres=P["b2"], bias_of_dx=P["bo"])

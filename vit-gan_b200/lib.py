@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("bias", vp), ("act", i32), ("act_param", f32),
         ("aux", vp), ("ldaux", i64), ("residual", vp), ("ldres", i64), ("c_pre", vp), ("ldpre", i64),
         ("c_row_group", i32), ("res_row_mod", i32), ("res_row_off", i32), ("accumulate", i32),
+        ("a_rowsum", vp),
     ]
 
 

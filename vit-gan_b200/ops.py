@@ -71,11 +71,13 @@ def _rowmajor2d(t: torch.Tensor, name: str):
 
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, act=L.ACT_NONE, act_param=0.0, aux=None, residual=None,
          want_pre=False, out=None, out_dtype=None, accumulate=False, c_row_group=0, res_row_mod=0, res_row_off=0,
-         path=L.GEMM_AUTO):
+         path=L.GEMM_AUTO, rowsum_out=None):
     """C[M,N] = opA(a) @ opB(b) with the fused epilogue of vg_gemm (see include/vitgan_b200.h).
 
     a: [M,K] (or [K,M] if trans_a); b: [N,K] if trans_b (an nn.Linear weight) else [K,N].
     Returns C, or (C, pre_activation) when want_pre.
+    rowsum_out: optional fp32 [M] vector, accumulated with the row sums of opA(a) (the bias gradient when this is a
+    weight-gradient GEMM); tcgen05 accumulate mode only -- raises VitganError (nothing launched) when unsupported.
     """
     _req(a, "a"); _req(b, "b")
     lda, ldb = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
@@ -110,6 +112,10 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, act=L.ACT_NONE, act_pa
     if pre is not None:
         g.c_pre, g.ldpre = pre.data_ptr(), N
     g.c_row_group, g.res_row_mod, g.res_row_off, g.accumulate = c_row_group, res_row_mod, res_row_off, int(accumulate)
+    if rowsum_out is not None:
+        if rowsum_out.dtype != torch.float32 or rowsum_out.numel() != M or not rowsum_out.is_contiguous():
+            raise ValueError("vitgan_b200.gemm: rowsum_out must be a contiguous fp32 vector of length M")
+        g.a_rowsum = rowsum_out.data_ptr()
     check(lib.vg_gemm(C.byref(g), stream()), "vg_gemm")
     _count()
     return (out, pre) if want_pre else out
