@@ -1,5 +1,5 @@
 """Launch each hot kernel ONCE at the C2 shapes (B=512, S=65, E=128, H=4) so that `ncu --set full` can capture them:
-   ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|attn_.*_tc|ln_' -o gpurun_out/prof python profiles/run_kernels.py
+   ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|attn_.*_hp|ln_' -o gpurun_out/prof python profiles/run_kernels.py
 """
 import os
 import sys
@@ -20,7 +20,9 @@ for rep in range(2):      # first pass warms caches/lazy init; ncu is told to sk
     vb.ops.gemm(x, wqkv, bias=bq, path=L.GEMM_TCGEN05)                                        # fwd qkv
     vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)           # fwd fc1 + gelu
     vb.ops.gemm(qkv, wqkv, trans_b=False, path=L.GEMM_TCGEN05)                                # dgrad qkv
-    vb.ops.gemm(qkv, x, trans_a=True, trans_b=False, accumulate=True, path=L.GEMM_TCGEN05)    # wgrad qkv
+    dw, db = torch.zeros(3 * E, E, device=dev), torch.zeros(3 * E, device=dev)
+    vb.ops.gemm(qkv, x, trans_a=True, trans_b=False, accumulate=True, out=dw, rowsum_out=db, path=L.GEMM_TCGEN05)    # wgrad qkv + bias grad
+    vb.ops.gemm(x, wqkv[:E], bias=bq[:E].contiguous(), residual=x, path=L.GEMM_TCGEN05)       # out-proj + bias + residual
     o, lse = vb.ops.attention_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, H, S, d, d ** -0.5)
     vb.ops.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], o, o, lse, B, H, S, d, d ** -0.5)
     y, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)

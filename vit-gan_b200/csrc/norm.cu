@@ -309,6 +309,209 @@ ln_bwd_e128_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LN, E <= 128, 8 lanes per row
+// The warp-per-row kernels above are ISSUE-bound at E = 128 (ncu: 145 / 170 warp instructions per row, issue slots 66 % busy
+// at 3.5 TB/s): 4 elements per lane leave the shuffles, address math and stores un-amortised.  Here a row is owned by 8 lanes
+// (16 elements each: two 8-element chunks 64 columns apart, so every load instruction of the warp is fully coalesced), a
+// warp works on 4 rows at once and the reductions are 3-step shuffles inside the 8-lane group: ~4x fewer instructions per row.
+template <typename T> struct Row8;
+template <> struct Row8<bf16> {
+  typedef uint4 raw;
+  static __device__ __forceinline__ raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ raw load(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const raw& r, float* v) {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xFFFF0000u); v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xFFFF0000u);
+    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xFFFF0000u); v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xFFFF0000u);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]), c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b); t.z = *reinterpret_cast<uint32_t*>(&c); t.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+template <> struct Row8<float> {
+  struct raw { float4 a, b; };
+  static __device__ __forceinline__ raw zero() { raw r; r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; return r; }
+  static __device__ __forceinline__ raw load(const float* p) { raw r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r; }
+  static __device__ __forceinline__ void unpack(const raw& r, float* v) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ void load_vec8(const float* p, bool on, float* v) {
+  if (on) { const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+  else { for (int j = 0; j < 8; ++j) v[j] = 0.f; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_fwd_x8_kernel(int64_t rows, int E, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, float eps) {
+  typedef typename Row8<T>::raw raw_t;
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;               // row quads in flight per warp
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, sub = lane & 7, rq = lane >> 3;
+  const int c0 = sub * 8, c1 = 64 + sub * 8;
+  const bool on0 = c0 < E, on1 = c1 < E;
+  float g[16], b[16];
+  load_vec8(gamma + c0, on0, g); load_vec8(gamma + c1, on1, g + 8);
+  load_vec8(beta + c0, on0, b); load_vec8(beta + c1, on1, b + 8);
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  const float invE = 1.0f / (float)E;
+  for (int64_t r0 = warp * (4 * U); r0 < rows; r0 += nwarps * (4 * U)) {
+    raw_t a[U][2];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = min(r0 + u * 4 + rq, rows - 1);
+      a[u][0] = on0 ? Row8<T>::load(x + r * E + c0) : Row8<T>::zero();
+      a[u][1] = on1 ? Row8<T>::load(x + r * E + c1) : Row8<T>::zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * 4 + rq;
+      float v[16];
+      Row8<T>::unpack(a[u][0], v); Row8<T>::unpack(a[u][1], v + 8);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];
+      const float mean = group8_sum(s) * invE;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v[j] = ((j < 8) ? on0 : on1) ? v[j] - mean : 0.f; q = fmaf(v[j], v[j], q); }
+      const float rstd = rsqrtf(group8_sum(q) * invE + eps);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j] * rstd, g[j], b[j]);
+      if (r < rows) {
+        if (on0) Row8<T>::store(y + r * E + c0, v);
+        if (on1) Row8<T>::store(y + r * E + c1, v + 8);
+        if (sub == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_bwd_x8_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
+                 T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_colsum,
+                 float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
+  typedef typename Row8<T>::raw raw_t;
+  constexpr int U = sizeof(T) == 2 ? 2 : 1;
+  __shared__ float s_all[4 * 128];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) s_all[i] = 0.f;
+  __syncthreads();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, sub = lane & 7, rq = lane >> 3;
+  const int c0 = sub * 8, c1 = 64 + sub * 8;
+  const bool on0 = c0 < E, on1 = c1 < E;
+  float g[16];
+  load_vec8(gamma + c0, on0, g); load_vec8(gamma + c1, on1, g + 8);
+  float adg[16], adb[16], adr[16], adx[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { adg[j] = 0.f; adb[j] = 0.f; adr[j] = 0.f; adx[j] = 0.f; }
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  const float invE = 1.0f / (float)E;
+  const bool has_res = dres != nullptr;
+  for (int64_t r0 = warp * (4 * U); r0 < rows; r0 += nwarps * (4 * U)) {
+    raw_t ax[U][2], ady[U][2], adrs[U][2];
+    float mu[U], rs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = min(r0 + u * 4 + rq, rows - 1);
+      const int64_t o0 = r * E + c0, o1 = r * E + c1;
+      ax[u][0] = on0 ? Row8<T>::load(x + o0) : Row8<T>::zero();
+      ax[u][1] = on1 ? Row8<T>::load(x + o1) : Row8<T>::zero();
+      ady[u][0] = on0 ? Row8<T>::load(dy + o0) : Row8<T>::zero();
+      ady[u][1] = on1 ? Row8<T>::load(dy + o1) : Row8<T>::zero();
+      adrs[u][0] = (on0 && has_res) ? Row8<T>::load(dres + o0) : Row8<T>::zero();
+      adrs[u][1] = (on1 && has_res) ? Row8<T>::load(dres + o1) : Row8<T>::zero();
+      mu[u] = __ldg(mean + r); rs[u] = __ldg(rstd + r);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * 4 + rq;
+      const bool live = r < rows;                        // a clamped duplicate row must not contribute to the column sums
+      float xv[16], dv[16], rv[16];
+      Row8<T>::unpack(ax[u][0], xv); Row8<T>::unpack(ax[u][1], xv + 8);
+      Row8<T>::unpack(ady[u][0], dv); Row8<T>::unpack(ady[u][1], dv + 8);
+      Row8<T>::unpack(adrs[u][0], rv); Row8<T>::unpack(adrs[u][1], rv + 8);
+      float k1 = 0.f, k2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool on = (j < 8) ? on0 : on1;
+        const float xh = (on && live) ? (xv[j] - mu[u]) * rs[u] : 0.f;
+        const float d = live ? dv[j] : 0.f;
+        const float gd = d * g[j];
+        adg[j] = fmaf(d, xh, adg[j]);
+        adb[j] += d;
+        k1 += gd;
+        k2 = fmaf(gd, xh, k2);
+        xv[j] = xh; dv[j] = gd;
+      }
+      k1 = group8_sum(k1) * invE;
+      k2 = group8_sum(k2) * invE;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float rj = live ? rv[j] : 0.f;
+        const float t = rs[u] * (dv[j] - k1 - xv[j] * k2);
+        adr[j] += rj;
+        dv[j] = rj + t;
+        adx[j] += live ? dv[j] : 0.f;
+      }
+      if (live) {
+        if (on0) Row8<T>::store(dx + r * E + c0, dv);
+        if (on1) Row8<T>::store(dx + r * E + c1, dv + 8);
+      }
+    }
+  }
+  // fold the four row groups of the warp (lanes l, l^8, l^16, l^24 own the same columns), then one smem atomic per column
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    adg[j] += __shfl_xor_sync(0xffffffffu, adg[j], 8); adg[j] += __shfl_xor_sync(0xffffffffu, adg[j], 16);
+    adb[j] += __shfl_xor_sync(0xffffffffu, adb[j], 8); adb[j] += __shfl_xor_sync(0xffffffffu, adb[j], 16);
+    adr[j] += __shfl_xor_sync(0xffffffffu, adr[j], 8); adr[j] += __shfl_xor_sync(0xffffffffu, adr[j], 16);
+    adx[j] += __shfl_xor_sync(0xffffffffu, adx[j], 8); adx[j] += __shfl_xor_sync(0xffffffffu, adx[j], 16);
+  }
+  if (rq == 0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = ((j < 8) ? c0 : c1) + (j & 7);
+      if ((j < 8) ? on0 : on1) {
+        atomicAdd(&s_all[c], adg[j]); atomicAdd(&s_all[E + c], adb[j]);
+        atomicAdd(&s_all[2 * E + c], adr[j]); atomicAdd(&s_all[3 * E + c], adx[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (ws != nullptr) {
+    float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
+    const int offs[4] = {0, E, 2 * E, 3 * E};
+    cta_replica_reduce(ws, ws_rows, counter, s_all, 4 * E, outs, offs, 4);
+  } else {
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+      atomicAdd(&dgamma[i], s_all[i]); atomicAdd(&dbeta[i], s_all[E + i]);
+      if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[2 * E + i]);
+      if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[3 * E + i]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ SLN forward
 template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -442,6 +645,16 @@ sln_bwd_kernel(int64_t rows, int64_t h_rows, int F, const T* __restrict__ dy, co
   if (threadIdx.x == 0) { atomicAdd(dgamma_s, s_scal[0]); atomicAdd(dbeta_s, s_scal[1]); }
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v >= 1 ? v : dflt;
+}
+bool x8_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VG_LN_X8"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
 int grid_for_rows(int64_t rows, int ctas_per_sm) {
   const int64_t need = (rows + WARPS - 1) / WARPS;
   const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
@@ -469,6 +682,15 @@ extern "C" int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, c
                                 void* y, float* mean, float* rstd, float eps, void* stream) {
   VG_NORM_CHECK(E);
   if (rows == 0) return VG_OK;
+  if (E <= 128 && E % 8 == 0 && x8_enabled()) {
+    const int rpi = dtype == VG_F32 ? 8 : 16;
+    const int g8 = grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_FWD_CTAS_PER_SM", 4));
+    if (dtype == VG_F32)
+      launch_pdl(ln_fwd_x8_kernel<float>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)x, gamma, beta, (float*)y, mean, rstd, eps);
+    else
+      launch_pdl(ln_fwd_x8_kernel<bf16>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, eps);
+    return check_launch("layernorm_fwd");
+  }
   const int grid = grid_for_rows(rows, 8);
   if (dtype == VG_F32)
     VG_NV_DISPATCH(E, (launch_pdl(ln_fwd_kernel<float, NV>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)x, gamma, beta, (float*)y, mean, rstd, eps)));
@@ -487,6 +709,17 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
   if (rows == 0) return VG_OK;
   static int per_sm = 0;
   if (per_sm == 0) { const char* e = getenv("VG_LN_BWD_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 2; }
+  if (E <= 128 && E % 8 == 0 && x8_enabled()) {      // 8 lanes per row, 8 (bf16) / 4 (fp32) rows per warp in flight
+    const int rpi = dtype == VG_F32 ? 4 : 8;
+    const int g8 = grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_BWD_X8_CTAS_PER_SM", 2));
+    if (dtype == VG_F32)
+      launch_pdl(ln_bwd_x8_kernel<float>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
+                 rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+    else
+      launch_pdl(ln_bwd_x8_kernel<bf16>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
+                 rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+    return check_launch("layernorm_bwd");
+  }
   if (E <= 128) {      // specialised kernel: 8 (bf16) / 4 (fp32) rows per warp in flight
     const int rpi = dtype == VG_F32 ? 4 : 8;
     const int grid = grid_for_rows((rows + rpi - 1) / rpi, per_sm);
