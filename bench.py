@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing section (used for ncu launch lists)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW instead of the fused flat Adam kernel")
+    ap.add_argument("--no-pg-stream", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
     ap.add_argument("--separate-d-passes", action="store_true",
                     help="run D(real) and D(fake) of the discriminator update as two passes (reference call order) instead of one concatenated pass")
     ap.add_argument("--keep-unused-d-grads", action="store_true",
@@ -384,7 +385,8 @@ def run_ours(args):
         if not args.no_graph:
             try:
                 gs = vb.train.GraphedStep(gen, disc, gopt, dopt, devb[0][0], devb[0][1], loss_kind, warmup=2, d_buckets=d_b,
-                                          g_buckets=g_b, skip_unused_d_grads=skip_unused, n_micro=n_micro, merge_d_passes=merge_d)
+                                          g_buckets=g_b, skip_unused_d_grads=skip_unused, n_micro=n_micro, merge_d_passes=merge_d,
+                                          param_grad_stream=not args.no_pg_stream)
                 step_fn, graph_used = gs, True
             except Exception as ex:      # fall back to eager launches of the same kernels (never to another implementation)
                 if rank == 0:

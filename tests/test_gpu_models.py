@@ -421,3 +421,31 @@ def test_merged_d_passes_equal_reference_call_order(vb, prec, golden):
         gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", merge_d_passes=True)]) for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
     assert rel(losses, fx["losses"]) < TOL[prec]
     vb.set_precision("bf16")
+
+
+def test_param_grad_side_stream_matches_main_stream(vb, golden):
+    """Weight-gradient GEMMs on the forked side stream (eager, joined before each optimizer step) give the same three-step
+    loss curve and the same final parameters as the single-stream step."""
+    vb.set_precision("bf16")
+    fx = golden("v2_tiny")
+    cfg = vb.v2.Config(**fx["config"])
+    ocfg = o2.V2Config(**fx["config"])
+    res = {}
+    for side in (False, True):
+        gan = vb.v2.ViTGAN(cfg)
+        gan.load_state_dict(fx["params"])
+        gan = gan.cuda()
+        gnet, dnet = vb.train.FlatNet(gan.generator), vb.train.FlatNet(gan.discriminator)
+        go = vb.train.FusedAdam(gnet, 5e-4, weight_decay=1e-3, decoupled=True)
+        do = vb.train.FusedAdam(dnet, 5e-4, weight_decay=1e-3, decoupled=True)
+        vb.functional.set_param_grad_stream(side)
+        try:
+            losses = torch.stack([torch.stack([t.reshape(()) for t in vb.train.gan_step(
+                gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", merge_d_passes=True)])
+                for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
+        finally:
+            vb.functional.set_param_grad_stream(False)
+        torch.cuda.synchronize()
+        res[side] = (losses.cpu(), gnet.flat_param.clone().cpu(), dnet.flat_param.clone().cpu())
+    assert rel(res[True][0], res[False][0]) < 1e-3
+    assert rel(res[True][1], res[False][1]) < 1e-3 and rel(res[True][2], res[False][2]) < 1e-3

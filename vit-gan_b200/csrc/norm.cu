@@ -709,7 +709,9 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
   if (rows == 0) return VG_OK;
   static int per_sm = 0;
   if (per_sm == 0) { const char* e = getenv("VG_LN_BWD_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 2; }
-  if (E <= 128 && E % 8 == 0 && x8_enabled()) {      // 8 lanes per row, 8 (bf16) / 4 (fp32) rows per warp in flight
+  static int bwd_x8 = -1;       // opt-in (VG_LN_BWD_X8=1): fewer instructions per row but 193 registers; measured slower (19 vs 17 us at C2)
+  if (bwd_x8 < 0) { const char* e = getenv("VG_LN_BWD_X8"); bwd_x8 = (e && e[0] == '1') ? 1 : 0; }
+  if (E <= 128 && E % 8 == 0 && bwd_x8 == 1) {      // 8 lanes per row, 8 (bf16) / 4 (fp32) rows per warp in flight
     const int rpi = dtype == VG_F32 ? 4 : 8;
     const int g8 = grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_BWD_X8_CTAS_PER_SM", 2));
     if (dtype == VG_F32)

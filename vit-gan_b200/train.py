@@ -154,6 +154,7 @@ class GradBuckets:
             self._make_hook(i)(param)
 
     def _launch(self, b):
+        Fn.join_param_grad_stream()      # side-stream weight-gradient GEMMs of this bucket must precede the all-reduce
         s, e = self.bounds[b]
         self.works.append(dist.all_reduce(self.net.flat_grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -220,6 +221,7 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
         loss_fake.backward()
     if d_buckets is not None:
         d_buckets.finish()
+    Fn.join_param_grad_stream()
     disc_opt.step()
     gen_opt.zero_grad(set_to_none=False) if isinstance(gen_opt, FusedAdam) else gen_opt.zero_grad(set_to_none=True)
     if g_buckets is not None:
@@ -230,6 +232,7 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
     loss_g.backward()     # with skip_unused_d_grads only D's blocks were recorded with skip_pg; G's are unaffected
     if g_buckets is not None:
         g_buckets.finish()
+    Fn.join_param_grad_stream()
     gen_opt.step()
     return loss_real.detach(), loss_fake.detach(), loss_g.detach()
 
@@ -270,6 +273,7 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
         l_fake = l_fake + loss.detach()
     if d_buckets is not None:
         d_buckets.finish()
+    Fn.join_param_grad_stream()
     disc_opt.step()
     zg(gen_opt)
     for i in range(n_micro):
@@ -284,6 +288,7 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
         l_g = l_g + loss.detach()
     if g_buckets is not None:
         g_buckets.finish()
+    Fn.join_param_grad_stream()
     gen_opt.step()
     return l_real, l_fake, l_g
 
@@ -293,8 +298,10 @@ class GraphedStep:
     with one cudaGraphLaunch (the small-E configs are launch-bound).  Inputs are copied
     into static buffers; losses are read from static outputs.  Requires FusedAdam (device-side step counter)."""
 
-    def __init__(self, gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", warmup=3, **kw):
+    def __init__(self, gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", warmup=3, param_grad_stream=True, **kw):
         self.real, self.noise = real.clone(), noise.clone()
+        prev_pg = Fn.param_grad_stream_enabled()
+        Fn.set_param_grad_stream(param_grad_stream)       # weight-gradient GEMMs on a forked stream inside the graph
         self.args = (gen, disc, gen_opt, disc_opt)
         self.kw = dict(loss_kind=loss_kind, **kw)
         step = gan_step_microbatched if kw.get("n_micro", 1) > 1 else gan_step
@@ -308,8 +315,11 @@ class GraphedStep:
                 step(*self.args, self.real, self.noise, **self.kw)
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.losses = step(*self.args, self.real, self.noise, **self.kw)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.losses = step(*self.args, self.real, self.noise, **self.kw)
+        finally:
+            Fn.set_param_grad_stream(prev_pg)             # the fork is baked into the graph; eager callers keep their setting
 
     def __call__(self, real, noise):
         self.real.copy_(real, non_blocking=True)
