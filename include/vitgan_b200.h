@@ -112,6 +112,17 @@ int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void*
                      float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
                      float* workspace /* persistent zeroed [ws_rows = R, 4*E] fp32 or NULL */, int ws_rows, unsigned* counter, void* stream);
 
+/* vg_layernorm_bwd with DEFERRED column reductions (E <= 128): dx as above; every CTA stores its partial
+ * [dgamma | dbeta | colsum(dres) | colsum(dx)] (4*E floats) to partials[cta] with plain stores -- no atomics and no
+ * last-CTA fold on the critical path.  Returns the number of partial rows written (1..max_parts) or a negative status.
+ * Fold them later (typically on another stream) with vg_fold_partials. */
+int vg_layernorm_bwd_partials(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
+                              const float* rstd, const float* gamma, const void* dres, void* dx, float* partials,
+                              int max_parts, void* stream);
+/* outK[i] += sum_p partials[p][K*E + i], K = 0..3 (NULL outputs are skipped; fp32, accumulated atomically) */
+int vg_fold_partials(const float* partials, int n_parts, int E, float* out0, float* out1, float* out2, float* out3,
+                     void* stream);
+
 /* Self-modulated LayerNorm  y = w * (gamma_s * (LN(h)*g + b) + beta_s)  (src/v1/spectral_layer_norm.py:19-20).
  * h has h_rows rows (h_rows == rows, or rows % h_rows == 0 for the first G layer where h is (S,F) and
  * broadcasts over the batch, src/v1/transformer.py:86).  gamma_s / beta_s are device scalars. */

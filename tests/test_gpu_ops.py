@@ -161,6 +161,13 @@ def test_layernorm(vb, dt, tol, rows, E):
     assert rel(dg, gr.grad) < max(tol, 1e-4) and rel(db, br.grad) < max(tol, 1e-4)
     # fused column sums (bias gradients of the neighbouring Linear layers): fp32 sums of the un-rounded values
     assert rel(cr, dres.float().sum(0)) < 1e-4 and rel(cx, (xr.grad + dres.float()).sum(0)) < max(tol, 1e-3)
+    if E <= 128:      # deferred column reductions: per-CTA partials + vg_fold_partials give the same five results
+        dx2, part = vb.ops.layernorm_bwd_partials(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dres=dres.cuda())
+        outs = [torch.zeros(E, device="cuda") for _ in range(4)]
+        vb.ops.fold_partials(part, E, *outs)
+        assert torch.equal(dx2, dx)
+        for got, want in zip(outs, (dg, db, cr, cx)):
+            assert rel(got, want) < 1e-5
 
 
 @pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])

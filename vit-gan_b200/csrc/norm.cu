@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_e128_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
                    T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_colsum,
-                   float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
+                   float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter,
+                   float* __restrict__ part) {
+  // part != nullptr: deferred reductions -- the CTA's partial column sums go to part[blockIdx.x][4E] with plain stores
   typedef typename Packed4<T>::raw raw_t;
   constexpr int RPI = sizeof(T) == 2 ? 8 : 4;
   __shared__ float s_all[4 * 128];
@@ -296,6 +298,10 @@ ln_bwd_e128_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __res
     }
   }
   __syncthreads();
+  if (part != nullptr) {
+    for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) part[(size_t)blockIdx.x * (4 * E) + i] = s_all[i];
+    return;
+  }
   if (ws != nullptr) {       // same [dgamma | dbeta | colsum(dres) | colsum(dx)] x E replica layout as ln_bwd_kernel
     float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
     const int offs[4] = {0, E, 2 * E, 3 * E};
@@ -509,6 +515,38 @@ ln_bwd_x8_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restr
       if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[2 * E + i]);
       if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[3 * E + i]);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ deferred column reductions
+// out_k[i] += sum_p part[p][k*E + i]: CTA = 32 columns x 8 row lanes, 4 independent loads in flight per thread.
+__global__ void __launch_bounds__(256)
+fold_partials_kernel(const float* __restrict__ part, int n_parts, int E, float* __restrict__ o0, float* __restrict__ o1,
+                     float* __restrict__ o2, float* __restrict__ o3) {
+  __shared__ float red[8][33];
+  pdl_trigger();
+  pdl_wait();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ncols = 4 * E;
+  const int col = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (col < ncols) {
+    int p = ty;
+    for (; p + 24 < n_parts; p += 32) {
+      const float a = __ldg(part + (size_t)p * ncols + col), b = __ldg(part + (size_t)(p + 8) * ncols + col),
+                  c = __ldg(part + (size_t)(p + 16) * ncols + col), d = __ldg(part + (size_t)(p + 24) * ncols + col);
+      acc += (a + b) + (c + d);
+    }
+    for (; p < n_parts; p += 8) acc += __ldg(part + (size_t)p * ncols + col);
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < ncols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    const int k = col / E, i = col - k * E;
+    float* o = k == 0 ? o0 : (k == 1 ? o1 : (k == 2 ? o2 : o3));
+    if (o != nullptr) atomicAdd(o + i, s);
   }
 }
 
@@ -727,10 +765,10 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
     const int grid = grid_for_rows((rows + rpi - 1) / rpi, per_sm);
     if (dtype == VG_F32)
       launch_pdl(ln_bwd_e128_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
-                 rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+                 rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter, (float*)nullptr);
     else
       launch_pdl(ln_bwd_e128_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
-                 rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+                 rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter, (float*)nullptr);
     return check_launch("layernorm_bwd");
   }
   int grid = grid_for_rows((rows + 3) / 4, per_sm);   // CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
@@ -775,4 +813,32 @@ extern "C" int vg_sln_bwd(int dtype, int64_t rows, int64_t h_rows, int F, const 
     VG_NV_DISPATCH(F, (sln_bwd_kernel<bf16, NV><<<grid, WARPS * 32, 0, as_stream(stream)>>>(rows, h_rows, F, (const bf16*)dy, (const bf16*)h, (const bf16*)w,
         mean, rstd, ln_g, ln_b, gamma_s, beta_s, (const bf16*)dh_res, (const bf16*)dw_res, dh, (bf16*)dw, dgamma_s, dbeta_s, dln_g, dln_b)));
   return check_launch("sln_bwd");
+}
+
+extern "C" int vg_layernorm_bwd_partials(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
+                                         const float* rstd, const float* gamma, const void* dres, void* dx, float* partials,
+                                         int max_parts, void* stream) {
+  VG_NORM_CHECK(E);
+  VG_REQUIRE(E <= 128, VG_ERR_UNSUPPORTED, "layernorm_bwd_partials: E <= 128 only (got %d)", E);
+  VG_REQUIRE(partials != nullptr && max_parts >= 1, VG_ERR_ARG, "layernorm_bwd_partials: no partial buffer");
+  VG_REQUIRE(rows > 0, VG_ERR_SHAPE, "layernorm_bwd_partials: empty input");
+  const int rpi = dtype == VG_F32 ? 4 : 8;
+  const int grid = min(grid_for_rows((rows + rpi - 1) / rpi, 2), max_parts);
+  if (dtype == VG_F32)
+    launch_pdl(ln_bwd_e128_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
+               rstd, gamma, (const float*)dres, (float*)dx, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, 0,
+               (unsigned*)nullptr, partials);
+  else
+    launch_pdl(ln_bwd_e128_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
+               rstd, gamma, (const bf16*)dres, (bf16*)dx, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, 0,
+               (unsigned*)nullptr, partials);
+  const int rc = check_launch("layernorm_bwd_partials");
+  return rc ? rc : grid;
+}
+
+extern "C" int vg_fold_partials(const float* partials, int n_parts, int E, float* out0, float* out1, float* out2, float* out3,
+                                void* stream) {
+  VG_REQUIRE(partials != nullptr && n_parts >= 1 && E >= 1, VG_ERR_ARG, "fold_partials: bad arguments");
+  launch_pdl(fold_partials_kernel, dim3((4 * E + 31) / 32), dim3(256), 0, as_stream(stream), partials, n_parts, E, out0, out1, out2, out3);
+  return check_launch("fold_partials");
 }

@@ -305,8 +305,18 @@ def ln_bwd(dy2, x2, mean, rstd, weight, bias, dres, want_pg, bias_of_dres=None, 
     gb, b_in = _acc_target([bias])
     cr, cr_in = _acc_target([bias_of_dres]) if bias_of_dres is not None else (None, True)
     cx, cx_in = _acc_target([bias_of_dx]) if bias_of_dx is not None else (None, True)
-    dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, dgamma_acc=gw, dbeta_acc=gb,
-                                 dres_colsum=cr, dx_colsum=cx)
+    if _PG_STREAM_ON and x2.shape[1] <= 128 and w_in and b_in and cr_in and cx_in:
+        # deferred reductions: per-CTA partials now, folded into .grad on the parameter-gradient stream
+        dx, part = ops.layernorm_bwd_partials(dy2, x2, mean, rstd, weight.detach(), dres=dres)
+        idx, side = _pg_side(x2.device)
+        side.wait_stream(torch.cuda.current_stream(idx))
+        with torch.cuda.stream(side):
+            ops.fold_partials(part, x2.shape[1], gw, gb, cr, cx)
+        _pg_forked.add(idx)
+        _pg_keepalive.append(part)
+    else:
+        dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, dgamma_acc=gw, dbeta_acc=gb,
+                                     dres_colsum=cr, dx_colsum=cx)
     _notify([p for p, flag in ((weight, w_in), (bias, b_in), (bias_of_dres, cr_in), (bias_of_dx, cx_in)) if p is not None and flag])
     return (dx, None if w_in else gw, None if b_in else gb, None if cr_in else cr, None if cx_in else cx)
 

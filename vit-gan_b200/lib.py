@@ -42,6 +42,8 @@ SIGNATURES = {
     "vg_colsum": [vp, i32, i64, i32, i64, vp, vp, i32, vp, vp],
     "vg_layernorm_fwd": [i32, i64, i32, vp, vp, vp, vp, vp, vp, f32, vp],
     "vg_layernorm_bwd": [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
+    "vg_layernorm_bwd_partials": [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "vg_fold_partials": [vp, i32, i32, vp, vp, vp, vp, vp],
     "vg_sln_fwd": [i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp],
     "vg_sln_bwd": [i32, i64, i64, i32] + [vp] * 17,
     "vg_attention_fwd": [i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, i64, vp, f32, vp],

@@ -175,6 +175,32 @@ def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbet
     return dx, dgamma_acc, dbeta_acc
 
 
+_MAX_PARTS = {}
+
+
+def layernorm_bwd_partials(dy2d, x2d, mean, rstd, gamma, dres=None):
+    """LayerNorm backward whose column reductions are deferred: returns (dx, partials[n, 4E]); see vg_fold_partials."""
+    _req(x2d, "x2d")
+    rows, e = x2d.shape
+    idx = x2d.device.index if x2d.device.index is not None else torch.cuda.current_device()
+    mp = _MAX_PARTS.get(idx)
+    if mp is None:
+        mp = _MAX_PARTS[idx] = 2 * torch.cuda.get_device_properties(idx).multi_processor_count
+    dx = torch.empty_like(x2d)
+    part = torch.empty(mp, 4 * e, dtype=torch.float32, device=x2d.device)
+    n = lib.vg_layernorm_bwd_partials(dt(x2d), rows, e, dy2d.data_ptr(), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                      gamma.data_ptr(), _ptr(dres), dx.data_ptr(), part.data_ptr(), mp, stream())
+    if n <= 0:
+        check(n if n < 0 else -1, "vg_layernorm_bwd_partials")
+    _count()
+    return dx, part[:n]
+
+
+def fold_partials(part, e, out0, out1, out2=None, out3=None):
+    check(lib.vg_fold_partials(part.data_ptr(), part.shape[0], e, _ptr(out0), _ptr(out1), _ptr(out2), _ptr(out3), stream()), "vg_fold_partials")
+    _count()
+
+
 def sln_fwd(h2d, w2d, ln_g, ln_b, gamma_s, beta_s, eps=1e-5):
     _req(w2d, "w2d")
     rows, f = w2d.shape
