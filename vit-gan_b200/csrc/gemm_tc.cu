@@ -314,7 +314,8 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
                                             const CUtensorMap* tmap_res, const CUtensorMap* tmap_aux, uint32_t taddr,
                                             uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
                                             uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane,
-                                            uint32_t rs_taddr = 0u) {
+                                            uint32_t rs_taddr = 0u, bool release = true) {
+  // release == false: more 64-column groups of the same accumulator follow (256-wide tiles); the last group frees TMEM
   // rs_taddr != 0: this warp also drains one row-sum column (a_rowsum) of its 32 rows and reduce-adds it into p.rowsum
   constexpr bool f32 = MODE == 2;
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
@@ -345,7 +346,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   tmem_ld_wait();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(tempty);         // accumulator is in registers: release TMEM to the MMA warp
+  if (lane == 0 && release) mbar_arrive(tempty);   // accumulator is in registers: release TMEM to the MMA warp
   if (MODE == 2 && rs_taddr != 0u) bias_s[lane] = __uint_as_float(rs);   // bias staging is idle in accumulate mode
   if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
   if (!(p.dbg & 1)) {
@@ -374,11 +375,16 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
 // MODE 0: direct epilogue (row remaps / unaligned outputs; activation switched at run time)
 // MODE 1: staged TMA epilogue, bf16 output, activation ACT fixed at compile time
 // MODE 2: staged TMA epilogue, fp32 output (plain or split-K reduce-add), no activation
-template <int MODE, int ACT>
+// BNT: tile width.  128 (4-stage ring) for the skinny / memory-bound shapes; 256 (3 stages, both accumulator stages = all 512
+// TMEM columns) for the compute-bound ones: a 128x128 tile reads 32 KB of smem per 2.1 MFLOP (256 clk of smem bandwidth for 256
+// clk of tensor pipe: smem-bound), a 128x256 tile 48 KB per 4.2 MFLOP (384 vs 512 clk).
+template <int MODE, int ACT, int BNT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
                const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
+  constexpr int BN = BNT, NSTAGES = BNT == 256 ? 3 : 4;                   // shadow the file-scope 128-wide constants
+  constexpr int B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_dyn[];
   // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -395,8 +401,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool do_rs = MODE == 2 && p.rowsum != nullptr;
-  const uint32_t tmem_cols = do_rs ? 512u : (uint32_t)TMEM_COLS;
+  const bool do_rs = MODE == 2 && BNT == 128 && p.rowsum != nullptr;
+  const uint32_t tmem_cols = (do_rs || BNT == 256) ? 512u : (uint32_t)TMEM_COLS;
 
   if (do_rs && warp == 2) {        // B operand of the row-sum MMA: bf16 ones (any swizzle / major reads ones)
 #pragma unroll
@@ -450,8 +456,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (p.trans_b) {
             tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);                 // box {64 k, 128 n}
           } else {
-            tma_load_2d(sb, &tmap_b, full_bar(stage), n_blk * BN, kb * BK);                 // box {64 n, 64 k} x2
-            tma_load_2d(sb + 8192, &tmap_b, full_bar(stage), n_blk * BN + 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)                                               // box {64 n, 64 k} x BN/64
+              tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n_blk * BN + 64 * j, kb * BK);
           }
           if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
         }
@@ -507,10 +514,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
-        const int m0 = m_blk * BM + quad * 32, n0 = n_blk * BN + half * 64;
+        const int m0 = m_blk * BM + quad * 32;
         const uint32_t rs_taddr = (do_rs && n_blk == 0 && half == 0 && m0 < p.M) ? tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(RS_COL + acc * RS_N) : 0u;
-        staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 64),
-                               tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n0, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr);
+#pragma unroll
+        for (int g = 0; g < BN / 128; ++g) {           // this warp's 64-column groups of the tile (one at BN = 128, two at 256)
+          const int col = half * (BN / 2) + g * 64;
+          staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
+                                 tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
+                                 g == BN / 128 - 1);
+        }
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
       if (lane == 0) tma_wait_read();   // smem may not be released while bulk stores still read it; visibility comes with grid completion
@@ -740,12 +752,27 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   rc = a.trans_a ? make_map(&ma, a.A, a.K, a.M, a.lda, 64, 64) : make_map(&ma, a.A, a.M, a.K, a.lda, 64, BM);
   if (rc) return rc;
   // B: trans_b=1 stored [N,K] -> box {64 k, 128 n};  trans_b=0 stored [K,N] -> box {64 n, 64 k}
-  rc = a.trans_b ? make_map(&mb, a.B, a.N, a.K, a.ldb, 64, BN) : make_map(&mb, a.B, a.K, a.N, a.ldb, 64, 64);
+  // tile width: 256 for compute-bound problems (deep K, N a multiple of 256, enough tiles to fill the machine) whose
+  // epilogue can be staged; 128 otherwise.  VG_TC_BN=128|256 overrides the heuristic (256 still needs the staged epilogue).
+  const int sms0 = num_sms();
+  const int esz0 = a.c_dtype == VG_F32 ? 4 : 2;
+  auto tma_ok0 = [&](const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz0) % 16 == 0; };
+  const char* dbg0 = getenv("VG_TC_DBG");
+  const bool stageable = !(dbg0 && (atoi(dbg0) & 2)) && a.c_row_group == 0 && a.res_row_mod == 0 && !a.a_rowsum && tma_ok0(a.C, a.ldc) &&
+                         (!a.residual || tma_ok0(a.residual, a.ldres)) && (!a.aux || tma_ok0(a.aux, a.ldaux)) &&
+                         (!a.c_pre || tma_ok0(a.c_pre, a.ldpre)) && !(a.c_dtype == VG_F32 && (a.aux || a.c_pre || a.act != VG_ACT_NONE));   // == epi_tma below
+  static int bn_env = -1;
+  if (bn_env < 0) { const char* e = getenv("VG_TC_BN"); bn_env = e ? atoi(e) : 0; }
+  bool wide = stageable && a.N % 256 == 0 && a.K >= 512 && (int64_t)((a.M + BM - 1) / BM) * (a.N / 256) >= sms0;
+  if (bn_env == 128) wide = false;
+  if (bn_env == 256) wide = stageable && a.N >= 256;
+  const int bn = wide ? 256 : BN;
+  rc = a.trans_b ? make_map(&mb, a.B, a.N, a.K, a.ldb, 64, bn) : make_map(&mb, a.B, a.K, a.N, a.ldb, 64, 64);
   if (rc) return rc;
 
   Params p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.trans_a = a.trans_a; p.trans_b = a.trans_b;
-  p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + BN - 1) / BN;
+  p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + bn - 1) / bn;
   p.kb_total = (a.K + BK - 1) / BK;
   p.splits = 1;
   const int sms = num_sms();
@@ -787,12 +814,14 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const int grid = min(total, sms);
   const int mode = !p.epi_tma ? 0 : (f32 ? 2 : 1);
   VG_REQUIRE(!a.a_rowsum || mode == 2, VG_ERR_UNSUPPORTED, "gemm_tc: a_rowsum needs the staged fp32 epilogue");
+  VG_REQUIRE(!(bn == 256 && mode == 0), VG_ERR_LAUNCH, "gemm_tc: internal: 256-wide tile without a staged epilogue");
+  const bool wide_k = bn == 256;
   // weight-stationary variant: staged epilogue, A K-major, no split-K, whole B (+ >= 2 A stages) fits next to the staging tiles
   const int nb_tiles = p.n_tiles * p.kb_total;
   const int ws_budget = 227 * 1024 - (EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512);
   int na = (ws_budget - nb_tiles * B_BYTES) / A_BYTES;
   na = min(na, min(8, 2 * p.kb_total));
-  const bool ws_ok = mode != 0 && !a.trans_a && !a.accumulate && p.n_tiles <= 3 && na >= 2 && p.m_tiles >= 2 && (p.dbg & 8);   // opt-in (VG_TC_DBG=8): measured no faster than the generic kernel at C2 shapes
+  const bool ws_ok = !wide_k && mode != 0 && !a.trans_a && !a.accumulate && p.n_tiles <= 3 && na >= 2 && p.m_tiles >= 2 && (p.dbg & 8);   // opt-in (VG_TC_DBG=8): measured no faster than the generic kernel at C2 shapes
   if (ws_ok) {
     p.na_stages = na;
     const int ws_smem = nb_tiles * B_BYTES + na * A_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512;
@@ -812,19 +841,23 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
 #undef VG_WS_LAUNCH
     return check_launch("gemm_tc_ws");
   }
-#define VG_TC_LAUNCH(MODE_, ACT_)                                                                                              \
+#define VG_TC_LAUNCH(MODE_, ACT_, BN_)                                                                                         \
   do {                                                                                                                         \
+    constexpr int smem_ = (BN_ == 256 ? 3 * (A_BYTES + 256 * BK * 2) : NSTAGES * STAGE_BYTES) + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + 1024 + 512; \
     static bool attr_set = false;                                                                                              \
     if (!attr_set) {                                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_); \
       VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                 \
       attr_set = true;                                                                                                         \
     }                                                                                                                          \
-    launch_pdl(gemm_tc_kernel<MODE_, ACT_>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, ma, mb, mc, mp, mr, mx, p);                                \
+    launch_pdl(gemm_tc_kernel<MODE_, ACT_, BN_>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);             \
   } while (0)
-  if (mode == 0) VG_TC_LAUNCH(0, 0);
-  else if (mode == 2) VG_TC_LAUNCH(2, 0);
-  else { VG_ACT_SWITCH(a.act, VG_TC_LAUNCH(1, ACT)) }
+  if (mode == 0) VG_TC_LAUNCH(0, 0, 128);
+  else if (wide_k) {
+    if (mode == 2) VG_TC_LAUNCH(2, 0, 256);
+    else { VG_ACT_SWITCH(a.act, VG_TC_LAUNCH(1, ACT, 256)) }
+  } else if (mode == 2) VG_TC_LAUNCH(2, 0, 128);
+  else { VG_ACT_SWITCH(a.act, VG_TC_LAUNCH(1, ACT, 128)) }
 #undef VG_TC_LAUNCH
   return check_launch("gemm_tc");
 }
