@@ -106,7 +106,8 @@ int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, const float*
                      void* y, float* mean, float* rstd, float eps, void* stream);
 /* dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta are atomically accumulated (zero them first).
  * dres_colsum / dx_colsum (optional, fp32 [E], accumulated): column sums of the skip-path gradient `dres` and of the
- * produced `dx` -- the bias gradients of the Linear layers on either side of the norm, computed here for free. */
+ * produced `dx` -- the bias gradients of the Linear layers on either side of the norm, computed here for free.
+ * dgamma == dbeta == NULL: dx only (the dgrad-only discriminator pass of the generator update), no reductions at all. */
 int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, const void* x, const float* mean,
                      const float* rstd, const float* gamma, const void* dres, void* dx,
                      float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,

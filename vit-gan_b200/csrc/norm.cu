@@ -175,6 +175,7 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
       store_row<T, NV>(dx + r * E, E, lane, dv[q]);
     }
   }
+  if (dgamma == nullptr) return;      // dx only (dgrad-only pass): no column reductions at all
   if (ws != nullptr) {
     // workspace path: [dgamma | dbeta | colsum(dres) | colsum(dx)] -> replicated accumulators, folded by the last CTA
     __shared__ float s_all[4 * MAXE];
@@ -290,6 +291,7 @@ ln_bwd_e128_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __res
       if (on) Vec4<T>::store(dx + r * E + c, dv);
     }
   }
+  if (dgamma == nullptr && part == nullptr) return;      // dx only (dgrad-only pass): no column reductions at all
   if (on) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -486,6 +488,7 @@ ln_bwd_x8_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restr
       }
     }
   }
+  if (dgamma == nullptr) return;      // dx only
   // fold the four row groups of the warp (lanes l, l^8, l^16, l^24 own the same columns), then one smem atomic per column
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -743,6 +746,8 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
                                 unsigned* counter, void* stream) {
   VG_NORM_CHECK(E);
   VG_REQUIRE(!(dres_colsum && !dres), VG_ERR_ARG, "layernorm_bwd: dres_colsum without dres");
+  VG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr) && !(dgamma == nullptr && (dres_colsum || dx_colsum)), VG_ERR_ARG,
+             "layernorm_bwd: dgamma/dbeta must be given together (both NULL = dx only, no column sums)");
   VG_REQUIRE(!(workspace && (!counter || ws_rows < 1)), VG_ERR_ARG, "layernorm_bwd: workspace needs a counter and ws_rows >= 1");
   if (rows == 0) return VG_OK;
   static int per_sm = 0;

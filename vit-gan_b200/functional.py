@@ -299,7 +299,7 @@ def ln_bwd(dy2, x2, mean, rstd, weight, bias, dres, want_pg, bias_of_dres=None, 
     bias_of_dres / bias_of_dx: bias parameters whose gradient is colsum(dres) / colsum(dx) (fused into this kernel).
     Gradients are accumulated in place into .grad when possible (then None is returned for them)."""
     if not want_pg:
-        dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres)
+        dx, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dres=dres, dx_only=True)
         return dx, None, None, None, None
     gw, w_in = _acc_target([weight])
     gb, b_in = _acc_target([bias])

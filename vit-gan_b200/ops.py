@@ -157,12 +157,20 @@ def layernorm_fwd(x2d, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbeta_acc=None, dres_colsum=None, dx_colsum=None):
+def layernorm_bwd(dy2d, x2d, mean, rstd, gamma, dres=None, dgamma_acc=None, dbeta_acc=None, dres_colsum=None, dx_colsum=None,
+                  dx_only=False):
     """dgamma_acc / dbeta_acc: optional fp32 buffers the kernel atomically ADDS into (e.g. the parameters' .grad).
-    dres_colsum / dx_colsum: optional fp32 [E] buffers accumulating the column sums of `dres` / of the returned dx."""
+    dres_colsum / dx_colsum: optional fp32 [E] buffers accumulating the column sums of `dres` / of the returned dx.
+    dx_only: no parameter gradients at all (returns (dx, None, None))."""
     _req(x2d, "x2d")
     rows, e = x2d.shape
     dx = torch.empty_like(x2d)
+    if dx_only:
+        check(lib.vg_layernorm_bwd(dt(x2d), rows, e, dy2d.data_ptr(), x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                   gamma.data_ptr(), _ptr(dres), dx.data_ptr(), None, None, None, None, None, 0, None, stream()),
+              "vg_layernorm_bwd")
+        _count()
+        return dx, None, None
     if dgamma_acc is None:
         dgb = torch.zeros(2, e, dtype=torch.float32, device=x2d.device)
         dgamma_acc, dbeta_acc = dgb[0], dgb[1]
