@@ -347,8 +347,8 @@ def run_ours(args):
         gen.eval()
 
         def one(real, noise):
-            with torch.no_grad():
-                return (gen(noise).mean(),)
+            # batched generator forward + fused de-normalise -> uint8 (the reference's sampling tail, generation.py:47-56)
+            return (vb.v2.sample_uint8(gen, noise).sum(dtype=torch.int64).float(),)
         d_b = g_b = None
         step_fn = one
         graph_used = False

@@ -186,6 +186,17 @@ int vg_broadcast_rows(int dtype, const void* src, int64_t src_rows, int64_t cols
 /* out[i] = dy[i] * act'(aux[i]) for act in {GELU, TANH, SIN, SIGMOID} (aux as in VG_ACT_MUL_D*): backward of the
  * activation of standalone Linear layers (heads, SIREN) whose dgrad GEMM belongs to the previous layer. */
 int vg_act_backward(int dtype, int64_t n, const void* dy, const void* aux, int act, float act_param, void* out, void* stream);
+
+/* Fused nn.CrossEntropyLoss (mean reduction, class-index int64 targets; src/v2/training.py:159) over rows/rows_per_group
+ * groups of consecutive rows: losses[g] = mean_{r in group g} CE(logits[r], targets[r]);  dlogits = d(sum_g losses[g])/dlogits.
+ * One launch instead of log_softmax + nll_loss forward/backward + reductions (loss head inside the
+ * captured step).  fp32 logits [rows, C]; rows %% rows_per_group == 0; at most 64 groups. */
+int vg_softmax_ce(const float* logits, const int64_t* targets, int rows, int C, int rows_per_group, float* losses,
+                  float* dlogits, void* stream);
+
+/* utils.convert_to_uint8 (src/v2/utils.py:194-196): out = uint8(clamp(x * 127.5 + 127.5, 0, 255)), the de-normalisation at
+ * the end of the sampling path (src/v2/generation.py:47-56, utils.py:165-166); byte-exact vs torch on identical fp32 input. */
+int vg_denorm_u8(int dtype, const void* x, int64_t n, uint8_t* out, void* stream);
 /* dst[r*ld_dst + c] = src[r*ld_src + c]: strided row gather/scatter (CLS-token rows: x[:,0,:], src/v2/modules.py:195) */
 int vg_copy_rows(int dtype, int64_t rows, int cols, const void* src, int64_t ld_src, void* dst, int64_t ld_dst, void* stream);
 

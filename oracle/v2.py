@@ -188,3 +188,8 @@ def flops_per_image_fwd(cfg: V2Config, generator: bool) -> float:
     if generator:
         f += 2 * cfg.classes_count * c * cfg.image_size ** 2
     return float(f)
+
+
+def convert_to_uint8(images):
+    """utils.convert_to_uint8 (src/v2/utils.py:194-196): de-normalise generator output to bytes."""
+    return (images * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)

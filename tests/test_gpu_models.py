@@ -449,3 +449,23 @@ def test_param_grad_side_stream_matches_main_stream(vb, golden):
         res[side] = (losses.cpu(), gnet.flat_param.clone().cpu(), dnet.flat_param.clone().cpu())
     assert rel(res[True][0], res[False][0]) < 1e-3
     assert rel(res[True][1], res[False][1]) < 1e-3 and rel(res[True][2], res[False][2]) < 1e-3
+
+
+def test_v2_batched_sampling_uint8(vb, golden):
+    """vb.v2.sample_uint8: one batched generator forward + fused de-normalise equals the oracle's generator followed by the
+    reference's convert_to_uint8 up to 1 grey level (fp32 path)."""
+    vb.set_precision("fp32")
+    fx = golden("v2_tiny")
+    cfg = vb.v2.Config(**fx["config"])
+    ocfg = o2.V2Config(**fx["config"])
+    gan = vb.v2.ViTGAN(cfg)
+    gan.load_state_dict(fx["params"])
+    gan = gan.cuda()
+    (_, noise), = harness.synthetic_batches_v2(ocfg, 5, 1)
+    got = vb.v2.sample_uint8(gan.generator, noise.cuda()).cpu()
+    orc = harness.OracleV2(ocfg, params=fx["params"])
+    with torch.no_grad():
+        want = o2.convert_to_uint8(orc.generator(noise))
+    assert got.dtype == torch.uint8 and got.shape == noise.shape
+    assert (got.int() - want.int()).abs().max() <= 1
+    vb.set_precision("bf16")

@@ -359,3 +359,27 @@ def test_attention_tensor_core_path(vb, B, H, S, d):
     qf = qkv.float().cuda()
     o32, lse32 = vb.ops.attention_fwd(qf[:, :hd], qf[:, hd:2 * hd], qf[:, 2 * hd:], B, H, S, d, scale, 0)
     assert rel(o, o32) < BF16_TOL and rel(lse, lse32) < 1e-3
+
+
+def test_softmax_ce_fused_head(vb):
+    """vg_softmax_ce == nn.CrossEntropyLoss per group (values and gradient of the summed losses), fp32 1e-5."""
+    g = gen(77)
+    for rows, C, rpg in ((1024, 10, 512), (512, 10, 512), (96, 7, 32)):
+        z = (torch.randn(rows, C, generator=g) * 3).requires_grad_(True)
+        t = torch.randint(0, C, (rows,), generator=g)
+        ref = torch.stack([F.cross_entropy(z[i:i + rpg], t[i:i + rpg]) for i in range(0, rows, rpg)])
+        ref.sum().backward()
+        zc = z.detach().cuda().requires_grad_(True)
+        got = vb.functional.softmax_ce(zc, t.cuda(), rpg)
+        got.sum().backward()
+        assert rel(got, ref.detach()) < 1e-5 and rel(zc.grad, z.grad) < 1e-5
+
+
+def test_denorm_u8_is_byte_exact(vb):
+    """vg_denorm_u8 == utils.convert_to_uint8 of the reference (src/v2/utils.py:194-196), bit for bit."""
+    from oracle import v2 as o2
+    g = gen(5)
+    x = torch.cat([torch.randn(3 * 32 * 32 * 7 + 3, generator=g) * 1.2, torch.tensor([-1.0, 1.0, 0.0, -2.0, 2.0, 0.999999, -0.999999])])
+    assert torch.equal(vb.ops.denorm_u8(x.cuda()).cpu(), o2.convert_to_uint8(x))
+    xb = x.bfloat16()
+    assert torch.equal(vb.ops.denorm_u8(xb.cuda()).cpu(), o2.convert_to_uint8(xb.float()))

@@ -151,3 +151,10 @@ def test_v1_default(golden):
     assert close(g[:, :, :4, :4], fx["g_out_slice"]) and close(g.mean(), fx["g_out_mean"])
     losses = torch.stack([torch.stack(orc.step(r, zz)) for r, zz in harness.synthetic_batches_v1(cfg, fx["batch"], 2)])
     assert close(losses, fx["losses"], 1e-5)
+
+
+def test_oracle_convert_to_uint8_known_answers():
+    """utils.convert_to_uint8 (src/v2/utils.py:194-196): known answers at the clamp edges and the mid-points."""
+    from oracle import v2 as o2
+    x = torch.tensor([-2.0, -1.0, -0.5, 0.0, 0.5, 1.0, 2.0, 0.999, -0.999])
+    assert o2.convert_to_uint8(x).tolist() == [0, 0, 63, 127, 191, 255, 255, 254, 0]

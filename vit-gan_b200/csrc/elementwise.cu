@@ -192,6 +192,53 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 __global__ void bump_kernel(int* c) { *c += 1; }
 
+
+// ------------------------------------------------------------------------------------------------ loss head / sampling tail
+// Fused CrossEntropyLoss (mean reduction, class-index targets: src/v2/training.py:159) over `rows/rows_per_group` groups of
+// rows (e.g. the real half and the fake half of the merged discriminator pass): losses[g] = mean_{r in g} (lse(z_r) - z_r[t_r]);
+// dlogits = d(sum_g losses[g]) / dz.  Replaces log_softmax + nll_loss forward/backward + the reductions (~10 launches) by one.
+// The head is [B, 10]: one CTA is plenty.
+__global__ void __launch_bounds__(1024)
+softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, int rows, int C, int rows_per_group,
+                  float* __restrict__ losses, float* __restrict__ dlogits) {
+  __shared__ float s_loss[64];
+  const int n_groups = rows / rows_per_group;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_loss[i] = 0.f;
+  __syncthreads();
+  const float inv = 1.0f / (float)rows_per_group;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* z = logits + (size_t)r * C;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, z[c]);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(z[c] - m);
+    const int t = (int)targets[r];
+    const float lse = m + logf(sum);
+    const float rs = 1.0f / sum;
+    for (int c = 0; c < C; ++c) dlogits[(size_t)r * C + c] = (expf(z[c] - m) * rs - (c == t ? 1.0f : 0.f)) * inv;
+    atomicAdd(&s_loss[r / rows_per_group], (lse - z[t]) * inv);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < n_groups; g += blockDim.x) losses[g] = s_loss[g];
+}
+
+// utils.convert_to_uint8 (src/v2/utils.py:194-196): (images * 127.5 + 127.5).clamp(0, 255).to(uint8) -- two separately rounded
+// fp32 operations (no FMA contraction) and truncation, so the bytes equal the reference's on identical inputs.
+__device__ __forceinline__ uint8_t to_u8(float v) { return (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(v, 127.5f), 127.5f), 0.f), 255.f); }
+template <typename T>
+__global__ void denorm_u8_kernel(const T* __restrict__ x, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float v[4];
+    Vec4<T>::load(x + i, v);
+    uchar4 o;
+    o.x = to_u8(v[0]); o.y = to_u8(v[1]); o.z = to_u8(v[2]); o.w = to_u8(v[3]);
+    *reinterpret_cast<uchar4*>(out + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = to_u8(to_f<T>(x[j]));
+  }
+}
+
 }  // namespace
 }  // namespace vg
 
@@ -299,4 +346,23 @@ extern "C" int vg_act_backward(int dtype, int64_t n, const void* dy, const void*
   if (dtype == VG_F32) act_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(n, (const float*)dy, (const float*)aux, bact, act_param, (float*)out);
   else act_bwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(n, (const bf16*)dy, (const bf16*)aux, bact, act_param, (bf16*)out);
   return check_launch("act_backward");
+}
+
+extern "C" int vg_softmax_ce(const float* logits, const int64_t* targets, int rows, int C, int rows_per_group, float* losses,
+                             float* dlogits, void* stream) {
+  VG_REQUIRE(logits && targets && losses && dlogits, VG_ERR_ARG, "softmax_ce: NULL argument");
+  VG_REQUIRE(rows >= 1 && C >= 1 && rows_per_group >= 1 && rows % rows_per_group == 0 && rows / rows_per_group <= 64, VG_ERR_SHAPE,
+             "softmax_ce: rows %d must be a multiple of rows_per_group %d with at most 64 groups", rows, rows_per_group);
+  softmax_ce_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, targets, rows, C, rows_per_group, losses, dlogits);
+  return check_launch("softmax_ce");
+}
+
+extern "C" int vg_denorm_u8(int dtype, const void* x, int64_t n, uint8_t* out, void* stream) {
+  if (n == 0) return VG_OK;
+  VG_REQUIRE(x && out, VG_ERR_ARG, "denorm_u8: NULL argument");
+  VG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, VG_ERR_ALIGN, "denorm_u8: unaligned buffers");
+  const int grid = grid1d((n + 3) / 4, 256);
+  if (dtype == VG_F32) denorm_u8_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, n, out);
+  else denorm_u8_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, n, out);
+  return check_launch("denorm_u8");
 }

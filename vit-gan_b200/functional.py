@@ -597,3 +597,27 @@ class ClsRowFn(Function):
         dx = torch.zeros(B, S, E, dtype=dy.dtype, device=dy.device)
         ops.copy_rows(dy.contiguous(), E, B, E, dx, S * E)
         return dx
+
+
+# --------------------------------------------------------------------------------------------------
+# loss head: nn.CrossEntropyLoss (mean) per group of rows, one launch forward, one multiply backward
+# --------------------------------------------------------------------------------------------------
+class SoftmaxCEFn(Function):
+    """losses[g] = CrossEntropyLoss(logits[g*n:(g+1)*n], targets[...]) (src/v2/training.py:159,182-210)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, rows_per_group):
+        losses, dlog = ops.softmax_ce(logits.contiguous(), targets, rows_per_group)
+        ctx.save_for_backward(dlog)
+        return losses
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dlog,) = ctx.saved_tensors
+        G = g.shape[0]
+        return (dlog.view(G, -1) * g.reshape(G, 1)).view_as(dlog), None, None
+
+
+def softmax_ce(logits, targets, rows_per_group=None):
+    return SoftmaxCEFn.apply(logits, targets, rows_per_group or logits.shape[0])

@@ -368,3 +368,27 @@ def adam_step(p, g, m, v, step_count, lr, b1, b2, eps, wd, decoupled, grad_scale
     check(lib.vg_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd,
                            int(decoupled), grad_scale, step_count.data_ptr(), _ptr(shadow), stream()), "vg_adam_step")
     _count(2)
+
+
+def softmax_ce(logits, targets, rows_per_group):
+    """-> (losses[G], dlogits[rows, C]) of the fused cross-entropy head (see vg_softmax_ce)."""
+    _req(logits, "logits")
+    if logits.dtype != torch.float32 or targets.dtype != torch.int64 or not logits.is_contiguous():
+        raise TypeError("vitgan_b200.softmax_ce: contiguous fp32 logits and int64 targets required")
+    rows, c = logits.shape
+    losses = torch.empty(rows // rows_per_group, dtype=torch.float32, device=logits.device)
+    dlog = torch.empty_like(logits)
+    check(lib.vg_softmax_ce(logits.data_ptr(), targets.data_ptr(), rows, c, rows_per_group, losses.data_ptr(), dlog.data_ptr(), stream()),
+          "vg_softmax_ce")
+    _count()
+    return losses, dlog
+
+
+def denorm_u8(x):
+    """uint8(clamp(x * 127.5 + 127.5, 0, 255)) -- utils.convert_to_uint8 of the reference, same shape as x."""
+    _req(x, "x")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(lib.vg_denorm_u8(dt(x), x.data_ptr(), x.numel(), out.data_ptr(), stream()), "vg_denorm_u8")
+    _count()
+    return out

@@ -202,15 +202,21 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
         ones = torch.ones(b, 1, device=dev)
         zeros = torch.zeros(b, 1, device=dev)
         crit = F.binary_cross_entropy
+    fused_ce = loss_kind == "ce" and merge_d_passes      # the optimised step also uses the one-launch CE head (vg_softmax_ce)
     disc_opt.zero_grad(set_to_none=False) if isinstance(disc_opt, FusedAdam) else disc_opt.zero_grad(set_to_none=True)
     if merge_d_passes:
         fake = gen(noise)
         if d_buckets is not None:
             d_buckets.arm()
         out = disc(torch.cat([real, fake.detach().to(real.dtype)], 0)).float()
-        per = crit(out, torch.cat([ones, zeros], 0), reduction="none").view(2, -1)
-        loss_real, loss_fake = per[0].mean(), per[1].mean()
-        (loss_real + loss_fake).backward()
+        if fused_ce and out.is_cuda:
+            per = Fn.softmax_ce(out, torch.cat([ones, zeros], 0), b)          # [loss_real, loss_fake], one launch
+            loss_real, loss_fake = per[0], per[1]
+            per.sum().backward()
+        else:
+            per = crit(out, torch.cat([ones, zeros], 0), reduction="none").view(2, -1)
+            loss_real, loss_fake = per[0].mean(), per[1].mean()
+            (loss_real + loss_fake).backward()
     else:
         loss_real = crit(disc(real).float(), ones)
         loss_real.backward()
@@ -228,7 +234,10 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
         g_buckets.arm()
     with Fn.skip_param_grads(skip_unused_d_grads):
         out = disc(fake)
-    loss_g = crit(out.float(), ones)
+    if fused_ce and out.is_cuda:
+        loss_g = Fn.softmax_ce(out.float(), ones, b)[0]
+    else:
+        loss_g = crit(out.float(), ones)
     loss_g.backward()     # with skip_unused_d_grads only D's blocks were recorded with skip_pg; G's are unaffected
     if g_buckets is not None:
         g_buckets.finish()

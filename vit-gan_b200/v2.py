@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from . import lib as L
+from . import ops
 
 
 @dataclasses.dataclass
@@ -210,3 +211,17 @@ class ViTGAN(nn.Module):
         generated_images = self.generator(z)
         discriminator_output = self.discriminator(generated_images)
         return generated_images, discriminator_output
+
+
+@torch.no_grad()
+def sample_uint8(generator, noise):
+    """Batched sampling path: the reference re-runs the generator per image and de-normalises on the
+    host (src/v2/generation.py:47-56, utils.convert_to_uint8 utils.py:194-196); here one batched forward through the CUDA
+    kernels and a fused `* 127.5 + 127.5 -> clamp -> uint8` kernel.  noise: (B, C, I, I) -> uint8 (B, C, I, I)."""
+    was_training = generator.training
+    generator.eval()
+    try:
+        img = generator(noise)
+    finally:
+        generator.train(was_training)
+    return ops.denorm_u8(img.float() if img.dtype != torch.float32 else img)
