@@ -374,6 +374,7 @@ def run_ours(args):
         def eager(real, noise):
             return vb.train.gan_step_microbatched(gen, disc, gopt, dopt, real, noise, loss_kind, n_micro=n_micro, d_buckets=d_b,
                                                   g_buckets=g_b, skip_unused_d_grads=skip_unused, merge_d_passes=merge_d)
+        vb.functional.set_param_grad_stream(not args.no_pg_stream)     # eager steps use the same two-stream schedule the graph captures
         # launches per step, counted on one eager step (the graph replays exactly these)
         eager(*devb[0])
         torch.cuda.synchronize()

@@ -273,6 +273,11 @@ def test_embed_split_colsum_fill(vb):
         assert torch.equal(dtok.cpu().view(B, S - 1, E), dx[:, 1:])
         assert rel(dcls, dx[:, 0].sum(0)) < 1e-6
         assert rel(dpos, dx.sum(0) if has_cls else dx[:, 1:].sum(0)) < 1e-6
+    for Bb, Ss, Ee, dt_ in ((512, 65, 128, torch.bfloat16), (37, 9, 128, torch.bfloat16), (70, 5, 768, torch.float32), (3, 4, 36, torch.float32)):
+        dxl = torch.randn(Bb, Ss, Ee, generator=g).to(dt_)        # vectorised kernel (16 B column groups) and its tails
+        dtok, dcls, dpos = vb.ops.embed_bwd_split(dxl.cuda(), False)
+        assert torch.equal(dtok.cpu().view(Bb, Ss - 1, Ee), dxl[:, 1:])
+        assert rel(dcls, dxl[:, 0].float().sum(0)) < 1e-5 and rel(dpos, dxl[:, 1:].float().sum(0)) < 1e-5
     x = torch.randn(1000, 200, generator=g)
     assert rel(vb.ops.colsum(x.cuda()), x.sum(0)) < 1e-5
     assert rel(vb.ops.colsum(x.bfloat16().cuda()), x.bfloat16().float().sum(0)) < 1e-5

@@ -88,6 +88,57 @@ __global__ void embed_bwd_split_kernel(int B, int S, int E, const T* __restrict_
   }
 }
 
+// vectorised variant (E a multiple of 16 B worth of elements, E/V <= 256): thread = (batch lane ty, 16-byte column group);
+// CTA = token s x a slice of the batch; 16 B loads/stores, two batch rows in flight per thread, smem fold over the batch lanes.
+template <typename T>
+__global__ void __launch_bounds__(256)
+embed_bwd_split_vec_kernel(int B, int S, int E, const T* __restrict__ dx, T* __restrict__ dtok, float* __restrict__ dcls,
+                           float* __restrict__ dpos, int pos_has_cls) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float red[256 * V];
+  const int s = blockIdx.x, cgs = E / V, lanes = 256 / cgs;
+  const int cg = threadIdx.x % cgs, ty = threadIdx.x / cgs;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  if (ty < lanes) {
+    const int step = gridDim.z * lanes;
+    int b = blockIdx.z * lanes + ty;
+    for (; b + step < B; b += 2 * step) {
+      const uint4 v0 = *reinterpret_cast<const uint4*>(dx + ((int64_t)b * S + s) * E + cg * V);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(dx + ((int64_t)(b + step) * S + s) * E + cg * V);
+      const T* e0 = reinterpret_cast<const T*>(&v0);
+      const T* e1 = reinterpret_cast<const T*>(&v1);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += to_f<T>(e0[j]) + to_f<T>(e1[j]);
+      if (s > 0) {
+        *reinterpret_cast<uint4*>(dtok + ((int64_t)b * (S - 1) + (s - 1)) * E + cg * V) = v0;
+        *reinterpret_cast<uint4*>(dtok + ((int64_t)(b + step) * (S - 1) + (s - 1)) * E + cg * V) = v1;
+      }
+    }
+    for (; b < B; b += step) {
+      const uint4 v0 = *reinterpret_cast<const uint4*>(dx + ((int64_t)b * S + s) * E + cg * V);
+      const T* e0 = reinterpret_cast<const T*>(&v0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += to_f<T>(e0[j]);
+      if (s > 0) *reinterpret_cast<uint4*>(dtok + ((int64_t)b * (S - 1) + (s - 1)) * E + cg * V) = v0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {       // column c lives in group c / V, element c % V of every batch lane
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(l * cgs + c / V) * V + (c % V)];
+    if (s == 0) {
+      atomicAdd(&dcls[c], t);
+      if (pos_has_cls) atomicAdd(&dpos[c], t);
+    } else {
+      atomicAdd(&dpos[(int64_t)(pos_has_cls ? s : s - 1) * E + c], t);
+    }
+  }
+}
+
 int grid1d(int64_t total, int block) {
   const int64_t need = (total + block - 1) / block;
   return (int)max((int64_t)1, min(need, (int64_t)num_sms() * 16));
@@ -152,6 +203,17 @@ extern "C" int vg_fill_rows(int dtype, int B, int S, int E, int row, const float
 
 extern "C" int vg_embed_bwd_split(int dtype, int B, int S, int E, const void* dx, void* dtok, float* dcls, float* dpos,
                                   int pos_has_cls, void* stream) {
+  const int vel = dtype == VG_F32 ? 4 : 8;
+  if (E % vel == 0 && E / vel <= 256 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dtok) & 15) == 0) {
+    const int lanes = 256 / (E / vel);
+    const int zs = max(1, min((B + 2 * lanes - 1) / (2 * lanes), (4 * num_sms() + S - 1) / S));     // >= 2 batch rows per thread, ~4 CTAs per SM
+    dim3 g(S, 1, zs);
+    if (dtype == VG_F32)
+      embed_bwd_split_vec_kernel<float><<<g, 256, 0, as_stream(stream)>>>(B, S, E, (const float*)dx, (float*)dtok, dcls, dpos, pos_has_cls);
+    else
+      embed_bwd_split_vec_kernel<bf16><<<g, 256, 0, as_stream(stream)>>>(B, S, E, (const bf16*)dx, (bf16*)dtok, dcls, dpos, pos_has_cls);
+    return check_launch("embed_bwd_split");
+  }
   const int bx = E >= 128 ? 128 : 32;
   int zsplit = max(1, min(B, (4 * num_sms()) / max(1, S * ((E + bx - 1) / bx))));
   dim3 grid(S, (E + bx - 1) / bx, zsplit);

@@ -764,7 +764,8 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   static int bn_env = -1;
   if (bn_env < 0) { const char* e = getenv("VG_TC_BN"); bn_env = e ? atoi(e) : 0; }
   bool wide = stageable && a.N % 256 == 0 && a.K >= 512 &&
-              ((int64_t)((a.M + BM - 1) / BM) * (a.N / 256) >= sms0 || (a.accumulate && a.K >= 4096));   // split-K supplies the parallelism
+              ((int64_t)((a.M + BM - 1) / BM) * (a.N / 256) >= sms0 ||
+               (a.accumulate && a.K >= 4096 && (int64_t)((a.M + BM - 1) / BM) * (a.N / 256) >= 8));   // split-K supplies the parallelism
   if (bn_env == 128) wide = false;
   if (bn_env == 256) wide = stageable && a.N >= 256;
   const int bn = wide ? 256 : BN;
@@ -781,7 +782,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
     // split-K factor: the smallest s (each split keeps >= 4 k-blocks) whose tiles*s work items fill >= 90 % of the
     // CTA rounds they need, else the best-filling one (e.g. 54 wide tiles: s = 8 -> 432 items = 2.92 rounds of 148)
     const int tiles = p.m_tiles * p.n_tiles;
-    const int smax = max(1, min(64, (p.kb_total + 3) / 4));
+    const int smax = max(1, min(sms, (p.kb_total + 3) / 4));
     int best = 1; double best_eff = 0.0;
     for (int sp = 1; sp <= smax; ++sp) {
       const int items = tiles * sp, rounds = (items + sms - 1) / sms;
