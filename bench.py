@@ -289,10 +289,19 @@ def kernel_rooflines(vb, spec, pk):
 
     dom = out[0]
     key = "frac_tensor" if dom["bound"] == "tensor" else "frac_hbm"
+    traffic = None
+    try:       # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(dom["kernel"])
+        if t and (M, E) == (33280, 128):
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roof = {"kernel": dom["kernel"], "bound": dom["bound"],
             "achieved": dom["tflops"] if dom["bound"] == "tensor" else dom["gbs"],
             "peak": pk["tf_burst"] if dom["bound"] == "tensor" else pk["hbm"],
-            "unit": "TFLOP/s" if dom["bound"] == "tensor" else "GB/s", "frac": dom[key], "traffic": None,
+            "unit": "TFLOP/s" if dom["bound"] == "tensor" else "GB/s", "frac": dom[key], "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram read + write, ncu --set full; outputs stay in L2 during the kernel)",
             "peak_source": pk["src"], "us_per_launch": dom["us"],
             "note": "timed alone inside one CUDA graph over rotating >L2 buffer sets (burst peak); traffic from profiles/ ncu --set full"}
     return roof, out

@@ -23,7 +23,7 @@ def main(path):
             if w in idx:
                 print(f"    {w:75s} {r[idx[w]]:>16s} {units[idx[w]]}")
         rd, wr = r[idx["dram__bytes_read.sum"]], r[idx["dram__bytes_write.sum"]]
-        print(f"    {'traffic = dram read + write':75s} {rd} + {wr} {units[idx['dram__bytes_read.sum']]}")
+        print(f"    {'traffic = dram read + write':75s} {rd} {units[idx['dram__bytes_read.sum']]} + {wr} {units[idx['dram__bytes_write.sum']]}")
 
 
 if __name__ == "__main__":
