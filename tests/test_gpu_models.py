@@ -469,3 +469,29 @@ def test_v2_batched_sampling_uint8(vb, golden):
     assert got.dtype == torch.uint8 and got.shape == noise.shape
     assert (got.int() - want.int()).abs().max() <= 1
     vb.set_precision("bf16")
+
+
+def test_v2_c4_shaped_step_vs_oracle_live(vb):
+    """BASELINE configs[3] geometry (128x128, patch 8, E=768 -> S=257, d=192, mlp 1536) at a size the oracle finishes in
+    seconds: 2 blocks, batch 48 (M = 12 336 rows: the QKV / fc1 / dgrad / wgrad GEMMs take the 256-wide tcgen05 tiles and the
+    split-K wide wgrad), one optimised G+D step (merged D pass, unused D grads skipped, fused CE head) in bf16 against the
+    oracle's step in fp32 on the same seeded init and data: discriminator logits and the three losses within 2e-2."""
+    vb.set_precision("bf16")
+    over = dict(image_size=128, patch_size=8, embeddings_dimension=768, transformer_blocks_count=2)
+    ocfg = o2.V2Config(**over, batch_size=3 * 128 * 128)
+    B = 48
+    (real, noise), = harness.synthetic_batches_v2(ocfg, B, 1)
+    orc = harness.OracleV2(ocfg, seed=0)
+    with torch.no_grad():
+        d_ref = orc.discriminator(real)
+    ref = torch.stack(orc.step(real, noise))
+    torch.manual_seed(0)
+    gan = vb.v2.ViTGAN(vb.v2.Config(**over, batch_size=3 * 128 * 128)).cuda()
+    with torch.no_grad():
+        assert rel(gan.discriminator(real.cuda()), d_ref) < 2e-2
+    gnet, dnet = vb.train.FlatNet(gan.generator), vb.train.FlatNet(gan.discriminator)
+    go = vb.train.FusedAdam(gnet, 5e-4, weight_decay=1e-3, decoupled=True)
+    do = vb.train.FusedAdam(dnet, 5e-4, weight_decay=1e-3, decoupled=True)
+    got = torch.stack([t.reshape(()) for t in vb.train.gan_step(gan.generator, gan.discriminator, go, do, real.cuda(), noise.cuda(), "ce",
+                                                               skip_unused_d_grads=True, merge_d_passes=True)])
+    assert rel(got, ref) < 2e-2
