@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VG_ABI_VERSION 2
+#define VG_ABI_VERSION 3
 
 typedef enum { VG_F32 = 0, VG_BF16 = 1 } vg_dtype;
 typedef enum {
@@ -79,6 +79,14 @@ typedef struct {
                              * (trans_a=1, A = dY) this is the bias gradient colsum(dY), obtained on the tensor cores from an
                              * extra N=16 MMA against a tile of ones.  tcgen05 path in accumulate mode only
                              * (VG_ERR_UNSUPPORTED otherwise, nothing launched). */
+  /* optional fused LayerNorm of the OUTPUT rows (src/v2/modules.py:168,172: the norm that follows out-proj / fc2 + skip):
+   * ln_out = LN(C_row) * ln_gamma + ln_beta (same dtype as C), ln_mean / ln_rstd [M] fp32 saved for the backward.  The
+   * statistics are taken over the bf16-rounded C values, i.e. exactly what a separate vg_layernorm_fwd would read.
+   * tcgen05 path, N == 128 (one tile = one complete row), bf16 C, no aux / c_pre (VG_ERR_UNSUPPORTED otherwise). */
+  const float* ln_gamma; const float* ln_beta;
+  void* ln_out; int64_t ld_ln;
+  float* ln_mean; float* ln_rstd;
+  float ln_eps;
 } vg_gemm_args;
 
 int vg_version(void);

@@ -495,3 +495,26 @@ def test_v2_c4_shaped_step_vs_oracle_live(vb):
     got = torch.stack([t.reshape(()) for t in vb.train.gan_step(gan.generator, gan.discriminator, go, do, real.cuda(), noise.cuda(), "ce",
                                                                skip_unused_d_grads=True, merge_d_passes=True)])
     assert rel(got, ref) < 2e-2
+
+
+def test_v2_fused_layernorm_epilogue_matches_unfused(vb):
+    """functional.set_fused_layernorm_epilogue(True): out-proj / fc2 GEMMs also emit the following LayerNorm (chained across
+    blocks) -- discriminator logits, input gradient and every parameter gradient equal the unfused path to bf16 noise."""
+    vb.set_precision("bf16")
+    cfg = vb.v2.Config(batch_size=3 * 32 * 32, transformer_blocks_count=3)
+    torch.manual_seed(0)
+    gan = vb.v2.ViTGAN(cfg).cuda()
+    x = torch.randn(24, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    res = {}
+    for fused in (False, True):
+        vb.functional.set_fused_layernorm_epilogue(fused)
+        try:
+            gan.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            out = gan.discriminator(xi)
+            out.float().square().sum().backward()
+            res[fused] = (out.detach().float(), xi.grad.clone(), {k: p.grad.clone() for k, p in gan.discriminator.named_parameters()})
+        finally:
+            vb.functional.set_fused_layernorm_epilogue(False)
+    assert rel(res[True][0], res[False][0]) < 1e-2 and rel(res[True][1], res[False][1]) < 2e-2
+    cmp_grads(res[True][2], res[False][2], 2e-2, "fused LayerNorm epilogue")

@@ -388,3 +388,26 @@ def test_denorm_u8_is_byte_exact(vb):
     assert torch.equal(vb.ops.denorm_u8(x.cuda()).cpu(), o2.convert_to_uint8(x))
     xb = x.bfloat16()
     assert torch.equal(vb.ops.denorm_u8(xb.cuda()).cpu(), o2.convert_to_uint8(xb.float()))
+
+
+@pytest.mark.parametrize("M,K,res", [(33280 // 8, 128, True), (300, 256, True), (65, 128, False)])
+def test_gemm_fused_layernorm_epilogue(vb, M, K, res):
+    """vg_gemm ln_*: C = A W^T + b (+ residual) and LayerNorm(C) with its statistics from ONE launch (N == 128); the
+    normalised output must equal a separate vg_layernorm_fwd on the stored bf16 C to bf16 rounding, and the fp32 formula."""
+    L = vb.lib
+    g = gen(M + K)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(128, K, generator=g) * 0.1).bfloat16()
+    b = torch.randn(128, generator=g)
+    r = torch.randn(M, 128, generator=g).bfloat16() if res else None
+    gam, bet = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    c, xn, mean, rstd = vb.ops.gemm(a.cuda(), w.cuda(), bias=b.cuda(), residual=None if r is None else r.cuda(),
+                                    ln=(gam.cuda(), bet.cuda(), 1e-5), path=L.GEMM_TCGEN05)
+    c_ref = a.float() @ w.float().t() + b + (0 if r is None else r.float())
+    assert rel(c, c_ref) < BF16_TOL
+    xn2, mean2, rstd2 = vb.ops.layernorm_fwd(c, gam.cuda(), bet.cuda())
+    assert rel(mean, mean2) < 1e-5 and rel(rstd, rstd2) < 1e-5
+    assert rel(xn, xn2) < 1e-2          # both are bf16 roundings of the same fp32 value up to summation order
+    assert rel(xn, F.layer_norm(c.float().cpu(), (128,), gam, bet, 1e-5)) < BF16_TOL
+    with pytest.raises(L.VitganError, match="LayerNorm"):
+        vb.ops.gemm(a.cuda(), torch.randn(256, K).bfloat16().cuda(), ln=(torch.ones(256).cuda(), torch.zeros(256).cuda(), 1e-5))

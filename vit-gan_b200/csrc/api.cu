@@ -64,7 +64,7 @@ extern "C" int vg_gemm(const vg_gemm_args* args, void* stream) {
   VG_REQUIRE(a.A && a.B && a.C, VG_ERR_ARG, "vg_gemm: NULL operand");
   cudaStream_t st = as_stream(stream);
   if (a.path == VG_GEMM_SIMT) {
-    VG_REQUIRE(!a.a_rowsum, VG_ERR_UNSUPPORTED, "vg_gemm(simt): a_rowsum is a tcgen05-path feature");
+    VG_REQUIRE(!a.a_rowsum && !a.ln_gamma, VG_ERR_UNSUPPORTED, "vg_gemm(simt): a_rowsum / fused LayerNorm are tcgen05-path features");
     return gemm_simt_launch(a, st);
   }
   const char* why = "";
@@ -75,6 +75,6 @@ extern "C" int vg_gemm(const vg_gemm_args* args, void* stream) {
   }
   // AUTO: tensor cores for bf16 problems the tcgen05 kernel accepts, CUDA cores otherwise (fp32 parity path,
   // tiny heads).  Both are this library's own sm_100a kernels -- there is no CPU or vendor-library fallback.
-  VG_REQUIRE(ok || !a.a_rowsum, VG_ERR_UNSUPPORTED, "vg_gemm: a_rowsum unsupported here: %s", why);
+  VG_REQUIRE(ok || (!a.a_rowsum && !a.ln_gamma), VG_ERR_UNSUPPORTED, "vg_gemm: a_rowsum / fused LayerNorm unsupported here: %s", why);
   return ok ? gemm_tc_launch(a, st) : gemm_simt_launch(a, st);
 }

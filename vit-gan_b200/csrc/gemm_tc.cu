@@ -32,7 +32,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STG_BYTES = 8192;         // per epilogue warp: two 4 KB swizzled staging tiles (32 rows x 128 B each)
 constexpr int BIAS_BYTES = EPI_WARPS * 64 * 4;   // per epilogue warp: the 64 bias values of its column slab
 constexpr int ONES_BYTES = 2048;        // [16 n x 64 k] bf16 tile of 1.0: B operand of the row-sum MMA (layout-agnostic)
-constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int LN_BYTES = EPI_WARPS * 128 * 4 + 2 * EPI_WARPS * 32 * 4;   // fused LayerNorm: per warp gamma|beta of its 64 columns + 2 exchange slots
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int TMEM_COLS = NACC * BN;   // 256: power of two >= 32
 constexpr int RS_COL = TMEM_COLS, RS_N = 16;   // row-sum accumulators (a_rowsum): 16 columns per stage behind the tile accumulators
 
@@ -170,7 +171,10 @@ struct Params {
   int epi_tma;                         // 1: smem-staged epilogue with TMA loads (residual/aux) and TMA stores / reduce-add
   int na_stages;                       // weight-stationary kernel: depth of the A k-block ring
   float* rowsum;                       // a_rowsum: rowsum[m] += sum_k opA(A)[m,k] (bias gradient of a wgrad GEMM) or NULL
+  const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd; float ln_eps;   // fused LayerNorm of the output rows (N == 128) or NULL
 };
+// per-warp scratch of the fused LayerNorm epilogue
+struct LnScratch { float* gb; float* slots; };   // gb: gamma[64] | beta[64] of this warp's columns; slots: [2][EPI_WARPS][32] row partials
 
 template <typename TC>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&r)[32], int m, int n0) {
@@ -241,9 +245,11 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 //   fp32: chunk cc has its own 4 KB tile (32 rows x 32 fp32)
 // Tiles use the TMA 128B swizzle: 16 B chunk L of row r is stored at r*128 + ((L ^ (r & 7)) * 16)  (conflict-free).
 // bufC holds the residual tile on entry (if any) and the output on exit; bufX holds aux on entry or c_pre on exit.
-template <bool F32, int ACT>
-__device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r)[32], int lane, int cc, int n0,
+template <bool F32, int ACT, bool KEEP = false>
+__device__ __forceinline__ void staged_chunk(const Params& p, uint32_t (&r)[32], int lane, int cc, int n0,
                                              uint32_t bufC, uint32_t bufX, const float* __restrict__ bias_s) {
+  // KEEP (bf16 only): the final, bf16-ROUNDED output values are written back into r[] as floats (fused LayerNorm input:
+  // the statistics are then taken over exactly the values a separate LayerNorm kernel would read from memory)
   const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
   if (F32) {
@@ -301,20 +307,64 @@ __device__ __forceinline__ void staged_chunk(const Params& p, const uint32_t (&r
         v[0] += bf16_lo(x0); v[1] += bf16_hi(x0); v[2] += bf16_lo(x1); v[3] += bf16_hi(x1);
         v[4] += bf16_lo(x2); v[5] += bf16_hi(x2); v[6] += bf16_lo(x3); v[7] += bf16_hi(x3);
       }
-      sts128(bufC + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      const uint32_t q0 = pack_bf16(v[0], v[1]), q1 = pack_bf16(v[2], v[3]), q2 = pack_bf16(v[4], v[5]), q3 = pack_bf16(v[6], v[7]);
+      sts128(bufC + off, q0, q1, q2, q3);
+      if (KEEP) {
+        r[h * 8 + 0] = q0 << 16; r[h * 8 + 1] = q0 & 0xFFFF0000u; r[h * 8 + 2] = q1 << 16; r[h * 8 + 3] = q1 & 0xFFFF0000u;
+        r[h * 8 + 4] = q2 << 16; r[h * 8 + 5] = q2 & 0xFFFF0000u; r[h * 8 + 6] = q3 << 16; r[h * 8 + 7] = q3 & 0xFFFF0000u;
+      }
     }
   }
+}
+
+// Fused LayerNorm of the 128-wide output row (N == BN == 128): this thread holds 64 of the row's values (r0 | r1, already
+// rounded to bf16), its partner warp (same TMEM lane quadrant, other column half) the other 64.  Two-pass statistics with one
+// smem exchange + 64-thread named barrier per pass; the normalised row goes to bufX (-> TMA store through the c_pre map).
+__device__ __forceinline__ void ln_epilogue(const Params& p, const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane, int ew, int m,
+                                            uint32_t bufX, const LnScratch& ln) {
+  const int quad = ew & 3, half = ew >> 2, partner = ew ^ 4;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
+  ln.slots[ew * 32 + lane] = s;
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+  const float mean = (s + ln.slots[partner * 32 + lane]) * (1.0f / 128.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float a = __uint_as_float(r0[i]) - mean, b = __uint_as_float(r1[i]) - mean;
+    q = fmaf(a, a, q); q = fmaf(b, b, q);
+  }
+  ln.slots[EPI_WARPS * 32 + ew * 32 + lane] = q;
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+  const float rstd = rsqrtf((q + ln.slots[EPI_WARPS * 32 + partner * 32 + lane]) * (1.0f / 128.0f) + p.ln_eps);
+  const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cc * 32 + h * 8 + j;
+        const float v = __uint_as_float(cc == 0 ? r0[h * 8 + j] : r1[h * 8 + j]);
+        y[j] = fmaf((v - mean) * rstd, ln.gb[c], ln.gb[64 + c]);
+      }
+      sts128(bufX + row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+    }
+  }
+  if (half == 0 && m < p.M) { p.ln_mean[m] = mean; p.ln_rstd[m] = rstd; }
 }
 
 // One epilogue warp's share ([32 rows x 64 columns]) of one accumulator tile, staged (TMA) epilogue:
 //   wait for the staging tiles -> stage bias -> prefetch residual/aux by TMA -> wait accumulator -> TMEM -> registers ->
 //   release TMEM -> math -> swizzled smem -> TMA store / reduce-add.
-template <int MODE, int ACT>
+template <int MODE, int ACT, bool LN = false>
 __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_pre,
                                             const CUtensorMap* tmap_res, const CUtensorMap* tmap_aux, uint32_t taddr,
                                             uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
                                             uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane,
-                                            uint32_t rs_taddr = 0u, bool release = true) {
+                                            uint32_t rs_taddr = 0u, bool release = true, int ew = 0, LnScratch ln = LnScratch{nullptr, nullptr}) {
   // release == false: more 64-column groups of the same accumulator follow (256-wide tiles); the last group frees TMEM
   // rs_taddr != 0: this warp also drains one row-sum column (a_rowsum) of its 32 rows and reduce-adds it into p.rowsum
   constexpr bool f32 = MODE == 2;
@@ -326,6 +376,12 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
     const int c0 = n0 + lane, c1 = n0 + 32 + lane;
     bias_s[lane] = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
     bias_s[32 + lane] = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
+    __syncwarp();
+  }
+  constexpr bool do_ln = LN && MODE == 1;     // compile-time: the LayerNorm code exists only in the one instantiation that needs it
+  if (do_ln) {                                // ... and its 64 LayerNorm gammas / betas (N == 128: always in range)
+    ln.gb[lane] = __ldg(p.ln_gamma + n0 + lane); ln.gb[32 + lane] = __ldg(p.ln_gamma + n0 + 32 + lane);
+    ln.gb[64 + lane] = __ldg(p.ln_beta + n0 + lane); ln.gb[96 + lane] = __ldg(p.ln_beta + n0 + 32 + lane);
     __syncwarp();
   }
   if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
@@ -350,8 +406,14 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   if (MODE == 2 && rs_taddr != 0u) bias_s[lane] = __uint_as_float(rs);   // bias staging is idle in accumulate mode
   if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
   if (!(p.dbg & 1)) {
-    staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
-    staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
+    if (do_ln) {
+      staged_chunk<f32, ACT, do_ln>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
+      staged_chunk<f32, ACT, do_ln>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
+      ln_epilogue(p, r0, r1, lane, ew, m0 + lane, bufX, ln);
+    } else {
+      staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
+      staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
+    }
     fence_async_smem();                       // generic-proxy smem writes -> visible to the async (TMA) proxy
     __syncwarp();
     if (lane == 0 && m0 < p.M && n0 < p.N) {
@@ -365,7 +427,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
         if (n0 + 32 < p.N) tma_store_2d(tmap_c, bufX, n0 + 32, m0);
       } else {
         tma_store_2d(tmap_c, bufC, n0, m0);
-        if (has_pre) tma_store_2d(tmap_pre, bufX, n0, m0);
+        if (has_pre || do_ln) tma_store_2d(tmap_pre, bufX, n0, m0);     // c_pre, or the fused LayerNorm output (same map slot)
       }
       tma_commit();
     }
@@ -378,7 +440,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
 // BNT: tile width.  128 (4-stage ring) for the skinny / memory-bound shapes; 256 (3 stages, both accumulator stages = all 512
 // TMEM columns) for the compute-bound ones: a 128x128 tile reads 32 KB of smem per 2.1 MFLOP (256 clk of smem bandwidth for 256
 // clk of tensor pipe: smem-bound), a 128x256 tile 48 KB per 4.2 MFLOP (384 vs 512 clk).
-template <int MODE, int ACT, int BNT>
+template <int MODE, int ACT, int BNT, bool LN = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
@@ -391,7 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t stg_base = smem_base + NSTAGES * STAGE_BYTES;          // 1024-aligned (stage bytes are multiples of 1024)
   const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;
   const uint32_t ones_base = bias_base + BIAS_BYTES;                    // 1024-aligned (all regions above are multiples of 1024)
-  const uint32_t bar_base = ones_base + ONES_BYTES;
+  const uint32_t ln_base = ones_base + ONES_BYTES;
+  const uint32_t bar_base = ln_base + LN_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGES + a); };
@@ -512,6 +575,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t wbar = warp_bar(ew);
       uint32_t wphase = 0;
       float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
+      float* ln_f = reinterpret_cast<float*>(smem_dyn + (ln_base - smem_u32(smem_dyn)));
+      const LnScratch ln = LN ? LnScratch{ln_f + ew * 128, ln_f + EPI_WARPS * 128} : LnScratch{nullptr, nullptr};
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
         const int m0 = m_blk * BM + quad * 32;
@@ -519,9 +584,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int g = 0; g < BN / 128; ++g) {           // this warp's 64-column groups of the tile (one at BN = 128, two at 256)
           const int col = half * (BN / 2) + g * 64;
-          staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
-                                 tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
-                                 g == BN / 128 - 1);
+          staged_tile<MODE, ACT, LN>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
+                                     tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
+                                     g == BN / 128 - 1, ew, ln);
         }
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
@@ -737,6 +802,11 @@ bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
   if (a.accumulate && a.c_dtype != VG_F32) { *why = "accumulate needs fp32 C"; return false; }
   if (a.accumulate && (a.act != VG_ACT_NONE || a.c_pre || a.bias || a.residual)) { *why = "accumulate supports a plain epilogue only"; return false; }
   if (act_needs_aux(a.act) && !a.aux) { *why = "activation needs aux"; return false; }
+  if (a.ln_gamma) {
+    if (a.N != 128 || a.c_dtype != VG_BF16 || a.aux || a.c_pre || a.accumulate || a.c_row_group || a.res_row_mod) { *why = "fused LayerNorm needs N == 128, bf16 C, no aux / c_pre / accumulate / row remap"; return false; }
+    if (!a.ln_beta || !a.ln_out || !a.ln_mean || !a.ln_rstd || (reinterpret_cast<uintptr_t>(a.ln_out) & 15) || (a.ld_ln * 2) % 16) { *why = "fused LayerNorm: missing or unaligned outputs"; return false; }
+    if ((reinterpret_cast<uintptr_t>(a.C) & 15) || (a.ldc * 2) % 16 || (a.residual && ((reinterpret_cast<uintptr_t>(a.residual) & 15) || (a.ldres * 2) % 16))) { *why = "fused LayerNorm needs TMA-addressable C / residual"; return false; }
+  }
   if (a.a_rowsum) {
     const bool c_tma = (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * 4) % 16 == 0 && a.c_row_group == 0 && a.res_row_mod == 0;
     if (!a.accumulate || !c_tma) { *why = "a_rowsum needs the split-K accumulate mode with a TMA-addressable fp32 C"; return false; }
@@ -758,7 +828,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const int esz0 = a.c_dtype == VG_F32 ? 4 : 2;
   auto tma_ok0 = [&](const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz0) % 16 == 0; };
   const char* dbg0 = getenv("VG_TC_DBG");
-  const bool stageable = !(dbg0 && (atoi(dbg0) & 2)) && a.c_row_group == 0 && a.res_row_mod == 0 && !a.a_rowsum && tma_ok0(a.C, a.ldc) &&
+  const bool stageable = !(dbg0 && (atoi(dbg0) & 2)) && a.c_row_group == 0 && a.res_row_mod == 0 && !a.a_rowsum && !a.ln_gamma && tma_ok0(a.C, a.ldc) &&
                          (!a.residual || tma_ok0(a.residual, a.ldres)) && (!a.aux || tma_ok0(a.aux, a.ldaux)) &&
                          (!a.c_pre || tma_ok0(a.c_pre, a.ldpre)) && !(a.c_dtype == VG_F32 && (a.aux || a.c_pre || a.act != VG_ACT_NONE));   // == epi_tma below
   static int bn_env = -1;
@@ -806,6 +876,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   p.dbg = 0;
   if (const char* d = getenv("VG_TC_DBG")) p.dbg = atoi(d);
   p.rowsum = a.a_rowsum;
+  p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_mean = a.ln_mean; p.ln_rstd = a.ln_rstd; p.ln_eps = a.ln_eps;
   // staged (TMA) epilogue whenever the output / side tensors are TMA-addressable and no row remap is requested
   const bool f32 = p.c_is_f32 != 0;
   const int esz = f32 ? 4 : 2;
@@ -818,6 +889,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
     const int bc = f32 ? 32 : 64;                      // 128-byte wide boxes, 32 rows
     if ((rc = make_map(&mc, a.C, a.M, a.N, a.ldc, bc, 32, f32))) return rc;
     if (a.c_pre && (rc = make_map(&mp, a.c_pre, a.M, a.N, a.ldpre, bc, 32, f32))) return rc;
+    if (a.ln_out && (rc = make_map(&mp, a.ln_out, a.M, a.N, a.ld_ln, bc, 32, f32))) return rc;
     if (a.residual && (rc = make_map(&mr, a.residual, a.M, a.N, a.ldres, bc, 32, f32))) return rc;
     if (a.aux && (rc = make_map(&mx, a.aux, a.M, a.N, a.ldaux, bc, 32, f32))) return rc;
   }
@@ -826,13 +898,14 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const int mode = !p.epi_tma ? 0 : (f32 ? 2 : 1);
   VG_REQUIRE(!a.a_rowsum || mode == 2, VG_ERR_UNSUPPORTED, "gemm_tc: a_rowsum needs the staged fp32 epilogue");
   VG_REQUIRE(!(bn == 256 && mode == 0), VG_ERR_LAUNCH, "gemm_tc: internal: 256-wide tile without a staged epilogue");
+  VG_REQUIRE(!a.ln_gamma || (mode == 1 && bn == 128), VG_ERR_UNSUPPORTED, "gemm_tc: fused LayerNorm needs the staged bf16 epilogue");
   const bool wide_k = bn == 256;
   // weight-stationary variant: staged epilogue, A K-major, no split-K, whole B (+ >= 2 A stages) fits next to the staging tiles
   const int nb_tiles = p.n_tiles * p.kb_total;
   const int ws_budget = 227 * 1024 - (EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512);
   int na = (ws_budget - nb_tiles * B_BYTES) / A_BYTES;
   na = min(na, min(8, 2 * p.kb_total));
-  const bool ws_ok = !wide_k && mode != 0 && !a.trans_a && !a.accumulate && p.n_tiles <= 3 && na >= 2 && p.m_tiles >= 2 && (p.dbg & 8);   // opt-in (VG_TC_DBG=8): measured no faster than the generic kernel at C2 shapes
+  const bool ws_ok = !wide_k && !a.ln_gamma && mode != 0 && !a.trans_a && !a.accumulate && p.n_tiles <= 3 && na >= 2 && p.m_tiles >= 2 && (p.dbg & 8);   // opt-in (VG_TC_DBG=8): measured no faster than the generic kernel at C2 shapes
   if (ws_ok) {
     p.na_stages = na;
     const int ws_smem = nb_tiles * B_BYTES + na * A_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512;
@@ -854,7 +927,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   }
 #define VG_TC_LAUNCH(MODE_, ACT_, BN_)                                                                                         \
   do {                                                                                                                         \
-    constexpr int smem_ = (BN_ == 256 ? 3 * (A_BYTES + 256 * BK * 2) : NSTAGES * STAGE_BYTES) + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + 1024 + 512; \
+    constexpr int smem_ = (BN_ == 256 ? 3 * (A_BYTES + 256 * BK * 2) : NSTAGES * STAGE_BYTES) + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512; \
     static bool attr_set = false;                                                                                              \
     if (!attr_set) {                                                                                                           \
       cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_); \
@@ -863,6 +936,18 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
     }                                                                                                                          \
     launch_pdl(gemm_tc_kernel<MODE_, ACT_, BN_>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);             \
   } while (0)
+  if (a.ln_gamma) {
+    VG_REQUIRE(a.act == VG_ACT_NONE, VG_ERR_UNSUPPORTED, "gemm_tc: fused LayerNorm is built for the activation-free epilogue");
+    constexpr int smem_ = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, VG_ACT_NONE, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_);
+      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    launch_pdl(gemm_tc_kernel<1, VG_ACT_NONE, 128, true>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);
+    return check_launch("gemm_tc");
+  }
   if (mode == 0) VG_TC_LAUNCH(0, 0, 128);
   else if (wide_k) {
     if (mode == 2) VG_TC_LAUNCH(2, 0, 256);

@@ -453,12 +453,48 @@ class EmbedV2Fn(Function):
 # --------------------------------------------------------------------------------------------------
 # attention sub-layer helpers (shared by SelfAttentionFn and EncoderFn)
 # --------------------------------------------------------------------------------------------------
-def _attn_fwd(xn, B, S, H, wqkv, bqkv, wo, bo, residual, scale, mode=L.ATTN_DOT):
+# LayerNorm of a GEMM's output rows inside its epilogue (vg_gemm ln_*; N == 128 on the tcgen05 path).  OFF by default: measured on
+# B200 at C2 the fused out-proj/fc2 + LayerNorm launch costs what the two launches cost (step 4.67 ms fused vs 4.57 ms unfused):
+# with 1.76 tiles per CTA the epilogue is on the critical path of every tile, and the two-pass statistics need two 64-thread
+# barriers between the warps that share a row.  set_fused_layernorm_epilogue(True) enables it (parity-tested either way).
+_FUSE_LN_IN_GEMM = False
+_gemm_ln_unsupported: set = set()
+
+
+def fused_layernorm_epilogue() -> bool:
+    return _FUSE_LN_IN_GEMM
+
+
+def set_fused_layernorm_epilogue(enabled: bool):
+    global _FUSE_LN_IN_GEMM
+    _FUSE_LN_IN_GEMM = enabled
+
+
+def gemm_ln(a, w, bias, residual, ln):
+    """C = a w^T + bias + residual followed by LayerNorm(C): -> (C, (xn, mean, rstd)).  One launch when the GEMM epilogue can
+    normalise the row (bf16, N == 128, tcgen05 path); otherwise the GEMM and the LayerNorm kernel."""
+    gamma, beta, eps = ln
+    key = (a.dtype, w.shape[0], w.shape[1])
+    if _FUSE_LN_IN_GEMM and a.dtype == torch.bfloat16 and w.shape[0] == 128 and key not in _gemm_ln_unsupported:
+        try:
+            y, xn, mean, rstd = ops.gemm(a, w, bias=bias, residual=residual, ln=(gamma, beta, eps))
+            return y, (xn, mean, rstd)
+        except L.VitganError:          # rejected before any launch
+            _gemm_ln_unsupported.add(key)
+    y = ops.gemm(a, w, bias=bias, residual=residual)
+    return y, ops.layernorm_fwd(y, gamma, beta, eps)
+
+
+def _attn_fwd(xn, B, S, H, wqkv, bqkv, wo, bo, residual, scale, mode=L.ATTN_DOT, ln=None):
+    """ln = (gamma, beta, eps) of the LayerNorm that follows the sub-layer: then a fifth result (xn, mean, rstd) is returned."""
     E3 = wqkv.shape[0]
     hd = E3 // 3
     d = hd // H
     qkv = ops.gemm(xn, wqkv, bias=bqkv)                                            # fused Q|K|V projection
     o, lse = ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale, mode)
+    if ln is not None:
+        y, stats = gemm_ln(o, wo, bo, residual, ln)                                # out-proj (+bias, +skip) + next LayerNorm
+        return y, qkv, o, lse, stats
     y = ops.gemm(o, wo, bias=bo, residual=residual)                                # out-proj (+bias, +skip)
     return y, qkv, o, lse
 
@@ -523,7 +559,10 @@ class SelfAttentionFn(Function):
 # --------------------------------------------------------------------------------------------------
 class EncoderFn(Function):
     @staticmethod
-    def forward(ctx, x, n_heads, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2):
+    def forward(ctx, x, ln1_xn, ln1_mean, ln1_rstd, next_g, next_b, n_heads, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2):
+        """ln1_*: LayerNorm-1 of x already produced by the previous block's fc2 epilogue (or None).  next_g / next_b: affine
+        parameters of the NEXT block's LayerNorm-1: then its (xn, mean, rstd) are returned as three extra, non-differentiable
+        outputs (they are functions of y; the gradient reaches y through the next block's own backward)."""
         adt = act_dtype()
         B, S, E = x.shape
         x2 = x.reshape(B * S, E)
@@ -531,22 +570,31 @@ class EncoderFn(Function):
             x2 = ops.cast(x2, adt)
         x2 = x2.contiguous()
         scale = 1.0 / math.sqrt(E // n_heads)
-        xn1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w.detach(), n1b.detach())
-        x1, qkv, o, lse = _attn_fwd(xn1, B, S, n_heads, packed([wq, wk, wv], adt), packed_vec([bq, bk, bv]),
-                                    packed([wo], adt), bo.detach(), x2, scale)
-        xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w.detach(), n2b.detach())
+        eps = 1e-5
+        if ln1_xn is not None:
+            xn1, mean1, rstd1 = ln1_xn, ln1_mean, ln1_rstd
+        else:
+            xn1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w.detach(), n1b.detach())
+        x1, qkv, o, lse, (xn2, mean2, rstd2) = _attn_fwd(xn1, B, S, n_heads, packed([wq, wk, wv], adt), packed_vec([bq, bk, bv]),
+                                                         packed([wo], adt), bo.detach(), x2, scale, ln=(n2w.detach(), n2b.detach(), eps))
         g, u = ops.gemm(xn2, packed([w1], adt), bias=b1.detach(), act=L.ACT_GELU, want_pre=True)   # fc1 + GELU
-        y = ops.gemm(g, packed([w2], adt), bias=b2.detach(), residual=x1)                           # fc2 + skip
+        nxt = (None, None, None)
+        if next_g is not None:
+            y, nxt = gemm_ln(g, packed([w2], adt), b2.detach(), x1, (next_g.detach(), next_b.detach(), eps))   # fc2 + skip + next LN1
+        else:
+            y = ops.gemm(g, packed([w2], adt), bias=b2.detach(), residual=x1)                       # fc2 + skip
         ctx.save_for_backward(x2, mean1, rstd1, xn1, qkv, o, lse, x1, mean2, rstd2, xn2, u, g,
                               n1w, wq, wk, wv, wo, n2w, w1, w2)
         ctx.prm = dict(wq=wq, wk=wk, wv=wv, wo=wo, bq=bq, bk=bk, bv=bv, bo=bo, n1b=n1b, n2b=n2b, b1=b1, b2=b2)
         ctx.meta = (B, S, E, n_heads, scale, x.dtype)
         ctx.skip_pg = _SKIP_PARAM_GRADS
-        return y.reshape(B, S, E)
+        if nxt[0] is not None:
+            ctx.mark_non_differentiable(*nxt)
+        return (y.reshape(B, S, E),) + tuple(nxt)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_unused):
         (x2, mean1, rstd1, xn1, qkv, o, lse, x1, mean2, rstd2, xn2, u, g, n1w, wq, wk, wv, wo, n2w, w1, w2) = ctx.saved_tensors
         B, S, E, H, scale, xdtype = ctx.meta
         adt = x2.dtype
@@ -574,7 +622,7 @@ class EncoderFn(Function):
         dx = dx.reshape(B, S, E)
         dwq, dwk, dwv = _split_rows(ga["wqkv"], (E, E, E))
         dbq, dbk, dbv = _split_rows(ga["bqkv"], (E, E, E))
-        return (dx, None, dn1w, dn1b, dwq, dbq, dwk, dbk, dwv, dbv, ga["wo"], ga["bo"], dn2w, dn2b, dw1, db1, dw2, db2)
+        return (dx, None, None, None, None, None, None, dn1w, dn1b, dwq, dbq, dwk, dbk, dwv, dbv, ga["wo"], ga["bo"], dn2w, dn2b, dw1, db1, dw2, db2)
 
 
 # --------------------------------------------------------------------------------------------------

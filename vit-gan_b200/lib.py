@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("aux", vp), ("ldaux", i64), ("residual", vp), ("ldres", i64), ("c_pre", vp), ("ldpre", i64),
         ("c_row_group", i32), ("res_row_mod", i32), ("res_row_off", i32), ("accumulate", i32),
         ("a_rowsum", vp),
+        ("ln_gamma", vp), ("ln_beta", vp), ("ln_out", vp), ("ld_ln", i64), ("ln_mean", vp), ("ln_rstd", vp), ("ln_eps", f32),
     ]
 
 

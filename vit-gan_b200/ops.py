@@ -71,13 +71,15 @@ def _rowmajor2d(t: torch.Tensor, name: str):
 
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, act=L.ACT_NONE, act_param=0.0, aux=None, residual=None,
          want_pre=False, out=None, out_dtype=None, accumulate=False, c_row_group=0, res_row_mod=0, res_row_off=0,
-         path=L.GEMM_AUTO, rowsum_out=None):
+         path=L.GEMM_AUTO, rowsum_out=None, ln=None):
     """C[M,N] = opA(a) @ opB(b) with the fused epilogue of vg_gemm (see include/vitgan_b200.h).
 
     a: [M,K] (or [K,M] if trans_a); b: [N,K] if trans_b (an nn.Linear weight) else [K,N].
     Returns C, or (C, pre_activation) when want_pre.
     rowsum_out: optional fp32 [M] vector, accumulated with the row sums of opA(a) (the bias gradient when this is a
     weight-gradient GEMM); tcgen05 accumulate mode only -- raises VitganError (nothing launched) when unsupported.
+    ln: optional (gamma, beta, eps): also return LayerNorm(C) and its statistics -> (C, ln_out, mean, rstd); tcgen05 path with
+    N == 128 only -- raises VitganError (nothing launched) when unsupported.
     """
     _req(a, "a"); _req(b, "b")
     lda, ldb = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
@@ -116,8 +118,19 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, act=L.ACT_NONE, act_pa
         if rowsum_out.dtype != torch.float32 or rowsum_out.numel() != M or not rowsum_out.is_contiguous():
             raise ValueError("vitgan_b200.gemm: rowsum_out must be a contiguous fp32 vector of length M")
         g.a_rowsum = rowsum_out.data_ptr()
+    ln_res = None
+    if ln is not None:
+        gamma, beta, eps = ln
+        ln_out = torch.empty((M, N), dtype=out.dtype, device=a.device)
+        mean = torch.empty(M, dtype=torch.float32, device=a.device)
+        rstd = torch.empty_like(mean)
+        g.ln_gamma, g.ln_beta, g.ln_out, g.ld_ln = gamma.data_ptr(), beta.data_ptr(), ln_out.data_ptr(), N
+        g.ln_mean, g.ln_rstd, g.ln_eps = mean.data_ptr(), rstd.data_ptr(), float(eps)
+        ln_res = (ln_out, mean, rstd)
     check(lib.vg_gemm(C.byref(g), stream()), "vg_gemm")
     _count()
+    if ln_res is not None:
+        return (out,) + ln_res
     return (out, pre) if want_pre else out
 
 

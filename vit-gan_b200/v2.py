@@ -54,13 +54,28 @@ def self_attention_forward(self, x):
                                     self.out_projection.bias)
 
 
+def encoder_forward_chained(self, x, ln1=None, next_norm=None):
+    """Encoder.forward (modules.py:178-183) as one autograd Function.  ln1 = (xn, mean, rstd) of this block's first LayerNorm if
+    the previous block's fc2 epilogue already produced it; next_norm = the next block's norm1 module, whose LayerNorm is then
+    computed by this block's fc2 epilogue.  -> (y, ln1-of-next-block | None)."""
+    a = self.attention
+    c = ln1 if ln1 is not None else (None, None, None)
+    ng, nb = (next_norm.weight, next_norm.bias) if next_norm is not None else (None, None)
+    out = Fn.EncoderFn.apply(x, c[0], c[1], c[2], ng, nb, a.n_attention_heads, self.norm1.weight, self.norm1.bias, a.queries.weight,
+                             a.queries.bias, a.keys.weight, a.keys.bias, a.values.weight, a.values.bias, a.out_projection.weight,
+                             a.out_projection.bias, self.norm2.weight, self.norm2.bias, self.fc1.weight, self.fc1.bias,
+                             self.fc2.weight, self.fc2.bias)
+    return out[0], (out[1:] if out[1] is not None else None)
+
+
 def encoder_forward(self, x):
     """Encoder.forward (modules.py:178-183)."""
-    a = self.attention
-    return Fn.EncoderFn.apply(x, a.n_attention_heads, self.norm1.weight, self.norm1.bias, a.queries.weight, a.queries.bias,
-                              a.keys.weight, a.keys.bias, a.values.weight, a.values.bias, a.out_projection.weight,
-                              a.out_projection.bias, self.norm2.weight, self.norm2.bias, self.fc1.weight, self.fc1.bias,
-                              self.fc2.weight, self.fc2.bias)
+    return encoder_forward_chained(self, x)[0]
+
+
+def _chainable(block, nxt):
+    return (type(nxt).__name__ == type(block).__name__ and getattr(nxt.norm1, "eps", None) == 1e-5 and getattr(block.norm2, "eps", None) == 1e-5
+            and tuple(nxt.norm1.normalized_shape) == tuple(block.norm1.normalized_shape))
 
 
 def _head(fc1, fc2, c):
@@ -77,8 +92,10 @@ def vit_forward(self, x):
     """VisionTransformer.forward (modules.py:232-238).  The final LayerNorm is applied to the CLS rows only:
     the reference normalises all S rows and then discards all but row 0 (modules.py:195,236)."""
     x = embed_forward(self.embedding, x)
-    for block in self.encoder:
-        x = encoder_forward(block, x)
+    blocks, ln1 = list(self.encoder), None
+    for i, block in enumerate(blocks):       # with the fused-LayerNorm epilogue enabled, block i's fc2 GEMM also normalises for block i+1
+        nxt = blocks[i + 1].norm1 if Fn.fused_layernorm_epilogue() and i + 1 < len(blocks) and _chainable(block, blocks[i + 1]) else None
+        x, ln1 = encoder_forward_chained(block, x, ln1, nxt)
     c = Fn.ClsRowFn.apply(x)
     c = Fn.LayerNormFn.apply(c, self.norm.weight, self.norm.bias, self.norm.eps)
     return _head(self.classifier.fc1, self.classifier.fc2, c)
