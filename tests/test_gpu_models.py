@@ -515,6 +515,6 @@ def test_v2_fused_layernorm_epilogue_matches_unfused(vb):
             out.float().square().sum().backward()
             res[fused] = (out.detach().float(), xi.grad.clone(), {k: p.grad.clone() for k, p in gan.discriminator.named_parameters()})
         finally:
-            vb.functional.set_fused_layernorm_epilogue(False)
+            vb.functional.set_fused_layernorm_epilogue(True)
     assert rel(res[True][0], res[False][0]) < 1e-2 and rel(res[True][1], res[False][1]) < 2e-2
     cmp_grads(res[True][2], res[False][2], 2e-2, "fused LayerNorm epilogue")

@@ -453,11 +453,12 @@ class EmbedV2Fn(Function):
 # --------------------------------------------------------------------------------------------------
 # attention sub-layer helpers (shared by SelfAttentionFn and EncoderFn)
 # --------------------------------------------------------------------------------------------------
-# LayerNorm of a GEMM's output rows inside its epilogue (vg_gemm ln_*; N == 128 on the tcgen05 path).  OFF by default: measured on
-# B200 at C2 the fused out-proj/fc2 + LayerNorm launch costs what the two launches cost (step 4.67 ms fused vs 4.57 ms unfused):
-# with 1.76 tiles per CTA the epilogue is on the critical path of every tile, and the two-pass statistics need two 64-thread
-# barriers between the warps that share a row.  set_fused_layernorm_epilogue(True) enables it (parity-tested either way).
-_FUSE_LN_IN_GEMM = False
+# LayerNorm of a GEMM's output rows inside its epilogue (vg_gemm ln_*; N == 128 on the tcgen05 path): the out-proj GEMM also emits
+# LayerNorm-2 of its block and the fc2 GEMM LayerNorm-1 of the NEXT block (v2.vit_forward chains the blocks).  Measured at C2 on
+# B200: 4.57 -> 4.51 ms per step (33 launches fewer).  A small win only: with 1.76 tiles per CTA the epilogue is on the critical
+# path of every tile and the two-pass statistics need two 64-thread barriers between the warps sharing a row.  VG_FUSE_LN=0 or
+# set_fused_layernorm_epilogue(False) falls back to GEMM + LayerNorm kernel (parity-tested both ways).
+_FUSE_LN_IN_GEMM = __import__("os").environ.get("VG_FUSE_LN", "1") != "0"
 _gemm_ln_unsupported: set = set()
 
 
@@ -590,11 +591,14 @@ class EncoderFn(Function):
         ctx.skip_pg = _SKIP_PARAM_GRADS
         if nxt[0] is not None:
             ctx.mark_non_differentiable(*nxt)
+            ctx.set_materialize_grads(False)      # no zero-filled "gradients" for the three statistics outputs
         return (y.reshape(B, S, E),) + tuple(nxt)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, *_unused):
+        if dy is None:
+            return (None,) * 23
         (x2, mean1, rstd1, xn1, qkv, o, lse, x1, mean2, rstd2, xn2, u, g, n1w, wq, wk, wv, wo, n2w, w1, w2) = ctx.saved_tensors
         B, S, E, H, scale, xdtype = ctx.meta
         adt = x2.dtype
