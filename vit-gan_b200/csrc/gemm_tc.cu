@@ -81,6 +81,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -364,13 +365,18 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
                                             const CUtensorMap* tmap_res, const CUtensorMap* tmap_aux, uint32_t taddr,
                                             uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
                                             uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane,
-                                            uint32_t rs_taddr = 0u, bool release = true, int ew = 0, LnScratch ln = LnScratch{nullptr, nullptr}) {
+                                            uint32_t rs_taddr = 0u, bool release = true, int ew = 0, LnScratch ln = LnScratch{nullptr, nullptr},
+                                            bool alt = false) {
+  // alt (bf16 epilogues without residual / aux / c_pre / LayerNorm only): consecutive calls alternate between the warp's two
+  // 4 KB staging tiles, so this tile is staged while the previous tile's bulk store is still reading the other one
   // release == false: more 64-column groups of the same accumulator follow (256-wide tiles); the last group frees TMEM
   // rs_taddr != 0: this warp also drains one row-sum column (a_rowsum) of its 32 rows and reduce-adds it into p.rowsum
   constexpr bool f32 = MODE == 2;
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
   // staging tiles are free once the previous tile's bulk stores have READ them
-  if (lane == 0) tma_wait_read();
+  const bool dbl = MODE == 1 && !LN && !has_res && !has_aux && !has_pre;
+  if (dbl && alt) { const uint32_t t = bufC; bufC = bufX; bufX = t; }
+  if (lane == 0) { if (dbl) tma_wait_read1(); else tma_wait_read(); }
   __syncwarp();
   if (p.bias) {                               // stage this warp's 64 bias values (previous tile's readers are past them)
     const int c0 = n0 + lane, c1 = n0 + 32 + lane;
@@ -577,6 +583,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
       float* ln_f = reinterpret_cast<float*>(smem_dyn + (ln_base - smem_u32(smem_dyn)));
       const LnScratch ln = LN ? LnScratch{ln_f + ew * 128, ln_f + EPI_WARPS * 128} : LnScratch{nullptr, nullptr};
+      int n_staged = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
         const int m0 = m_blk * BM + quad * 32;
@@ -586,7 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int col = half * (BN / 2) + g * 64;
           staged_tile<MODE, ACT, LN>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
                                      tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
-                                     g == BN / 128 - 1, ew, ln);
+                                     g == BN / 128 - 1, ew, ln, (n_staged++ & 1) != 0);
         }
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
