@@ -100,23 +100,62 @@ def step_flops_per_image(spec, skip_unused):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML (nvidia_ml_py) polled every ~2 ms -- the
+    timed region of the default run is ~140 ms, too short for `nvidia-smi -lms`, whose first sample arrives after ~100 ms;
+    nvidia-smi is the fallback when NVML cannot be loaded."""
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        self.sm, self.mx, self.reasons = [], None, set()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.h = pynvml, h
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml, self.h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(reasons_fn(h))
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
+                    "reasons": sorted(self.reasons), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -133,7 +172,7 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
@@ -286,6 +325,35 @@ def kernel_rooflines(vb, spec, pk):
         _, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)
         return lambda: vb.ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dr)
     entry("layernorm bwd (+residual grad)", mk_lnb, 2 * 4 * M * E, 12.0 * M * E, 2.0 * 4 * M * E)
+
+    # the same GEMM kernel at the compute-bound geometry of BASELINE configs[3] (E=768, 256 images x 257 tokens per GPU): the
+    # regime in which the north star's ">= 60 % of bf16 tensor peak on the MLP/attention GEMMs" is meaningful (256-wide tiles)
+    M4, E4 = 256 * 257, 768
+    w4 = mk(3 * E4, E4)
+    b4 = torch.randn(3 * E4, device=dev)
+
+    def entry_big(name, make_call, flops, bytes_):
+        t = time_graph(make_call, 2, iters=6) * 1e-3
+        tf, gb = flops / t / 1e12, bytes_ / t / 1e9
+        out.append({"kernel": name, "bound": "tensor", "us": t * 1e6, "tflops": tf, "gbs": gb, "frac_tensor": tf / pk["tf_burst"],
+                    "frac_hbm": gb / pk["hbm"], "alg_flops": flops, "alg_bytes": bytes_, "buffer_sets": 2})
+
+    def mk4_f(i):
+        x, o = mk(M4, E4), torch.empty(M4, 3 * E4, device=dev, dtype=bf)
+        return lambda: vb.ops.gemm(x, w4, bias=b4, out=o, path=L.GEMM_TCGEN05)
+
+    def mk4_d(i):
+        dy, o = mk(M4, 3 * E4), torch.empty(M4, E4, device=dev, dtype=bf)
+        return lambda: vb.ops.gemm(dy, w4, trans_b=False, out=o, path=L.GEMM_TCGEN05)
+
+    def mk4_w(i):
+        dy, x, o = mk(M4, 3 * E4), mk(M4, E4), torch.zeros(3 * E4, E4, device=dev)
+        return lambda: vb.ops.gemm(dy, x, trans_a=True, trans_b=False, accumulate=True, out=o, path=L.GEMM_TCGEN05)
+    f4 = 2.0 * M4 * 3 * E4 * E4
+    entry_big("gemm_tc C4 shape fwd qkv [65792,768]x[768,2304]+bias (256-wide tile)", mk4_f, f4, 2.0 * (M4 * E4 + 3 * E4 * E4 + M4 * 3 * E4))
+    entry_big("gemm_tc C4 shape dgrad qkv [65792,2304]x[2304,768] (256-wide tile)", mk4_d, f4, 2.0 * (M4 * 3 * E4 + 3 * E4 * E4 + M4 * E4))
+    entry_big("gemm_tc C4 shape wgrad qkv [2304,65792]x[65792,768] split-K (256-wide tile)", mk4_w, f4, 2.0 * (M4 * 3 * E4 + M4 * E4) + 4.0 * 3 * E4 * E4)
+    torch.cuda.empty_cache()
 
     dom = out[0]
     key = "frac_tensor" if dom["bound"] == "tensor" else "frac_hbm"

@@ -10,6 +10,7 @@ Double backward is not supported (the reference's active path never needs it, SU
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch.autograd import Function
@@ -458,7 +459,7 @@ class EmbedV2Fn(Function):
 # B200: 4.57 -> 4.51 ms per step (33 launches fewer).  A small win only: with 1.76 tiles per CTA the epilogue is on the critical
 # path of every tile and the two-pass statistics need two 64-thread barriers between the warps sharing a row.  VG_FUSE_LN=0 or
 # set_fused_layernorm_epilogue(False) falls back to GEMM + LayerNorm kernel (parity-tested both ways).
-_FUSE_LN_IN_GEMM = __import__("os").environ.get("VG_FUSE_LN", "1") != "0"
+_FUSE_LN_IN_GEMM = os.environ.get("VG_FUSE_LN", "1") != "0"
 _gemm_ln_unsupported: set = set()
 
 
