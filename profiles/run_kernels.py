@@ -27,5 +27,13 @@ for rep in range(2):      # first pass warms caches/lazy init; ncu is told to sk
     vb.ops.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], o, o, lse, B, H, S, d, d ** -0.5)
     y, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)
     vb.ops.layernorm_bwd(x, x, mean, rstd, gam, dres=x)
+# compute-bound geometry (BASELINE configs[3]: E=768, 256 images x 257 tokens): the 256-wide tcgen05 tile
+M4, E4 = 256 * 257, 768
+x4, w4, dy4 = mk(M4, E4), mk(3 * E4, E4), mk(M4, 3 * E4)
+b4 = torch.randn(3 * E4, device=dev)
+for rep in range(2):
+    vb.ops.gemm(x4, w4, bias=b4, path=L.GEMM_TCGEN05)                                          # fwd qkv, BN=256
+    vb.ops.gemm(dy4, w4, trans_b=False, path=L.GEMM_TCGEN05)                                   # dgrad qkv, BN=256
+    vb.ops.gemm(dy4, x4, trans_a=True, trans_b=False, accumulate=True, path=L.GEMM_TCGEN05)    # wgrad qkv, BN=256 split-K
 torch.cuda.synchronize()
 print("ok")
