@@ -95,6 +95,10 @@ const char* vg_last_error(void);
 int vg_device_is_sm100(void);
 
 int vg_gemm(const vg_gemm_args* args, void* stream);
+/* Development aid: while `buffer` (device memory, >= 16 * gridDim u64, caller-zeroed) is set, every tcgen05 GEMM CTA records
+ * %globaltimer at its pipeline milestones (entry, prologue done, dependency wait done, first tile's TMA issued / landed / MMA
+ * committed / stored, stores drained, exit) into buffer[cta * 16 + k].  NULL switches it off.  Process-global, not thread-safe. */
+int vg_gemm_set_trace(void* buffer);
 
 /* dst[i] = (dst_dtype) (scale ? *scale : 1) * src[i]; used to make bf16 copies of fp32 parameters and to
  * apply the spectral rescale W <- sigma0/sigma * W (src/v1/attention.py:60-64) while packing. */

@@ -78,3 +78,8 @@ extern "C" int vg_gemm(const vg_gemm_args* args, void* stream) {
   VG_REQUIRE(ok || (!a.a_rowsum && !a.ln_gamma), VG_ERR_UNSUPPORTED, "vg_gemm: a_rowsum / fused LayerNorm unsupported here: %s", why);
   return ok ? gemm_tc_launch(a, st) : gemm_simt_launch(a, st);
 }
+
+extern "C" int vg_gemm_set_trace(void* buffer) {
+  gemm_tc_set_trace(static_cast<unsigned long long*>(buffer));
+  return VG_OK;
+}

@@ -224,5 +224,6 @@ __device__ __forceinline__ void cta_replica_reduce(float* __restrict__ ws, int R
 int gemm_simt_launch(const vg_gemm_args& a, cudaStream_t st);
 int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st);
 bool gemm_tc_supported(const vg_gemm_args& a, const char** why);
+void gemm_tc_set_trace(unsigned long long* p);
 
 }  // namespace vg

@@ -173,8 +173,17 @@ struct Params {
   int na_stages;                       // weight-stationary kernel: depth of the A k-block ring
   float* rowsum;                       // a_rowsum: rowsum[m] += sum_k opA(A)[m,k] (bias gradient of a wgrad GEMM) or NULL
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd; float ln_eps;   // fused LayerNorm of the output rows (N == 128) or NULL
+  unsigned long long* trace;           // per-CTA timeline buffer or NULL
 };
 // per-warp scratch of the fused LayerNorm epilogue
+// optional per-CTA timeline (vg_gemm_set_trace): trace[blockIdx.x * 16 + k] = %globaltimer at milestone k (see TR_* below)
+enum { TR_ENTRY = 0, TR_PROLOGUE, TR_PDL, TR_TMA0, TR_FULL0, TR_MMA0, TR_TFULL0, TR_STORE0, TR_DRAINED, TR_EXIT, TR_TILES };
+// Compiled in only with -DVG_TC_TRACE (make TRACE=1): even a never-taken branch per milestone cost 0.2-0.3 us per skinny GEMM.
+__device__ __forceinline__ void trace_mark(unsigned long long* tr, int k) {
+#ifdef VG_TC_TRACE
+  if (tr != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); tr[blockIdx.x * 16 + k] = t; }
+#endif
+}
 struct LnScratch { float* gb; float* slots; };   // gb: gamma[64] | beta[64] of this warp's columns; slots: [2][EPI_WARPS][32] row partials
 
 template <typename TC>
@@ -470,6 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_mark(p.trace, TR_ENTRY);
   const bool do_rs = MODE == 2 && BNT == 128 && p.rowsum != nullptr;
   const uint32_t tmem_cols = (do_rs || BNT == 256) ? 512u : (uint32_t)TMEM_COLS;
 
@@ -481,6 +491,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    if (MODE != 0) {     // the epilogue's maps too: a cold descriptor fetch costs ~0.5-0.9 us on the first tile (profiles/trace_gemm.py)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+      if (p.c_pre != nullptr || LN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_pre) : "memory");
+      if (p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_res) : "memory");
+      if (p.aux != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_aux) : "memory");
+    }
     for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(warp_bar(w), 1);
@@ -494,8 +510,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) trace_mark(p.trace, TR_PROLOGUE);
   pdl_trigger();   // dependents may start their prologue; they wait for our completion before touching memory
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) trace_mark(p.trace, TR_PDL);
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
   // smem tile geometry per operand
@@ -531,6 +549,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
         }
+        if (w == (int)blockIdx.x) trace_mark(p.trace, TR_TMA0);
       }
     }
   } else if (warp == 1) {
@@ -555,6 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);                 // TMA bytes have landed
           tc_fence_after();
+          if (w == (int)blockIdx.x && kb == kb0) trace_mark(p.trace, TR_FULL0);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
@@ -567,6 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
+        if (w == (int)blockIdx.x) trace_mark(p.trace, TR_MMA0);
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -595,9 +616,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                      tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
                                      g == BN / 128 - 1, ew, ln, (n_staged++ & 1) != 0);
         }
+        if (ew == 0 && lane == 0 && w == (int)blockIdx.x) trace_mark(p.trace, TR_STORE0);
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
       if (lane == 0) tma_wait_read();   // smem may not be released while bulk stores still read it; visibility comes with grid completion
+#ifdef VG_TC_TRACE
+      if (ew == 0 && lane == 0) { trace_mark(p.trace, TR_DRAINED); if (p.trace) p.trace[blockIdx.x * 16 + TR_TILES] = (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x; }
+#endif
     } else {
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
@@ -625,6 +650,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(p.trace, TR_EXIT);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -798,6 +824,9 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
 
 }  // namespace
 
+static unsigned long long* g_trace = nullptr;
+void gemm_tc_set_trace(unsigned long long* p) { g_trace = p; }
+
 bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
   static int sm100 = -1;
   if (sm100 < 0) sm100 = vg_device_is_sm100();
@@ -883,6 +912,7 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   p.dbg = 0;
   if (const char* d = getenv("VG_TC_DBG")) p.dbg = atoi(d);
   p.rowsum = a.a_rowsum;
+  p.trace = g_trace;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_mean = a.ln_mean; p.ln_rstd = a.ln_rstd; p.ln_eps = a.ln_eps;
   // staged (TMA) epilogue whenever the output / side tensors are TMA-addressable and no row remap is requested
   const bool f32 = p.c_is_f32 != 0;

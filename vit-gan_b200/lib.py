@@ -39,6 +39,7 @@ SIGNATURES = {
     "vg_last_error": [],
     "vg_device_is_sm100": [],
     "vg_gemm": [C.POINTER(GemmArgs), vp],
+    "vg_gemm_set_trace": [vp],
     "vg_cast_scale": [vp, i32, vp, i32, i64, vp, vp, vp],
     "vg_colsum": [vp, i32, i64, i32, i64, vp, vp, i32, vp, vp],
     "vg_layernorm_fwd": [i32, i64, i32, vp, vp, vp, vp, vp, vp, f32, vp],
