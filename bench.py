@@ -502,6 +502,47 @@ def run_ours(args):
             total_ms += s.elapsed_time(e)
         return total_ms, last
 
+    def timed_e2e(n_steps):
+        """End to end through the public step API, as an input pipeline runs it: every step's inputs are uploaded from pinned host
+        memory (copy stream, double-buffered device staging: the upload of step i+1 overlaps the compute of step i) and every
+        step's losses are read back to pinned host memory (asynchronous copy, checked after the region).  One CUDA-event pair
+        around the whole region, the first upload included; ms/step = elapsed / n_steps."""
+        main = torch.cuda.current_stream()
+        copy_s = torch.cuda.Stream()
+        stage = [tuple(torch.empty_like(t) for t in devb[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        res_host = torch.zeros(n_steps, 8, dtype=torch.float32).pin_memory()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record(main)
+        copy_s.wait_event(s)
+
+        def upload(i):
+            k = i % 2
+            with torch.cuda.stream(copy_s):
+                if i >= 2:
+                    copy_s.wait_event(freed[k])                    # step i-2 has consumed this staging pair
+                for dst, src in zip(stage[k], host[i % n_data]):
+                    dst.copy_(src, non_blocking=True)
+                ready[k].record(copy_s)
+        upload(0)
+        last, nres = None, 0
+        for i in range(n_steps):
+            if i + 1 < n_steps:
+                upload(i + 1)
+            main.wait_event(ready[i % 2])
+            last = step_fn(*stage[i % 2])
+            freed[i % 2].record(main)
+            vals = torch.stack([t.float().reshape(()) for t in last])
+            nres = vals.numel()
+            res_host[i, :nres].copy_(vals, non_blocking=True)      # D2H read of the step's result
+        e.record(main)
+        e.synchronize()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(res_host[:, :nres]).all()), "non-finite result in the end-to-end region"
+        return s.elapsed_time(e), last
+
     # ---- warm-up, then the device-resident timed region
     timed(max(args.warmup, 3), False)
     barrier()
@@ -512,9 +553,9 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     # ---- end to end: pinned host buffers in, losses out, every step
-    timed(2, True)
+    timed_e2e(2)
     barrier()
-    ms_e2e, last_e2e = timed(args.steps, True)
+    ms_e2e, last_e2e = timed_e2e(args.steps)
     barrier()
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -546,6 +587,7 @@ def run_ours(args):
                        "d_update_passes": "D(real) and D(fake) as one concatenated pass (same gradient sum)" if (merge_d and spec["kind"] != "v2_sample" and n_micro == 1) else "separate",
                        "l2": "192 MiB buffer written between timed steps (L2 flush); step working set is >1 GB anyway"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(last_e2e),
+                    "how": "public step API fed from pinned host buffers: per step one H2D upload of its inputs (copy stream, double-buffered staging, overlapping the previous step) and one async D2H read of its losses; one event pair around all steps (no L2 flush: each step streams >1 GB through the 126 MB L2 and its inputs arrive from the host)",
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "wall_s_timed_region": t_wall, "losses_last_step": losses, "losses_finite": finite,
