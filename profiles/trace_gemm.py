@@ -8,20 +8,28 @@ import vitgan_b200 as vb
 L, bf = vb.lib, torch.bfloat16
 names = ["entry", "prologue", "pdl_wait", "tma0_issued", "full0", "mma0_commit", "tfull0", "store0", "drained", "exit"]
 
-def run(M, N, K=128, label=""):
+def run(M, N, K=128, label="", kind="plain"):
     x, w, b = torch.randn(M, K, device="cuda").to(bf), torch.randn(N, K, device="cuda").to(bf), torch.randn(N, device="cuda")
     o = torch.empty(M, N, device="cuda", dtype=bf)
+    aux = torch.randn(M, N, device="cuda").to(bf)
+    wt = torch.randn(K, N, device="cuda").to(bf)
+    if kind == "fc1":
+        call = lambda: vb.ops.gemm(x, w, bias=b, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)
+    elif kind == "dgrad_gelu":
+        call = lambda: vb.ops.gemm(x, wt, trans_b=False, act=L.ACT_MUL_DGELU, aux=aux, out=o, path=L.GEMM_TCGEN05)
+    else:
+        call = lambda: vb.ops.gemm(x, w, bias=b, out=o, path=L.GEMM_TCGEN05)
     flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
     tr = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
     for rep in range(3):
         flush.zero_()
-        vb.ops.gemm(x, w, bias=b, out=o, path=L.GEMM_TCGEN05)           # predecessor (same kernel, PDL edge)
+        call()           # predecessor (same kernel, PDL edge)
         tr.zero_()
         torch.cuda.synchronize()
         vb.lib.lib.vg_gemm_set_trace(tr.data_ptr())
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        vb.ops.gemm(x, w, bias=b, out=o, path=L.GEMM_TCGEN05)
+        call()
         e.record()
         torch.cuda.synchronize()
         vb.lib.lib.vg_gemm_set_trace(None)
@@ -38,3 +46,5 @@ def run(M, N, K=128, label=""):
 run(33280, 384, label="qkv fwd")
 run(33280, 128, label="out-proj")
 run(66560, 384, label="qkv fwd (merged D pass)")
+run(33280, 256, label="fc1 + GELU (+pre)", kind="fc1")
+run(33280, 256, label="dgrad fc2 x GELU'(aux)", kind="dgrad_gelu")

@@ -118,9 +118,23 @@ __device__ __forceinline__ float erf_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
   return copysignf(fmaf(-p, e, 1.0f), x);
 }
-__device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
+// erf(x / sqrt2) as ONE MUFU: tanh(x * (A0 + A1 x^2 + A2 x^4)), minimax-fitted on [0, 6] (|erf error| <= 3.7e-5, i.e. |GELU error|
+// <= 5.5e-5 + the 2^-11 of tanh.approx -- below half a bf16 ulp of any |GELU| > 0.03; the far negative tail, |GELU| < 5e-3, keeps
+// an ABSOLUTE error < 8e-4).  7 instructions per GELU instead of 15 (A&S erf_fast) or ~25 (erff): the fc1 / dgrad-fc2 epilogues
+// were issue-bound at 2.7-3.7 us per 128x128 tile (profiles/r02_gemm_timeline.txt).
+__device__ __forceinline__ float erf_sqrt2_tanh(float x) {
+  const float x2 = x * x;
+  const float poly = fmaf(fmaf(-3.1580704e-4f, x2, 3.6798256e-2f), x2, 7.9771783e-1f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * poly));
+  return t;
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_sqrt2_tanh(x), hx);
+}
 __device__ __forceinline__ float dgelu_erf_fast(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
+  const float cdf = fmaf(0.5f, erf_sqrt2_tanh(x), 0.5f);
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));     // exp(-x^2/2)
   return fmaf(x * 0.39894228040143267794f, e, cdf);
