@@ -937,6 +937,7 @@ attn_bwd_hp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           }
         }
         // pass 3: dS = P * (dP - delta) * scale -> smem, over P
+        const float nds = -delta * g.scale;
 #pragma unroll
         for (int c = 0; c < NKG; ++c) {
           uint32_t dv[16];
@@ -944,9 +945,9 @@ attn_bwd_hp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tmem_ld_wait();
           uint32_t ds[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float s0 = bf16_lo(pk[8 * c + j]) * (__uint_as_float(dv[2 * j]) - delta) * g.scale;
-            const float s1 = bf16_hi(pk[8 * c + j]) * (__uint_as_float(dv[2 * j + 1]) - delta) * g.scale;
+          for (int j = 0; j < 8; ++j) {      // p * (dp - delta) * scale  as  p * fma(dp, scale, -delta * scale): 2 instead of 3 per element
+            const float s0 = bf16_lo(pk[8 * c + j]) * fmaf(__uint_as_float(dv[2 * j]), g.scale, nds);
+            const float s1 = bf16_hi(pk[8 * c + j]) * fmaf(__uint_as_float(dv[2 * j + 1]), g.scale, nds);
             ds[j] = pack_bf16(s0, s1);
           }
           if (row < NK) {

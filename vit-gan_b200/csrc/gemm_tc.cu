@@ -354,11 +354,14 @@ __device__ __forceinline__ void ln_epilogue(const Params& p, const uint32_t (&r0
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       float y[8];
+      const int c0 = cc * 32 + h * 8;       // gamma | beta of these 8 columns: four 16-byte broadcast loads
+      const float4 g0 = *reinterpret_cast<const float4*>(ln.gb + c0), g1 = *reinterpret_cast<const float4*>(ln.gb + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(ln.gb + 64 + c0), b1 = *reinterpret_cast<const float4*>(ln.gb + 64 + c0 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = cc * 32 + h * 8 + j;
         const float v = __uint_as_float(cc == 0 ? r0[h * 8 + j] : r1[h * 8 + j]);
-        y[j] = fmaf((v - mean) * rstd, ln.gb[c], ln.gb[64 + c]);
+        y[j] = fmaf((v - mean) * rstd, gg[j], bb[j]);
       }
       sts128(bufX + row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4), pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
     }
