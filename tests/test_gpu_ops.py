@@ -411,3 +411,22 @@ def test_gemm_fused_layernorm_epilogue(vb, M, K, res):
     assert rel(xn, F.layer_norm(c.float().cpu(), (128,), gam, bet, 1e-5)) < BF16_TOL
     with pytest.raises(L.VitganError, match="LayerNorm"):
         vb.ops.gemm(a.cuda(), torch.randn(256, K).bfloat16().cuda(), ln=(torch.ones(256).cuda(), torch.zeros(256).cuda(), 1e-5))
+
+
+def test_gemm_gelu_epilogue_large_arguments(vb):
+    """The bf16 GELU / GELU' epilogues evaluate erf through a fitted tanh polynomial whose argument is clamped to [-8, 8]:
+    pre-activations far outside that range (outliers) must still give GELU(x) = x / 0 and GELU'(x) = 1 / 0."""
+    L = vb.lib
+    bias = torch.cat([torch.linspace(-60, 60, 120), torch.tensor([-1e4, 1e4, -11.7, 11.7, -9.0, 9.0, -3.0, 3.0])])
+    a = torch.zeros(256, 64).bfloat16()
+    w = torch.zeros(128, 64).bfloat16()
+    out, pre = vb.ops.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)
+    ref = F.gelu(bias.bfloat16().float()).expand(256, 128)
+    assert torch.isfinite(out).all() and rel(out, ref) < BF16_TOL
+    assert (out.float().cpu()[0] - ref[0]).abs().max() <= 8e-3 * ref.abs().max()
+    dy = torch.ones(256, 128).bfloat16()
+    eye = torch.eye(128).bfloat16()                              # dX = dY I  x  GELU'(aux)
+    dgrad = vb.ops.gemm(dy.cuda(), eye.cuda(), trans_b=False, act=L.ACT_MUL_DGELU, aux=pre, path=L.GEMM_TCGEN05)
+    xr = bias.bfloat16().float().requires_grad_(True)
+    F.gelu(xr).sum().backward()
+    assert torch.isfinite(dgrad).all() and (dgrad.float().cpu()[0] - xr.grad).abs().max() < 1e-2

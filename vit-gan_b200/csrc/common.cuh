@@ -122,22 +122,30 @@ __device__ __forceinline__ float erf_fast(float x) {
 // <= 5.5e-5 + the 2^-11 of tanh.approx -- below half a bf16 ulp of any |GELU| > 0.03; the far negative tail, |GELU| < 5e-3, keeps
 // an ABSOLUTE error < 8e-4).  7 instructions per GELU instead of 15 (A&S erf_fast) or ~25 (erff): the fc1 / dgrad-fc2 epilogues
 // were issue-bound at 2.7-3.7 us per 128x128 tile (profiles/r02_gemm_timeline.txt).
+// The argument is clamped to [-8, 8] (erf(8/sqrt2) == 1 in fp32): the fitted polynomial turns over beyond |x| ~ 11.
 __device__ __forceinline__ float erf_sqrt2_tanh(float x) {
-  const float x2 = x * x;
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
   const float poly = fmaf(fmaf(-3.1580704e-4f, x2, 3.6798256e-2f), x2, 7.9771783e-1f);
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * poly));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * poly));
   return t;
 }
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, erf_sqrt2_tanh(x), hx);
 }
+// GELU'(x) = Phi(x) + x phi(x), as the exact derivative of the approximation above (no second MUFU for the exp):
+// 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x), u' = A0 + 3 A1 x^2 + 5 A2 x^4; |error| <= 1.4e-4 against the erf form.
 __device__ __forceinline__ float dgelu_erf_fast(float x) {
-  const float cdf = fmaf(0.5f, erf_sqrt2_tanh(x), 0.5f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));     // exp(-x^2/2)
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
+  const float poly = fmaf(fmaf(-3.1580704e-4f, x2, 3.6798256e-2f), x2, 7.9771783e-1f);
+  const float dpoly = fmaf(fmaf(-1.5790352e-3f, x2, 1.1039477e-1f), x2, 7.9771783e-1f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * poly));
+  const float cdf = fmaf(0.5f, t, 0.5f);
+  return fmaf(0.5f * xc * dpoly, fmaf(-t, t, 1.0f), cdf);
 }
 
 // epilogue activation shared by the SIMT and tcgen05 GEMMs; `a` is the aux value (ignored when unused)
