@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_x8_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
                  T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_colsum,
-                 float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
+                 float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter,
+                 float* __restrict__ part) {
   typedef typename Row8<T>::raw raw_t;
   constexpr int U = sizeof(T) == 2 ? 2 : 1;
   __shared__ float s_all[4 * 128];
@@ -488,7 +489,7 @@ ln_bwd_x8_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restr
       }
     }
   }
-  if (dgamma == nullptr) return;      // dx only
+  if (dgamma == nullptr && part == nullptr) return;      // dx only
   // fold the four row groups of the warp (lanes l, l^8, l^16, l^24 own the same columns), then one smem atomic per column
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -508,6 +509,10 @@ ln_bwd_x8_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restr
     }
   }
   __syncthreads();
+  if (part != nullptr) {
+    for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) part[(size_t)blockIdx.x * (4 * E) + i] = s_all[i];
+    return;
+  }
   if (ws != nullptr) {
     float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
     const int offs[4] = {0, E, 2 * E, 3 * E};
@@ -759,10 +764,10 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
     const int g8 = grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_BWD_X8_CTAS_PER_SM", 2));
     if (dtype == VG_F32)
       launch_pdl(ln_bwd_x8_kernel<float>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
-                 rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+                 rstd, gamma, (const float*)dres, (float*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter, (float*)nullptr);
     else
       launch_pdl(ln_bwd_x8_kernel<bf16>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
-                 rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+                 rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter, (float*)nullptr);
     return check_launch("layernorm_bwd");
   }
   if (E <= 128) {      // specialised kernel: 8 (bf16) / 4 (fp32) rows per warp in flight
@@ -828,6 +833,21 @@ extern "C" int vg_layernorm_bwd_partials(int dtype, int64_t rows, int E, const v
   VG_REQUIRE(partials != nullptr && max_parts >= 1, VG_ERR_ARG, "layernorm_bwd_partials: no partial buffer");
   VG_REQUIRE(rows > 0, VG_ERR_SHAPE, "layernorm_bwd_partials: empty input");
   const int rpi = dtype == VG_F32 ? 4 : 8;
+  static int px8 = -1;
+  if (px8 < 0) { const char* e = getenv("VG_LN_BWD_X8"); px8 = (e && e[0] == '1') ? 1 : 0; }
+  if (px8 == 1 && E % 8 == 0) {          // experiment: 8-lanes-per-row variant (half the instructions, 193 registers -> 1 CTA/SM)
+    const int g8 = min(grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_BWD_X8_CTAS_PER_SM", 1)), max_parts);
+    if (dtype == VG_F32)
+      launch_pdl(ln_bwd_x8_kernel<float>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
+                 rstd, gamma, (const float*)dres, (float*)dx, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, 0,
+                 (unsigned*)nullptr, partials);
+    else
+      launch_pdl(ln_bwd_x8_kernel<bf16>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
+                 rstd, gamma, (const bf16*)dres, (bf16*)dx, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, 0,
+                 (unsigned*)nullptr, partials);
+    const int rc8 = check_launch("layernorm_bwd_partials");
+    return rc8 ? rc8 : g8;
+  }
   const int grid = min(grid_for_rows((rows + rpi - 1) / rpi, 2), max_parts);
   if (dtype == VG_F32)
     launch_pdl(ln_bwd_e128_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)dy, (const float*)x, mean,
