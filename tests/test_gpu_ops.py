@@ -131,6 +131,29 @@ def test_gemm_row_remaps(vb):
         assert rel(out.view(B, n + 1, E), ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("B,n,K,E,off", [(5, 64, 48, 128, 0), (3, 256, 192, 768, 0), (4, 64, 432, 432 + 16, 1), (2, 32, 64, 64, 0)])
+def test_gemm_row_remaps_staged_3d(vb, B, n, K, E, off):
+    """Row groups that are multiples of 32 (the real patch-embedding shapes: 64 / 256 patches per image) take the staged
+    epilogue with 3-D TMA stores (slot 0 of every group untouched) and the broadcast positional table as a TMA-loaded
+    residual; must equal the direct-epilogue result and the fp32 formula."""
+    g = gen(B + n + K)
+    a = torch.randn(B * n, K, generator=g).bfloat16()
+    w = (torch.randn(E, K, generator=g) * 0.2).bfloat16()
+    bias = torch.randn(E, generator=g)
+    pos = torch.randn(n + off, E, generator=g).bfloat16()
+    ref = torch.full((B, n + 1, E), 7.0)
+    ref[:, 1:] = (a.float() @ w.float().t() + bias).view(B, n, E) + pos.float()[off:]
+    out = torch.full((B * (n + 1), E), 7.0, device="cuda", dtype=torch.bfloat16)
+    vb.ops.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), residual=pos.cuda(), res_row_mod=n, res_row_off=off, c_row_group=n, out=out,
+                path=vb.lib.GEMM_TCGEN05)
+    assert rel(out.view(B, n + 1, E), ref) < BF16_TOL
+    assert torch.equal(out.view(B, n + 1, E)[:, 0].float().cpu(), torch.full((B, E), 7.0))       # CLS slots untouched
+    out2 = torch.full((B * (n + 1), E), 7.0, device="cuda", dtype=torch.bfloat16)
+    vb.ops.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), residual=pos.cuda(), res_row_mod=n, res_row_off=off, c_row_group=n, out=out2,
+                path=vb.lib.GEMM_SIMT)
+    assert rel(out, out2) < BF16_TOL
+
+
 def test_gemm_tc_rejects_and_errors(vb):
     a = torch.randn(16, 10, device="cuda").bfloat16()       # K=10 -> 20-byte pitch: not TMA-able
     w = torch.randn(32, 10, device="cuda").bfloat16()

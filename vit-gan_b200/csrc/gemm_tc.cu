@@ -256,7 +256,7 @@ __device__ __forceinline__ void ln_epilogue(const Params& p, const uint32_t (&r0
 // One epilogue warp's share ([32 rows x 64 columns]) of one accumulator tile, staged (TMA) epilogue:
 //   wait for the staging tiles -> stage bias -> prefetch residual/aux by TMA -> wait accumulator -> TMEM -> registers ->
 //   release TMEM -> math -> swizzled smem -> TMA store / reduce-add.
-template <int MODE, int ACT, bool LN = false>
+template <int MODE, int ACT, bool LN = false, bool REMAP = false>
 __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_pre,
                                             const CUtensorMap* tmap_res, const CUtensorMap* tmap_aux, uint32_t taddr,
                                             uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
@@ -289,7 +289,8 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
     mbar_expect_tx(wbar, (has_res ? (f32 ? 8192u : 4096u) : 0u) + (has_aux ? 4096u : 0u));
     if (has_res) {
-      tma_load_2d(bufC, tmap_res, wbar, n0, m0);
+      // REMAP: the residual is a [mod (+off), N] table broadcast over the row groups (positional embedding)
+      tma_load_2d(bufC, tmap_res, wbar, n0, REMAP ? (p.res_row_mod > 0 ? m0 % p.res_row_mod : m0) + p.res_row_off : m0);
       if (f32) tma_load_2d(bufX, tmap_res, wbar, n0 + 32, m0);
     }
     if (has_aux) tma_load_2d(bufX, tmap_aux, wbar, n0, m0);
@@ -327,6 +328,10 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
       } else if (f32) {
         tma_store_2d(tmap_c, bufC, n0, m0);
         if (n0 + 32 < p.N) tma_store_2d(tmap_c, bufX, n0 + 32, m0);
+      } else if (REMAP) {
+        // C is [M / G, G + 1, N]: row m of the product lands in slot 1 + m % G of group m / G (slot 0 = CLS token, left alone);
+        // G % 32 == 0, so this warp's 32 rows stay inside one group
+        tma_store_3d(tmap_c, bufC, n0, 1 + m0 % p.c_row_group, m0 / p.c_row_group);
       } else {
         tma_store_2d(tmap_c, bufC, n0, m0);
         if (has_pre || do_ln) tma_store_2d(tmap_pre, bufX, n0, m0);     // c_pre, or the fused LayerNorm output (same map slot)
@@ -342,7 +347,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
 // BNT: tile width.  128 (4-stage ring) for the skinny / memory-bound shapes; 256 (3 stages, both accumulator stages = all 512
 // TMEM columns) for the compute-bound ones: a 128x128 tile reads 32 KB of smem per 2.1 MFLOP (256 clk of smem bandwidth for 256
 // clk of tensor pipe: smem-bound), a 128x256 tile 48 KB per 4.2 MFLOP (384 vs 512 clk).
-template <int MODE, int ACT, int BNT, bool LN = false>
+template <int MODE, int ACT, int BNT, bool LN = false, bool REMAP = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
@@ -499,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int g = 0; g < BN / 128; ++g) {           // this warp's 64-column groups of the tile (one at BN = 128, two at 256)
           const int col = half * (BN / 2) + g * 64;
-          staged_tile<MODE, ACT, LN>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
+          staged_tile<MODE, ACT, LN, REMAP>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
                                      tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
                                      g == BN / 128 - 1, ew, ln, (n_staged++ & 1) != 0);
         }
@@ -709,6 +714,20 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
   return VG_OK;
 }
 
+// bf16 tensor [d2, d1, cols] with byte strides s1 (between d1 rows) and s2 (between d2 slabs); box {64 cols, 32 rows, 1}, 128B swizzle
+int make_map3(CUtensorMap* map, const void* ptr, int64_t cols, int64_t d1, int64_t d2, int64_t s1, int64_t s2) {
+  EncodeTiledFn enc = get_encode();
+  VG_REQUIRE(enc != nullptr, VG_ERR_LAUNCH, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)s1, (cuuint64_t)s2};
+  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_REQUIRE(r == CUDA_SUCCESS, VG_ERR_LAUNCH, "gemm_tc: cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+  return VG_OK;
+}
+
 }  // namespace
 
 static unsigned long long* g_trace = nullptr;
@@ -808,8 +827,18 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   p.epi_tma = !(p.dbg & 2) && a.c_row_group == 0 && a.res_row_mod == 0 && tma_ok(a.C, a.ldc) &&
               (!a.residual || tma_ok(a.residual, a.ldres)) && (!a.aux || tma_ok(a.aux, a.ldaux)) &&
               (!a.c_pre || tma_ok(a.c_pre, a.ldpre)) && !(f32 && (a.aux || a.c_pre || a.act != VG_ACT_NONE));
+  // row-group remap (patch embedding: CLS slot + broadcast positional table) through 3-D TMA stores when the groups are
+  // warp-tile aligned; otherwise the direct (MODE 0) epilogue
+  const bool remap = !(p.dbg & 2) && a.c_row_group > 0 && a.c_row_group % 32 == 0 && a.M % a.c_row_group == 0 &&
+                     (a.res_row_mod == 0 || a.res_row_mod == a.c_row_group) && !f32 && !a.aux && !a.c_pre && !a.ln_gamma && !a.accumulate &&
+                     a.act == VG_ACT_NONE && tma_ok(a.C, a.ldc) && (!a.residual || tma_ok(a.residual, a.ldres));
   CUtensorMap mc = ma, mp = ma, mr = ma, mx = ma;     // placeholders when unused
-  if (p.epi_tma) {
+  if (remap) {
+    p.epi_tma = 1;
+    const int G = a.c_row_group;
+    if ((rc = make_map3(&mc, a.C, a.N, G + 1, a.M / G, a.ldc * 2, (int64_t)(G + 1) * a.ldc * 2))) return rc;
+    if (a.residual && (rc = make_map(&mr, a.residual, (a.res_row_mod > 0 ? a.res_row_mod : a.M) + a.res_row_off, a.N, a.ldres, 64, 32, false))) return rc;
+  } else if (p.epi_tma) {
     const int bc = f32 ? 32 : 64;                      // 128-byte wide boxes, 32 rows
     if ((rc = make_map(&mc, a.C, a.M, a.N, a.ldc, bc, 32, f32))) return rc;
     if (a.c_pre && (rc = make_map(&mp, a.c_pre, a.M, a.N, a.ldpre, bc, 32, f32))) return rc;
@@ -860,6 +889,17 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
     }                                                                                                                          \
     launch_pdl(gemm_tc_kernel<MODE_, ACT_, BN_>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);             \
   } while (0)
+  if (remap) {
+    constexpr int smem_ = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, VG_ACT_NONE, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_);
+      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    launch_pdl(gemm_tc_kernel<1, VG_ACT_NONE, 128, false, true>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);
+    return check_launch("gemm_tc");
+  }
   if (a.ln_gamma) {
     VG_REQUIRE(a.act == VG_ACT_NONE, VG_ERR_UNSUPPORTED, "gemm_tc: fused LayerNorm is built for the activation-free epilogue");
     constexpr int smem_ = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512;
