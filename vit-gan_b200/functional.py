@@ -244,8 +244,7 @@ def acc_wgrad(dy2, x2, params, bias_params=None):
     """dW = dy2^T x2 for one parameter or a row-stack of parameters.  Returns the gradient tensor ([sum N, K]),
     or None if it was accumulated in place into the parameters' .grad.
     bias_params: the matching bias parameter(s); their gradient colsum(dy2) is then produced by the same GEMM when both
-    gradients accumulate in place on the tcgen05 path -- returns (dW, db) with db == "fused" in that case, else db is
-    whatever acc_colsum returns."""
+    gradients accumulate in place on the tcgen05 path -- returns (None, None) in that case, else (acc_wgrad(...), acc_colsum(...))."""
     n = sum(p.shape[0] for p in params)
     view = _grad_view(params, n, x2.shape[1])
     if bias_params is None:
@@ -372,11 +371,15 @@ class LinearFn(Function):
             if dx.dtype != xdtype:
                 dx = ops.cast(dx, xdtype)
             dx = dx.reshape(xshape)
-        if _want(ctx, 1):
-            dw = acc_wgrad(dy2, x2, [weight])
+        if _want(ctx, 1) and has_bias and _want(ctx, 2):
+            dw, db = acc_wgrad(dy2, x2, [weight], [ctx.bias_ref])        # bias gradient from the same GEMM where supported
             dw = None if dw is None else dw.reshape(weight.shape)
-        if has_bias and _want(ctx, 2):
-            db = acc_colsum(dy2, [ctx.bias_ref])
+        else:
+            if _want(ctx, 1):
+                dw = acc_wgrad(dy2, x2, [weight])
+                dw = None if dw is None else dw.reshape(weight.shape)
+            if has_bias and _want(ctx, 2):
+                db = acc_colsum(dy2, [ctx.bias_ref])
         return dx, dw, db, None, None, None, None
 
 
@@ -445,9 +448,8 @@ class EmbedV2Fn(Function):
             dimg = ops.col2im(dpatches, B, Cc, I, patch)
         if ctx.skip_pg:
             return dimg, None, None, None, None, None
-        dw = acc_wgrad(dtok, patches, [conv_w])
+        dw, db = acc_wgrad(dtok, patches, [conv_w], [ctx.bias_ref])
         dw = None if dw is None else dw.reshape(conv_w.shape)
-        db = acc_colsum(dtok, [ctx.bias_ref])
         return dimg, dw, db, dpos.reshape(pos_shape), dcls.reshape(cls_shape), None
 
 
