@@ -932,6 +932,26 @@ attn_bwd_hp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
 }
 
+// ================================================================================================ next: S = 257, d = 192 (C4) -- design notes
+// Not built yet; these shapes (and v1's d = 96 / 108 and the L2-distance scores) still run on the CUDA-core kernels of
+// attention.cu.  What the budget analysis of this round says the tcgen05 version has to look like:
+//   forward, work item = (b, h, 128-row q tile), one CTA per SM:
+//     TMEM  S [128 x NK<=272] fp32 (272 columns: one MMA of N = 256 plus one of N = 16) | O [128 x 192] (192 columns) = 464 <= 512;
+//     smem  Q [128 x 192] = 3 SW128 chunks (48 KB) | P [128 x 272] bf16 K-major = 5 chunks (80 KB) | ring of 64-key K / V blocks,
+//           3 chunks x 8 KB = 24 KB each, 3 stages (72 KB) = 200 KB;
+//     flow  stream K blocks -> S (12 k-steps per block) ; one softmax over the whole key range (no online rescaling: 257 keys fit
+//           in one S tile), thread = row, two TMEM passes ; stream V blocks -> O += P_j V_j (B MN-major, N = 192 through LBO) ;
+//           drain through the P region (free once the last PV has committed) -> TMA store.  ~4.5 us per item, 3072 items per
+//           GPU at C4 -> ~95 us per layer against ~600 us of GEMMs.  The third q tile holds one row (S = 256 + CLS): skip the
+//           softmax work of empty TMEM lane quadrants as the head-parallel kernels do.
+//   backward: d = 192 does not leave room for dK / dV accumulators of all 272 keys (3 M tiles x 192 columns x 2 = 1152 TMEM
+//     columns), so either (a) item = (b, h, q tile): S and dP share [0, 272), one [128 x 192] output tile at a time behind them,
+//     dQ stored, partial dK / dV of the three q tiles combined with bf16 TMA reduce-add into zero-initialised buffers; smem is
+//     the constraint (Q 48 + dO 48 + P/dS 80 + ring 48 = 224 KB, staging must alias the ring); or (b) the H = 12 / d = 64
+//     variant of the same model (identical FLOPs), where K / V of a head (34 KB each) stay resident and only
+//     S / dP need streaming.  The L2-distance variant adds the row norms |q|^2, |k|^2 (one extra N = 16 ones-MMA each, as in
+//     gemm_tc's a_rowsum) and a sqrt in the score epilogue; d = 108 needs the head padded to 112 columns at projection time.
+
 // ================================================================================================ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
