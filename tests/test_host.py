@@ -128,3 +128,26 @@ def test_grad_buckets_gloo_world2_equals_global_batch():
     torch.nn.functional.mse_loss(net[:4](x * 0.5), y).backward()
     assert torch.allclose(ret[0], ret[1])
     assert torch.allclose(ret[0], flat.flat_grad, atol=1e-6), (ret[0] - flat.flat_grad).abs().max()
+
+
+def test_merged_discriminator_pass_is_the_same_step_host_logic():
+    """train.gan_step(merge_d_passes=True) -- D(real) and D(fake.detach()) as ONE pass over the concatenated batch with
+    loss = mean_real + mean_fake -- is the reference's two-pass sequence (src/v2/training.py:177-197) up to fp32 summation
+    order: same three losses and same parameters after two optimizer steps.  Host-side schedule only (plain torch modules on
+    the CPU stand in for the kernels; the GPU tests pin the real thing against the reference-generated loss curves)."""
+    import copy
+    import vitgan_b200 as vb
+    torch.manual_seed(0)
+    g0 = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(12, 16), torch.nn.Tanh(), torch.nn.Linear(16, 12), torch.nn.Unflatten(1, (3, 2, 2)))
+    d0 = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
+    data = [(torch.randn(6, 3, 2, 2), torch.randn(6, 3, 2, 2)) for _ in range(2)]
+    out = {}
+    for merged in (False, True):
+        g, d = copy.deepcopy(g0).double(), copy.deepcopy(d0).double()
+        go, do = torch.optim.AdamW(g.parameters(), lr=1e-2), torch.optim.AdamW(d.parameters(), lr=1e-2)
+        losses = [torch.stack([t.reshape(()) for t in vb.train.gan_step(g, d, go, do, r.double(), n.double(), "ce", merge_d_passes=merged)])
+                  for r, n in data]
+        out[merged] = (torch.stack(losses), torch.cat([p.detach().reshape(-1) for p in list(g.parameters()) + list(d.parameters())]))
+    # gan_step evaluates the loss head in fp32 (`.float()` on the logits), so fp32 rounding is the floor
+    assert torch.allclose(out[True][0], out[False][0], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out[True][1], out[False][1], rtol=1e-4, atol=1e-5)
