@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VG_ABI_VERSION 3
+#define VG_ABI_VERSION 4
 
 typedef enum { VG_F32 = 0, VG_BF16 = 1 } vg_dtype;
 typedef enum {
@@ -162,6 +162,10 @@ int vg_attention_bwd(int dtype, int mode, int B, int H, int S, int d, const void
                      const void* v, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o,
                      const float* lse, void* dq, void* dk, void* dv, int64_t ld_dqkv, float scale,
                      float* delta_ws /* [B,H,S] fp32 scratch */, void* stream);
+/* Which kernel family the two calls above take for a bf16/fp32 problem of this shape with 16-byte aligned operands:
+ * 0 = CUDA-core flash kernel (fp32 parity path, odd head sizes), 1 = single-tile tcgen05 (S <= 128, d in {32, 64}, dot),
+ * 2 = multi-tile tcgen05 (d in {96, 112, 192}, S <= 272; L2-distance scores for d = 96 / 112).  Test / bench introspection. */
+int vg_attention_path(int dtype, int mode, int B, int H, int S, int d);
 
 /* v2 patchify: img fp32 (B,C,I,I) -> patches[B*N, C*P*P] in `dtype`, k = c*P*P + i*P + j (conv weight order).
  * Together with vg_gemm (bias, c_row_group = N, residual = pos_embedding with res_row_mod = N) and

@@ -469,6 +469,14 @@ int attention_fwd_tc(int B, int H, int S, int d, const void* q, const void* k, c
                      float* lse, float scale, cudaStream_t st);
 int attention_bwd_tc(int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, const void* d_o,
                      int64_t ldo, const float* lse, void* dq, void* dk, void* dv, int64_t ldd, float scale, cudaStream_t st);
+// multi-tile tcgen05 kernels (attention_mt.cu): d = 96 / 112 / 192, dot or L2 scores, S <= 272
+bool attention_mt_supported(int dtype, int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v,
+                            int64_t ld_qkv, const void* o, int64_t ld_o);
+int attention_fwd_mt(int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                     float* lse, float scale, cudaStream_t st);
+int attention_bwd_mt(int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, const void* o,
+                     const void* d_o, int64_t ldo, const float* lse, void* dq, void* dk, void* dv, int64_t ldd, float scale, float* delta,
+                     cudaStream_t st);
 }  // namespace vg
 
 using namespace vg;
@@ -482,6 +490,8 @@ extern "C" int vg_attention_fwd(int dtype, int mode, int B, int H, int S, int d,
   // tensor-core path (attention_tc.cu) for the single-tile bf16 dot-product case; CUDA-core flash kernel otherwise
   if (attention_tc_supported(dtype, mode, B, H, S, d, q, k, v, ld_qkv, o, ld_o))
     return attention_fwd_tc(B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st);
+  if (attention_mt_supported(dtype, mode, B, H, S, d, q, k, v, ld_qkv, o, ld_o))
+    return attention_fwd_mt(mode, B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st);
   if (dtype == VG_F32)
     return mode == VG_ATTN_L2 ? fwd_t<float, VG_ATTN_L2>(B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st)
                               : fwd_t<float, VG_ATTN_DOT>(B, H, S, d, q, k, v, ld_qkv, o, ld_o, lse, scale, st);
@@ -500,6 +510,9 @@ extern "C" int vg_attention_bwd(int dtype, int mode, int B, int H, int S, int d,
   if (attention_tc_supported(dtype, mode, B, H, S, d, q, k, v, ld_qkv, d_o, ld_o) && ld_dqkv % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0)
     return attention_bwd_tc(B, H, S, d, q, k, v, ld_qkv, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, st);
+  if (attention_mt_supported(dtype, mode, B, H, S, d, q, k, v, ld_qkv, d_o, ld_o) && ld_dqkv % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
+    return attention_bwd_mt(mode, B, H, S, d, q, k, v, ld_qkv, o, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, delta_ws, st);
   if (dtype == VG_F32)
     return mode == VG_ATTN_L2
                ? bwd_t<float, VG_ATTN_L2>(B, H, S, d, q, k, v, ld_qkv, o, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, delta_ws, st)
@@ -507,4 +520,14 @@ extern "C" int vg_attention_bwd(int dtype, int mode, int B, int H, int S, int d,
   return mode == VG_ATTN_L2
              ? bwd_t<bf16, VG_ATTN_L2>(B, H, S, d, q, k, v, ld_qkv, o, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, delta_ws, st)
              : bwd_t<bf16, VG_ATTN_DOT>(B, H, S, d, q, k, v, ld_qkv, o, d_o, ld_o, lse, dq, dk, dv, ld_dqkv, scale, delta_ws, st);
+}
+
+/* Which kernel family vg_attention_fwd / _bwd take for this problem (pointers and pitches assumed 16-byte friendly):
+ * 0 = CUDA-core flash kernel, 1 = single-tile tcgen05 (attention_tc.cu), 2 = multi-tile tcgen05 (attention_mt.cu). */
+extern "C" int vg_attention_path(int dtype, int mode, int B, int H, int S, int d) {
+  const void* al = reinterpret_cast<const void*>(uintptr_t(256));
+  const int64_t ld = (int64_t)3 * H * d, ldo = (int64_t)H * d;
+  if (ld % 8 == 0 && attention_tc_supported(dtype, mode, B, H, S, d, al, al, al, ld, al, ldo)) return 1;
+  if (ld % 8 == 0 && attention_mt_supported(dtype, mode, B, H, S, d, al, al, al, ld, al, ldo)) return 2;
+  return 0;
 }

@@ -1,0 +1,1060 @@
+// attention_mt.cu -- multi-tile flash attention on tcgen05 / TMEM / TMA for the head sizes the single-tile kernels of
+// attention_tc.cu cannot take: d = 192 with S = 257 (the scaled v2 config, src/v2/modules.py:142-159), d = 96 (v1 generator,
+// dot scores, src/v1/attention.py:69-70) and d = 112 (v1 discriminator head of 108 zero-padded to 112 by the caller,
+// L2-distance scores, src/v1/attention.py:66-67).  bf16 operands, fp32 accumulation / statistics, S <= 272 keys.
+//
+// Three kernels, one CTA per SM, persistent over (batch, head) problems; warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
+// alloc), warps 2..5 = 128 compute threads (thread = TMEM lane = one row of the accumulator tile):
+//   forward          item = 128-query tile.  S[128 x NK] = Q K^T is accumulated over 64-key blocks streamed through a TMA ring
+//                    (NK <= 272 fp32 columns: the whole key range fits TMEM, so the softmax is exact two-pass -- no online
+//                    rescaling); P goes to smem as bf16 in 64-key chunks and O += P_j V_j starts while later chunks are still
+//                    being exponentiated; O (D columns) sits beside S in TMEM.
+//   backward, dQ     item = 128-query tile, q-major: per 64-key block S = Q K_j^T and dP = dO V_j^T (double-buffered TMEM),
+//                    dS = P (dP - delta) scale -> smem -> dQ += dS K_j.  Also produces delta = rowsum(dO * O) for the dK/dV
+//                    kernel.
+//   backward, dK/dV  item = 128-key tile, key-major (transposed scores): per 64-query block S^T = K Q_i^T, P^T -> smem,
+//                    dP^T = V dO_i^T over the consumed S^T columns, dV += P^T dO_i, dS^T -> smem, dK += dS^T Q_i.
+//                    dK | dV accumulators take 2 D <= 384 TMEM columns, the two S^T/dP^T buffers the other 128.
+// The two backward kernels recompute S (7 GEMMs instead of 5) but need no cross-CTA reduction and no atomics: with d = 192
+// the dQ, dK and dV accumulators of one problem (3 x 192 columns x 3 row tiles) cannot live in one SM's 512 TMEM columns.
+//
+// L2-distance mode (torch.cdist matmul-path semantics): score = sqrt(max(0, |q|^2 + |k|^2 - 2 q.k)); the row norms
+// come from the bf16 operands in fp32.  Backward: G = P (dP - delta) scale / dist (0 where dist = 0),
+// dQ = rowsum(G) q - G K, dK = colsum(G) k - G^T Q  -- the same MMAs with a rank-1 correction in the drain.
+//
+// All global <-> shared traffic is TMA: operands arrive as [rows x 64 col] SWIZZLE_128B chunks straight from the fused QKV
+// projection output (3-D maps [B, S, cols]; rows >= S zero-filled on load, clipped on store), results leave through swizzled
+// staging sub-tiles of 64 / 32 / 16 columns (SWIZZLE_128B / 64B / 32B) so that d = 96 and 112 store exactly their own columns.
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace vg {
+namespace {
+
+constexpr int NTHREADS = 192;
+constexpr int QCH = 128 * 128;            // one [128 rows x 64 bf16] swizzled chunk
+constexpr int BCH = 64 * 128;             // one [64 rows x 64 bf16] swizzled chunk
+constexpr int MAXNK = 272;                // S rounded up to 16 must fit the S region of TMEM
+constexpr int MAXKB = 5;                  // ceil(272 / 64)
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct OutMaps { CUtensorMap m64, m32, m16; };
+
+struct MtGeo {
+  int B, H, S, NK;          // NK = S rounded up to 16
+  int n_t;                  // 128-row tiles per problem
+  int n_b;                  // 64-row blocks per problem
+  int64_t ld, ldo;          // element pitch of q/k/v rows and of o/dO rows (direct global reads: norms, delta)
+  float scale;
+  float* lse;               // [B, H, S]
+  float* delta;             // [B, H, S]
+  const bf16 *q, *k, *o;
+};
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+// n = 32 or 16 accumulator columns of this thread's lane -> v[0..n)
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[32], int n) {
+  if (n >= 32) tmem_ld32_nowait(taddr, v); else tmem_ld16p(taddr, v);
+  tmem_ld_wait();
+}
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// ---- staging tile of a [128 x D] bf16 result: D/64 SW128 chunks, then a 32-column SW64 sub-tile, then a 16-column SW32 one
+template <int D> struct Stg {
+  static constexpr int FULL = D / 64;
+  static constexpr bool R32 = (D % 64) >= 32;
+  static constexpr bool R16 = (D % 32) >= 16;
+};
+template <int D>
+__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int row, int c8) {   // 16-byte chunk c8 = column / 8 of `row`
+  constexpr int FULL = Stg<D>::FULL;
+  if (c8 < FULL * 8) return base + (uint32_t)(c8 >> 3) * QCH + (uint32_t)row * 128u + ((((uint32_t)c8 & 7u) ^ ((uint32_t)row & 7u)) << 4);
+  uint32_t b2 = base + FULL * QCH;
+  int c = c8 - FULL * 8;
+  if (Stg<D>::R32) {
+    if (c < 4) return b2 + (uint32_t)row * 64u + (((uint32_t)c ^ (((uint32_t)row >> 1) & 3u)) << 4);
+    b2 += 128 * 64; c -= 4;
+  }
+  return b2 + (uint32_t)row * 32u + (((uint32_t)c ^ (((uint32_t)row >> 2) & 1u)) << 4);
+}
+template <int D>
+__device__ __forceinline__ void stg_store(const OutMaps& m, uint32_t base, int col0, int row0, int b) {
+  constexpr int FULL = Stg<D>::FULL;
+#pragma unroll
+  for (int i = 0; i < FULL; ++i) tma_store_3d(&m.m64, base + i * QCH, col0 + 64 * i, row0, b);
+  if (Stg<D>::R32) tma_store_3d(&m.m32, base + FULL * QCH, col0 + 64 * FULL, row0, b);
+  if (Stg<D>::R16) tma_store_3d(&m.m16, base + FULL * QCH + (Stg<D>::R32 ? 128 * 64 : 0), col0 + 64 * FULL + (Stg<D>::R32 ? 32 : 0), row0, b);
+}
+// 32 (or 16) fp32 accumulator values -> bf16 -> staging columns [c, c + n) of `row`
+template <int D>
+__device__ __forceinline__ void stg_write(uint32_t base, int row, int c, const float* o, int n) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (8 * i < n)
+      sts128(stg_addr<D>(base, row, (c >> 3) + i), pack_bf16(o[8 * i], o[8 * i + 1]), pack_bf16(o[8 * i + 2], o[8 * i + 3]),
+             pack_bf16(o[8 * i + 4], o[8 * i + 5]), pack_bf16(o[8 * i + 6], o[8 * i + 7]));
+}
+// squared norm of D contiguous bf16 (16-byte aligned), fp32
+template <int D>
+__device__ __forceinline__ float row_sqnorm(const bf16* p) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; c += 8) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p + c));
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float a = bf16_lo(u[j]), b = bf16_hi(u[j]); s = fmaf(a, a, s); s = fmaf(b, b, s); }
+  }
+  return s;
+}
+// this thread's row of a K-major operand tile ([rows x 64 col] SW128 chunks, `chunk_bytes` apart) -> fp32
+template <int D>
+__device__ __forceinline__ void read_tile_row(uint32_t tile, uint32_t chunk_bytes, int row, float* out) {
+#pragma unroll
+  for (int c8 = 0; c8 < D / 8; ++c8) {
+    uint32_t a0, a1, a2, a3;
+    lds128(swz(tile + (uint32_t)(c8 >> 3) * chunk_bytes, row, c8 & 7), a0, a1, a2, a3);
+    out[8 * c8] = bf16_lo(a0); out[8 * c8 + 1] = bf16_hi(a0); out[8 * c8 + 2] = bf16_lo(a1); out[8 * c8 + 3] = bf16_hi(a1);
+    out[8 * c8 + 4] = bf16_lo(a2); out[8 * c8 + 5] = bf16_hi(a2); out[8 * c8 + 6] = bf16_lo(a3); out[8 * c8 + 7] = bf16_hi(a3);
+  }
+}
+// K-major descriptor of k-step `k` (16 bf16) inside a tile made of 64-column chunks `chunk_bytes` apart
+__device__ __forceinline__ uint64_t kdesc(uint32_t tile, uint32_t chunk_bytes, int k) {
+  return desc_k(tile + (uint32_t)(k >> 2) * chunk_bytes + (uint32_t)(k & 3) * 32u);
+}
+
+__device__ __forceinline__ void tmem_alloc512(uint32_t slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free512(uint32_t tmem) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ================================================================================================ forward
+template <int D> struct FwdCfg {
+  static constexpr int DC = (D + 63) / 64, KS = D / 16;
+  static constexpr int NST = 4;                              // ring stages of one 64-key K or V block
+  static constexpr int O_COL = 288;                          // S in TMEM columns [0, 272), O in [288, 288 + D)
+  static constexpr int Q_OFF = 0, P_OFF = DC * QCH, RING_OFF = P_OFF + MAXKB * QCH, KN_OFF = RING_OFF + NST * DC * BCH;
+  static constexpr int BAR_OFF = KN_OFF + MAXNK * 4, NBAR = 6 + 2 * NST + 2 * MAXKB;
+  static constexpr int SMEM = BAR_OFF + NBAR * 8 + 16;
+};
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ OutMaps map_o, const MtGeo g) {
+  using C = FwdCfg<D>;
+  constexpr int DC = C::DC, KS = C::KS, NST = C::NST, O_COL = C::O_COL;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t base = smem_u32(smem_dyn);
+  const uint32_t q_t = base + C::Q_OFF, p_t = base + C::P_OFF, ring = base + C::RING_OFF, bar = base + C::BAR_OFF;
+  float* kn = reinterpret_cast<float*>(smem_dyn + C::KN_OFF);
+  const uint32_t q_full = bar, q_empty = bar + 8, s_full = bar + 16, s_free = bar + 24, o_full = bar + 32, o_free = bar + 40;
+  auto kv_full = [&](int i) { return bar + 8u * (6 + i); };
+  auto kv_empty = [&](int i) { return bar + 8u * (6 + NST + i); };
+  auto p_full = [&](int i) { return bar + 8u * (6 + 2 * NST + i); };
+  auto p_empty = [&](int i) { return bar + 8u * (6 + 2 * NST + MAXKB + i); };
+  const uint32_t tmem_slot = bar + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + C::BAR_OFF + 8 * C::NBAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) { printf("attention_mt: dynamic smem base not 1024-aligned\n"); __trap(); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(o_full, 1); mbar_init(o_free, 128);
+    for (int i = 0; i < NST; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_empty(i), 1); }
+    for (int i = 0; i < MAXKB; ++i) { mbar_init(p_full(i), 128); mbar_init(p_empty(i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
+  const int total = g.B * g.H;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t rc = 0, tc = 0;                       // ring slot counter, tile counter
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / g.H, col0 = (w % g.H) * D;
+        for (int t = 0; t < g.n_t; ++t, ++tc) {
+          mbar_wait(q_empty, (tc & 1u) ^ 1u);
+          mbar_expect_tx(q_full, DC * QCH);
+#pragma unroll
+          for (int c = 0; c < DC; ++c) tma_load_3d(q_t + c * QCH, &map_q, q_full, col0 + 64 * c, t * 128, b);
+          for (int pass = 0; pass < 2; ++pass)
+            for (int kb = 0; kb < g.n_b; ++kb, ++rc) {
+              const int st = rc % NST;
+              mbar_wait(kv_empty(st), ((rc / NST) & 1u) ^ 1u);
+              mbar_expect_tx(kv_full(st), DC * BCH);
+#pragma unroll
+              for (int c = 0; c < DC; ++c)
+                tma_load_3d(ring + (st * DC + c) * BCH, pass == 0 ? &map_k : &map_v, kv_full(st), col0 + 64 * c, kb * 64, b);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_pv = make_idesc(128, D, 0, 1);            // O = P V : A K-major, B MN-major
+      uint32_t rc = 0, tc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int t = 0; t < g.n_t; ++t, ++tc) {
+          const uint32_t par = tc & 1u;
+          mbar_wait(q_full, par);
+          mbar_wait(s_free, par ^ 1u);
+          tc_fence_after();
+          for (int kb = 0; kb < g.n_b; ++kb, ++rc) {                  // S[:, 64 kb ..] = Q K_kb^T
+            const int st = rc % NST, nk = min(64, g.NK - 64 * kb);
+            mbar_wait(kv_full(st), (rc / NST) & 1u);
+            tc_fence_after();
+            const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = ring + st * DC * BCH;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * kb), kdesc(q_t, QCH, k), kdesc(kt, BCH, k), idesc_s, k > 0);
+            tc_commit(kv_empty(st));
+          }
+          tc_commit(s_full);
+          tc_commit(q_empty);
+          mbar_wait(o_free, par ^ 1u);
+          for (int kb = 0; kb < g.n_b; ++kb, ++rc) {                  // O += P_kb V_kb
+            const int st = rc % NST, nk = min(64, g.NK - 64 * kb);
+            mbar_wait(kv_full(st), (rc / NST) & 1u);
+            mbar_wait(p_full(kb), par);
+            tc_fence_after();
+            const uint32_t vt = ring + st * DC * BCH, pt = p_t + kb * QCH;
+            for (int kk = 0; kk < nk / 16; ++kk)
+              tc_mma(tmem + O_COL, desc_k(pt + kk * 32u), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(kv_empty(st));
+            tc_commit(p_empty(kb));
+          }
+          tc_commit(o_full);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + output drain: thread = query row
+    const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
+    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const bool leader = threadIdx.x == 64;
+    const float sc2 = g.scale * LOG2E;
+    uint32_t tc = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int b = w / g.H, h = w % g.H, col0 = h * D;
+      if (MODE == VG_ATTN_L2) {                       // |k_j|^2 of this problem's keys -> smem (broadcast reads below)
+        named_bar(2, 128);
+        for (int j = tid; j < g.NK; j += 128)
+          kn[j] = j < g.S ? row_sqnorm<D>(g.k + ((int64_t)b * g.S + j) * g.ld + col0) : 0.f;
+        named_bar(2, 128);
+      }
+      for (int t = 0; t < g.n_t; ++t, ++tc) {
+        const uint32_t par = tc & 1u;
+        const int row_g = t * 128 + row;
+        const bool warp_on = t * 128 + quad * 32 < g.S;               // warp-uniform: this warp owns real query rows
+        float qq = 0.f;
+        if (MODE == VG_ATTN_L2 && row_g < g.S) qq = row_sqnorm<D>(g.q + ((int64_t)b * g.S + row_g) * g.ld + col0);
+        mbar_wait(s_full, par);
+        tc_fence_after();
+        float m = -INFINITY, l = 0.f;
+        // pass 1: row maximum of the raw scores (dot) / distances (L2) over the real keys
+        if (warp_on) {
+          for (int c = 0; c < g.NK; c += 32) {
+            uint32_t v[32];
+            const int n = min(32, g.NK - c);
+            tmem_ldn(t_lane + (uint32_t)c, v, n);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < n) {
+                float s = __uint_as_float(v[j]);
+                if (MODE == VG_ATTN_L2) s = sqrtf(fmaxf(fmaf(-2.f, s, qq + kn[c + j]), 0.f));
+                if (c + j < g.S) m = fmaxf(m, s);
+              }
+            }
+          }
+        }
+        // the previous tile's output store must have finished reading the staging tile (it aliases the P chunks)
+        if (leader) tma_wait_read();
+        named_bar(1, 128);
+        // pass 2: P = exp2((s - m) scale log2e) -> bf16 -> smem, one 64-key chunk at a time (the PV MMAs trail by one chunk)
+        const float mb = m * sc2;
+        for (int kb = 0; kb < g.n_b; ++kb) {
+          mbar_wait(p_empty(kb), par ^ 1u);
+          if (warp_on) {
+            const int nk = min(64, g.NK - 64 * kb);
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              if (c >= nk) break;
+              uint32_t v[32];
+              const int n = min(32, nk - c), c0 = 64 * kb + c;
+              tmem_ldn(t_lane + (uint32_t)c0, v, n);
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float p0 = 0.f, p1 = 0.f;
+                if (2 * j < n) {
+                  float s0 = __uint_as_float(v[2 * j]), s1 = __uint_as_float(v[2 * j + 1]);
+                  if (MODE == VG_ATTN_L2) {
+                    s0 = sqrtf(fmaxf(fmaf(-2.f, s0, qq + kn[c0 + 2 * j]), 0.f));
+                    s1 = sqrtf(fmaxf(fmaf(-2.f, s1, qq + kn[c0 + 2 * j + 1]), 0.f));
+                  }
+                  p0 = (c0 + 2 * j < g.S) ? ex2a(fmaf(s0, sc2, -mb)) : 0.f;
+                  p1 = (c0 + 2 * j + 1 < g.S) ? ex2a(fmaf(s1, sc2, -mb)) : 0.f;
+                  l += p0 + p1;
+                }
+                pk[j] = pack_bf16(p0, p1);
+              }
+              const uint32_t tile = p_t + kb * QCH;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (8 * i < n) sts128(swz(tile, row, (c >> 3) + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
+          }
+          fence_async_smem();                          // P chunk visible to the tensor-core (async) proxy
+          mbar_arrive(p_full(kb));
+        }
+        tc_fence_before();
+        mbar_arrive(s_free);                           // S fully read: the next tile's Q K^T may overwrite it
+        const float inv_l = 1.0f / l;
+        if (row_g < g.S) g.lse[(int64_t)w * g.S + row_g] = m * g.scale + __logf(l);
+        // ---- drain O: TMEM -> * 1/l -> bf16 -> staging (over the P chunks, all consumed once o_full fires) -> TMA store
+        mbar_wait(o_full, par);
+        tc_fence_after();
+        if (warp_on) {
+#pragma unroll
+          for (int c = 0; c < D; c += 32) {
+            uint32_t v[32];
+            const int n = (D - c) >= 32 ? 32 : 16;
+            tmem_ldn(t_lane + (uint32_t)(O_COL + c), v, n);
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * inv_l;
+            stg_write<D>(p_t, row, c, o, n);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(o_free);
+        fence_async_smem();
+        named_bar(1, 128);
+        if (leader) { stg_store<D>(map_o, p_t, col0, t * 128, b); tma_commit(); }
+      }
+    }
+    if (leader) tma_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_free512(tmem); }
+}
+
+// ================================================================================================ backward: dQ (+ delta)
+template <int D> struct DqCfg {
+  static constexpr int DC = (D + 63) / 64, KS = D / 16;
+  static constexpr int NS = D > 128 ? 2 : 3;                 // ring stages per operand (K blocks, V blocks)
+  static constexpr int DQ_COL = 256;                         // [S | dP] x 2 buffers in columns [0, 256), dQ in [256, 256 + D)
+  static constexpr int Q_OFF = 0, DO_OFF = DC * QCH, KR_OFF = 2 * DC * QCH, VR_OFF = KR_OFF + NS * DC * BCH;
+  static constexpr int DS_OFF = VR_OFF + NS * DC * BCH, KN_OFF = DS_OFF + 2 * QCH, BAR_OFF = KN_OFF + MAXNK * 4;
+  static constexpr int NBAR = 5 + 4 * NS + 8;
+  static constexpr int SMEM = BAR_OFF + NBAR * 8 + 16;
+};
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                      const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                      const __grid_constant__ OutMaps map_dq, const MtGeo g) {
+  using C = DqCfg<D>;
+  constexpr int DC = C::DC, KS = C::KS, NS = C::NS, DQ_COL = C::DQ_COL;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t base = smem_u32(smem_dyn);
+  const uint32_t q_t = base + C::Q_OFF, do_t = base + C::DO_OFF, kr = base + C::KR_OFF, vr = base + C::VR_OFF, ds_t = base + C::DS_OFF;
+  const uint32_t bar = base + C::BAR_OFF;
+  float* kn = reinterpret_cast<float*>(smem_dyn + C::KN_OFF);
+  const uint32_t qdo_full = bar, q_free = bar + 8, do_empty = bar + 16, dq_full = bar + 24, dq_free = bar + 32;
+  auto k_full = [&](int i) { return bar + 8u * (5 + i); };
+  auto k_empty = [&](int i) { return bar + 8u * (5 + NS + i); };
+  auto v_full = [&](int i) { return bar + 8u * (5 + 2 * NS + i); };
+  auto v_empty = [&](int i) { return bar + 8u * (5 + 3 * NS + i); };
+  auto sdp_full = [&](int i) { return bar + 8u * (5 + 4 * NS + i); };
+  auto sdp_free = [&](int i) { return bar + 8u * (7 + 4 * NS + i); };
+  auto ds_full = [&](int i) { return bar + 8u * (9 + 4 * NS + i); };
+  auto ds_empty = [&](int i) { return bar + 8u * (11 + 4 * NS + i); };
+  const uint32_t tmem_slot = bar + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + C::BAR_OFF + 8 * C::NBAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) { printf("attention_mt: dynamic smem base not 1024-aligned\n"); __trap(); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    mbar_init(qdo_full, 1); mbar_init(q_free, 1); mbar_init(do_empty, 1); mbar_init(dq_full, 1); mbar_init(dq_free, 128);
+    for (int i = 0; i < NS; ++i) { mbar_init(k_full(i), 1); mbar_init(k_empty(i), 1); mbar_init(v_full(i), 1); mbar_init(v_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(sdp_full(i), 1); mbar_init(sdp_free(i), 128); mbar_init(ds_full(i), 128); mbar_init(ds_empty(i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
+  const int total = g.B * g.H;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t bc = 0, tc = 0;                       // key-block counter, tile counter
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / g.H, col0 = (w % g.H) * D;
+        for (int t = 0; t < g.n_t; ++t, ++tc) {
+          mbar_wait(q_free, (tc & 1u) ^ 1u);           // the previous tile's dQ store has read the staging tile (= the Q tile)
+          mbar_wait(do_empty, (tc & 1u) ^ 1u);
+          mbar_expect_tx(qdo_full, 2 * DC * QCH);
+#pragma unroll
+          for (int c = 0; c < DC; ++c) {
+            tma_load_3d(q_t + c * QCH, &map_q, qdo_full, col0 + 64 * c, t * 128, b);
+            tma_load_3d(do_t + c * QCH, &map_do, qdo_full, col0 + 64 * c, t * 128, b);
+          }
+          for (int kb = 0; kb < g.n_b; ++kb, ++bc) {
+            const int st = bc % NS;
+            const uint32_t par = ((bc / NS) & 1u) ^ 1u;
+            mbar_wait(k_empty(st), par);
+            mbar_expect_tx(k_full(st), DC * BCH);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(kr + (st * DC + c) * BCH, &map_k, k_full(st), col0 + 64 * c, kb * 64, b);
+            mbar_wait(v_empty(st), par);
+            mbar_expect_tx(v_full(st), DC * BCH);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(vr + (st * DC + c) * BCH, &map_v, v_full(st), col0 + 64 * c, kb * 64, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_dq = make_idesc(128, D, 0, 1);            // dQ = dS K : A K-major (dS), B MN-major (K block)
+      uint32_t bc0 = 0, tc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int t = 0; t < g.n_t; ++t, ++tc) {
+          const uint32_t tpar = tc & 1u;
+          mbar_wait(qdo_full, tpar);
+          tc_fence_after();
+          auto issue_dq = [&](int j) {
+            const uint32_t c = bc0 + j;
+            const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * j);
+            mbar_wait(ds_full(buf), (c >> 1) & 1u);
+            if (j == 0) mbar_wait(dq_free, tpar ^ 1u);
+            tc_fence_after();
+            const uint32_t kt = kr + st * DC * BCH, dst = ds_t + buf * QCH;
+            for (int kk = 0; kk < nk / 16; ++kk)
+              tc_mma(tmem + DQ_COL, desc_k(dst + kk * 32u), desc_mn(kt + kk * 2048u, BCH), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(ds_empty(buf));
+            tc_commit(k_empty(st));
+          };
+          for (int j = 0; j < g.n_b; ++j) {
+            const uint32_t c = bc0 + j;
+            const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * j);
+            mbar_wait(k_full(st), (c / NS) & 1u);
+            mbar_wait(v_full(st), (c / NS) & 1u);
+            mbar_wait(sdp_free(buf), ((c >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = kr + st * DC * BCH, vt = vr + st * DC * BCH;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf), kdesc(q_t, QCH, k), kdesc(kt, BCH, k), idesc_s, k > 0);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf + 64), kdesc(do_t, QCH, k), kdesc(vt, BCH, k), idesc_s, k > 0);
+            tc_commit(sdp_full(buf));
+            tc_commit(v_empty(st));
+            if (j > 0) issue_dq(j - 1);
+          }
+          issue_dq(g.n_b - 1);
+          tc_commit(dq_full);
+          tc_commit(do_empty);
+          bc0 += g.n_b;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- thread = query row
+    const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
+    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const bool leader = threadIdx.x == 64;
+    const float sc2 = g.scale * LOG2E;
+    uint32_t bc0 = 0, tc = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int b = w / g.H, h = w % g.H, col0 = h * D;
+      if (MODE == VG_ATTN_L2) {
+        named_bar(2, 128);
+        for (int j = tid; j < g.NK; j += 128)
+          kn[j] = j < g.S ? row_sqnorm<D>(g.k + ((int64_t)b * g.S + j) * g.ld + col0) : 0.f;
+        named_bar(2, 128);
+      }
+      for (int t = 0; t < g.n_t; ++t, ++tc) {
+        const uint32_t tpar = tc & 1u;
+        const int row_g = t * 128 + row;
+        const bool row_on = row_g < g.S;
+        const bool warp_on = t * 128 + quad * 32 < g.S;
+        mbar_wait(qdo_full, tpar);
+        // delta = rowsum(dO * O): dO from the smem tile, O from global (this thread's own row, D contiguous bf16)
+        float delta = 0.f, lse2 = 1e30f, qq = 0.f;
+        if (row_on) {
+          const bf16* orow = g.o + ((int64_t)b * g.S + row_g) * g.ldo + col0;
+#pragma unroll
+          for (int c8 = 0; c8 < D / 8; ++c8) {
+            uint32_t a0, a1, a2, a3;
+            lds128(swz(do_t + (uint32_t)(c8 >> 3) * QCH, row, c8 & 7), a0, a1, a2, a3);
+            const uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow + 8 * c8));
+            delta = fmaf(bf16_lo(a0), bf16_lo(ov.x), delta); delta = fmaf(bf16_hi(a0), bf16_hi(ov.x), delta);
+            delta = fmaf(bf16_lo(a1), bf16_lo(ov.y), delta); delta = fmaf(bf16_hi(a1), bf16_hi(ov.y), delta);
+            delta = fmaf(bf16_lo(a2), bf16_lo(ov.z), delta); delta = fmaf(bf16_hi(a2), bf16_hi(ov.z), delta);
+            delta = fmaf(bf16_lo(a3), bf16_lo(ov.w), delta); delta = fmaf(bf16_hi(a3), bf16_hi(ov.w), delta);
+          }
+          g.delta[(int64_t)w * g.S + row_g] = delta;
+          lse2 = __ldg(g.lse + (int64_t)w * g.S + row_g) * LOG2E;
+          if (MODE == VG_ATTN_L2) qq = row_sqnorm<D>(g.q + ((int64_t)b * g.S + row_g) * g.ld + col0);
+        }
+        float gsum = 0.f;
+        for (int j = 0; j < g.n_b; ++j) {
+          const uint32_t c = bc0 + j;
+          const int buf = c & 1, nk = min(64, g.NK - 64 * j);
+          mbar_wait(sdp_full(buf), (c >> 1) & 1u);
+          tc_fence_after();
+          mbar_wait(ds_empty(buf), ((c >> 1) & 1u) ^ 1u);           // dQ MMA of block j-2 has consumed this dS buffer
+          if (warp_on) {
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {
+              if (cc >= nk) break;
+              uint32_t sv[32], dv[32];
+              const int n = min(32, nk - cc), c0 = 64 * j + cc;
+              if (n >= 32) { tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + cc), sv); tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + 64 + cc), dv); }
+              else { tmem_ld16p(t_lane + (uint32_t)(128 * buf + cc), sv); tmem_ld16p(t_lane + (uint32_t)(128 * buf + 64 + cc), dv); }
+              tmem_ld_wait();
+              uint32_t pk[16];
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                float d2[2] = {0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int x = 2 * jj + e;
+                  if (x < n && c0 + x < g.S) {
+                    float s = __uint_as_float(sv[x]);
+                    float f = g.scale;
+                    if (MODE == VG_ATTN_L2) {
+                      s = sqrtf(fmaxf(fmaf(-2.f, s, qq + kn[c0 + x]), 0.f));
+                      f = s > 0.f ? __fdividef(g.scale, s) : 0.f;
+                    }
+                    const float p = ex2a(fmaf(s, sc2, -lse2));
+                    d2[e] = p * (__uint_as_float(dv[x]) - delta) * f;
+                  }
+                }
+                pk[jj] = pack_bf16(d2[0], d2[1]);
+                if (MODE == VG_ATTN_L2) gsum += bf16_lo(pk[jj]) + bf16_hi(pk[jj]);
+              }
+              const uint32_t tile = ds_t + buf * QCH;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (8 * i < n) sts128(swz(tile, row, (cc >> 3) + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(sdp_free(buf));
+          fence_async_smem();
+          mbar_arrive(ds_full(buf));
+        }
+        bc0 += g.n_b;
+        // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> staging over the Q tile -> TMA store
+        mbar_wait(dq_full, tpar);                       // every MMA of the tile is complete: Q tile no longer read
+        tc_fence_after();
+        float qrow[MODE == VG_ATTN_L2 ? D : 1];
+        if (MODE == VG_ATTN_L2) {
+          if (warp_on) read_tile_row<D>(q_t, QCH, row, qrow);
+          named_bar(1, 128);                            // staging sub-tiles do not coincide with the operand chunks
+        }
+        if (warp_on) {
+#pragma unroll
+          for (int c = 0; c < D; c += 32) {
+            uint32_t v[32];
+            const int n = (D - c) >= 32 ? 32 : 16;
+            tmem_ldn(t_lane + (uint32_t)(DQ_COL + c), v, n);
+            float o[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              o[jj] = __uint_as_float(v[jj]);
+              if (MODE == VG_ATTN_L2 && jj < n) o[jj] = fmaf(gsum, qrow[(c + jj) < D ? (c + jj) : 0], -o[jj]);
+            }
+            stg_write<D>(q_t, row, c, o, n);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(dq_free);
+        fence_async_smem();
+        named_bar(1, 128);
+        if (leader) {
+          stg_store<D>(map_dq, q_t, col0, t * 128, b);
+          tma_commit();
+          tma_wait_read();
+          mbar_arrive(q_free);
+        }
+      }
+    }
+    if (leader) tma_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_free512(tmem); }
+}
+
+// ================================================================================================ backward: dK, dV
+template <int D> struct DkvCfg {
+  static constexpr int DC = (D + 63) / 64, KS = D / 16;
+  static constexpr int NS = D > 128 ? 2 : 3;                 // ring stages of one (Q block, dO block) pair
+  static constexpr int DK_COL = 128, DV_COL = 128 + D;       // S^T/dP^T buffers in columns [0, 64) and [64, 128)
+  static constexpr int K_OFF = 0, V_OFF = DC * QCH, QR_OFF = 2 * DC * QCH, DOR_OFF = QR_OFF + NS * DC * BCH;
+  static constexpr int PT_OFF = DOR_OFF + NS * DC * BCH, DST_OFF = PT_OFF + QCH;
+  static constexpr int LSE_OFF = DST_OFF + QCH, DEL_OFF = LSE_OFF + MAXNK * 4, QN_OFF = DEL_OFF + MAXNK * 4;
+  static constexpr int NBAR = 8 + 2 * NS + 6;
+  static constexpr int smem(int mode) { return (mode == VG_ATTN_L2 ? QN_OFF + MAXNK * 4 : QN_OFF) + NBAR * 8 + 16; }
+};
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                       const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                       const __grid_constant__ OutMaps map_dk, const __grid_constant__ OutMaps map_dv, const MtGeo g) {
+  using C = DkvCfg<D>;
+  constexpr int DC = C::DC, KS = C::KS, NS = C::NS, DK_COL = C::DK_COL, DV_COL = C::DV_COL;
+  constexpr int BAR_OFF = MODE == VG_ATTN_L2 ? C::QN_OFF + MAXNK * 4 : C::QN_OFF;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t base = smem_u32(smem_dyn);
+  const uint32_t k_t = base + C::K_OFF, v_t = base + C::V_OFF, qr = base + C::QR_OFF, dor = base + C::DOR_OFF;
+  const uint32_t pt_t = base + C::PT_OFF, dst_t = base + C::DST_OFF, bar = base + BAR_OFF;
+  float* lse_s = reinterpret_cast<float*>(smem_dyn + C::LSE_OFF);
+  float* del_s = reinterpret_cast<float*>(smem_dyn + C::DEL_OFF);
+  float* qn_s = reinterpret_cast<float*>(smem_dyn + C::QN_OFF);      // L2 mode only
+  const uint32_t kvt_full = bar, kvt_free = bar + 8, out_full = bar + 16, out_free = bar + 24;
+  const uint32_t pt_full = bar + 32, pt_empty = bar + 40, dst_full = bar + 48, dst_empty = bar + 56;
+  auto qdo_full = [&](int i) { return bar + 8u * (8 + i); };
+  auto qdo_empty = [&](int i) { return bar + 8u * (8 + NS + i); };
+  auto st_full = [&](int i) { return bar + 8u * (8 + 2 * NS + i); };
+  auto st_free = [&](int i) { return bar + 8u * (10 + 2 * NS + i); };
+  auto dpt_full = [&](int i) { return bar + 8u * (12 + 2 * NS + i); };
+  const uint32_t tmem_slot = bar + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + BAR_OFF + 8 * C::NBAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) { printf("attention_mt: dynamic smem base not 1024-aligned\n"); __trap(); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
+    mbar_init(kvt_full, 1); mbar_init(kvt_free, 1); mbar_init(out_full, 1); mbar_init(out_free, 128);
+    mbar_init(pt_full, 128); mbar_init(pt_empty, 1); mbar_init(dst_full, 128); mbar_init(dst_empty, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(qdo_full(i), 1); mbar_init(qdo_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(st_full(i), 1); mbar_init(st_free(i), 128); mbar_init(dpt_full(i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
+  const int total = g.B * g.H;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t bc = 0, ic = 0;                       // query-block counter, item (key tile) counter
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / g.H, col0 = (w % g.H) * D;
+        for (int t = 0; t < g.n_t; ++t, ++ic) {
+          mbar_wait(kvt_free, (ic & 1u) ^ 1u);         // previous item's dK/dV stores have read the staging (= the K, V tiles)
+          mbar_expect_tx(kvt_full, 2 * DC * QCH);
+#pragma unroll
+          for (int c = 0; c < DC; ++c) {
+            tma_load_3d(k_t + c * QCH, &map_k, kvt_full, col0 + 64 * c, t * 128, b);
+            tma_load_3d(v_t + c * QCH, &map_v, kvt_full, col0 + 64 * c, t * 128, b);
+          }
+          for (int i = 0; i < g.n_b; ++i, ++bc) {
+            const int st = bc % NS;
+            mbar_wait(qdo_empty(st), ((bc / NS) & 1u) ^ 1u);
+            mbar_expect_tx(qdo_full(st), 2 * DC * BCH);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) {
+              tma_load_3d(qr + (st * DC + c) * BCH, &map_q, qdo_full(st), col0 + 64 * c, i * 64, b);
+              tma_load_3d(dor + (st * DC + c) * BCH, &map_do, qdo_full(st), col0 + 64 * c, i * 64, b);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_kv = make_idesc(128, D, 0, 1);            // dV = P^T dO, dK = dS^T Q : A K-major, B MN-major
+      uint32_t bc0 = 0, ic = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int t = 0; t < g.n_t; ++t, ++ic) {
+          const uint32_t ipar = ic & 1u;
+          mbar_wait(kvt_full, ipar);
+          tc_fence_after();
+          auto issue_st = [&](int i) {                                // S^T[:, block i] = K_tile Q_i^T
+            const uint32_t c = bc0 + i;
+            const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * i);
+            mbar_wait(qdo_full(st), (c / NS) & 1u);
+            mbar_wait(st_free(buf), ((c >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t idesc_s = make_idesc(128, ni, 0, 0), qt = qr + st * DC * BCH;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(k_t, QCH, k), kdesc(qt, BCH, k), idesc_s, k > 0);
+            tc_commit(st_full(buf));
+          };
+          issue_st(0);
+          for (int i = 0; i < g.n_b; ++i) {
+            if (i + 1 < g.n_b) issue_st(i + 1);
+            const uint32_t c = bc0 + i;
+            const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * i);
+            const uint32_t qt = qr + st * DC * BCH, dot = dor + st * DC * BCH, idesc_s = make_idesc(128, ni, 0, 0);
+            mbar_wait(pt_full, c & 1u);                               // P^T in smem; S^T of this block fully read from TMEM
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(v_t, QCH, k), kdesc(dot, BCH, k), idesc_s, k > 0);
+            tc_commit(dpt_full(buf));
+            if (i == 0) { mbar_wait(out_free, ipar ^ 1u); tc_fence_after(); }
+            for (int kk = 0; kk < ni / 16; ++kk)
+              tc_mma(tmem + DV_COL, desc_k(pt_t + kk * 32u), desc_mn(dot + kk * 2048u, BCH), idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(pt_empty);
+            mbar_wait(dst_full, c & 1u);
+            tc_fence_after();
+            for (int kk = 0; kk < ni / 16; ++kk)
+              tc_mma(tmem + DK_COL, desc_k(dst_t + kk * 32u), desc_mn(qt + kk * 2048u, BCH), idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(dst_empty);
+            tc_commit(qdo_empty(st));
+          }
+          tc_commit(out_full);
+          bc0 += g.n_b;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- thread = key row
+    const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
+    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const bool leader = threadIdx.x == 64;
+    const float sc2 = g.scale * LOG2E;
+    uint32_t bc0 = 0, ic = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int b = w / g.H, h = w % g.H, col0 = h * D;
+      // per-query statistics of this problem -> smem: lse * log2e (+huge for padding queries: P = 0), delta, (L2) |q|^2
+      named_bar(2, 128);
+      for (int q = tid; q < g.n_b * 64 && q < MAXNK; q += 128) {
+        const bool on = q < g.S;
+        lse_s[q] = on ? __ldg(g.lse + (int64_t)w * g.S + q) * LOG2E : 1e30f;
+        del_s[q] = on ? __ldg(g.delta + (int64_t)w * g.S + q) : 0.f;
+        if (MODE == VG_ATTN_L2) qn_s[q] = on ? row_sqnorm<D>(g.q + ((int64_t)b * g.S + q) * g.ld + col0) : 0.f;
+      }
+      named_bar(2, 128);
+      for (int t = 0; t < g.n_t; ++t, ++ic) {
+        const uint32_t ipar = ic & 1u;
+        const int key_g = t * 128 + row;
+        const bool warp_on = t * 128 + quad * 32 < g.S;
+        float kk2 = 0.f, gsum = 0.f;
+        if (MODE == VG_ATTN_L2 && key_g < g.S) kk2 = row_sqnorm<D>(g.k + ((int64_t)b * g.S + key_g) * g.ld + col0);
+        for (int i = 0; i < g.n_b; ++i) {
+          const uint32_t c = bc0 + i;
+          const int buf = c & 1, ni = min(64, g.NK - 64 * i);
+          uint32_t f[32];                               // P * scale (dot) or P * scale / dist (L2) of this key row, packed bf16
+          // stage A: S^T -> P^T (smem, A operand of dV) and the factor f kept in registers
+          mbar_wait(st_full(buf), (c >> 1) & 1u);
+          tc_fence_after();
+          mbar_wait(pt_empty, (c & 1u) ^ 1u);             // dV MMA of the previous block has consumed the P^T buffer
+          if (warp_on) {
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {
+              if (cc >= ni) break;
+              uint32_t sv[32];
+              const int n = min(32, ni - cc), q0 = 64 * i + cc;
+              tmem_ldn(t_lane + (uint32_t)(64 * buf + cc), sv, n);
+              uint32_t pk[16];
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                float p2[2] = {0.f, 0.f}, f2[2] = {0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int x = 2 * jj + e;
+                  if (x < n) {
+                    float s = __uint_as_float(sv[x]);
+                    float fs = g.scale;
+                    if (MODE == VG_ATTN_L2) {
+                      s = sqrtf(fmaxf(fmaf(-2.f, s, kk2 + qn_s[q0 + x]), 0.f));
+                      fs = s > 0.f ? __fdividef(g.scale, s) : 0.f;
+                    }
+                    p2[e] = ex2a(fmaf(s, sc2, -lse_s[q0 + x]));
+                    f2[e] = p2[e] * fs;
+                  }
+                }
+                pk[jj] = pack_bf16(p2[0], p2[1]);
+                f[(cc >> 1) + jj] = pack_bf16(f2[0], f2[1]);
+              }
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii)
+                if (8 * ii < n) sts128(swz(pt_t, row, (cc >> 3) + ii), pk[4 * ii], pk[4 * ii + 1], pk[4 * ii + 2], pk[4 * ii + 3]);
+            }
+          }
+          tc_fence_before();
+          fence_async_smem();
+          mbar_arrive(pt_full);
+          // stage B: dP^T -> dS^T = f (dP^T - delta) -> smem (A operand of dK)
+          mbar_wait(dpt_full(buf), (c >> 1) & 1u);
+          tc_fence_after();
+          mbar_wait(dst_empty, (c & 1u) ^ 1u);
+          if (warp_on) {
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {
+              if (cc >= ni) break;
+              uint32_t dv[32];
+              const int n = min(32, ni - cc), q0 = 64 * i + cc;
+              tmem_ldn(t_lane + (uint32_t)(64 * buf + cc), dv, n);
+              uint32_t pk[16];
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                float d0 = 0.f, d1 = 0.f;
+                if (2 * jj < n) {
+                  const uint32_t ff = f[(cc >> 1) + jj];
+                  d0 = bf16_lo(ff) * (__uint_as_float(dv[2 * jj]) - del_s[q0 + 2 * jj]);
+                  d1 = bf16_hi(ff) * (__uint_as_float(dv[2 * jj + 1]) - del_s[q0 + 2 * jj + 1]);
+                }
+                pk[jj] = pack_bf16(d0, d1);
+                if (MODE == VG_ATTN_L2) gsum += bf16_lo(pk[jj]) + bf16_hi(pk[jj]);
+              }
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii)
+                if (8 * ii < n) sts128(swz(dst_t, row, (cc >> 3) + ii), pk[4 * ii], pk[4 * ii + 1], pk[4 * ii + 2], pk[4 * ii + 3]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(st_free(buf));
+          fence_async_smem();
+          mbar_arrive(dst_full);
+        }
+        bc0 += g.n_b;
+        // ---- drain dK, dV: TMEM -> (L2: colsum(G) k - G^T Q) -> bf16 -> staging over the K and V tiles -> TMA stores
+        mbar_wait(out_full, ipar);
+        tc_fence_after();
+        float krow[MODE == VG_ATTN_L2 ? D : 1];
+        if (MODE == VG_ATTN_L2) {
+          if (warp_on) read_tile_row<D>(k_t, QCH, row, krow);
+          named_bar(1, 128);
+        }
+        if (warp_on) {
+#pragma unroll
+          for (int c = 0; c < D; c += 32) {
+            uint32_t v[32];
+            const int n = (D - c) >= 32 ? 32 : 16;
+            tmem_ldn(t_lane + (uint32_t)(DK_COL + c), v, n);
+            float o[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              o[jj] = __uint_as_float(v[jj]);
+              if (MODE == VG_ATTN_L2 && jj < n) o[jj] = fmaf(gsum, krow[(c + jj) < D ? (c + jj) : 0], -o[jj]);
+            }
+            stg_write<D>(k_t, row, c, o, n);
+          }
+#pragma unroll
+          for (int c = 0; c < D; c += 32) {
+            uint32_t v[32];
+            const int n = (D - c) >= 32 ? 32 : 16;
+            tmem_ldn(t_lane + (uint32_t)(DV_COL + c), v, n);
+            float o[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(v[jj]);
+            stg_write<D>(v_t, row, c, o, n);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(out_free);
+        fence_async_smem();
+        named_bar(1, 128);
+        if (leader) {
+          stg_store<D>(map_dk, k_t, col0, t * 128, b);
+          stg_store<D>(map_dv, v_t, col0, t * 128, b);
+          tma_commit();
+          tma_wait_read();
+          mbar_arrive(kvt_free);
+        }
+      }
+    }
+    if (leader) tma_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_free512(tmem); }
+}
+
+// ================================================================================================ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return (EncodeTiledFn) nullptr;
+  }();
+  return fn;
+}
+// bf16 tensor viewed as [B, S, cols] with row pitch ld elements; box {box_cols, box_rows, 1}; swizzle span = box_cols * 2 bytes
+int make_map(CUtensorMap* map, const void* ptr, int B, int S, int cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VG_REQUIRE(enc != nullptr, VG_ERR_LAUNCH, "attention_mt: cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)S * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_REQUIRE(r == CUDA_SUCCESS, VG_ERR_LAUNCH, "attention_mt: cuTensorMapEncodeTiled failed (%d) B=%d S=%d cols=%d ld=%lld box=%dx%d", (int)r, B, S,
+             cols, (long long)ld, box_cols, box_rows);
+  return VG_OK;
+}
+int make_out_maps(OutMaps* m, const void* ptr, int B, int S, int cols, int64_t ld, int d) {
+  int rc;
+  memset(m, 0, sizeof(*m));
+  if (d >= 64 && (rc = make_map(&m->m64, ptr, B, S, cols, ld, 64, 128))) return rc;
+  if ((d % 64) >= 32 && (rc = make_map(&m->m32, ptr, B, S, cols, ld, 32, 128))) return rc;
+  if ((d % 32) >= 16 && (rc = make_map(&m->m16, ptr, B, S, cols, ld, 16, 128))) return rc;
+  return VG_OK;
+}
+
+MtGeo make_geo(int B, int H, int S, int64_t ld, int64_t ldo, float scale, const void* q, const void* k, const void* o, float* lse, float* delta) {
+  MtGeo g;
+  g.B = B; g.H = H; g.S = S; g.NK = (S + 15) / 16 * 16; g.n_t = (S + 127) / 128; g.n_b = (g.NK + 63) / 64; g.ld = ld; g.ldo = ldo;
+  g.scale = scale; g.lse = lse; g.delta = delta;
+  g.q = static_cast<const bf16*>(q); g.k = static_cast<const bf16*>(k); g.o = static_cast<const bf16*>(o);
+  return g;
+}
+
+template <typename K>
+int set_smem_once(K kern, int bytes, bool* done) {
+  if (!*done) {
+    VG_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess, VG_ERR_LAUNCH,
+               "attention_mt: cudaFuncSetAttribute(%d B) failed", bytes);
+    *done = true;
+  }
+  return VG_OK;
+}
+
+template <int D, int MODE>
+int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const OutMaps& mo, const MtGeo& g, cudaStream_t st) {
+  static bool set = false;
+  int rc = set_smem_once(attn_fwd_mt_kernel<D, MODE>, FwdCfg<D>::SMEM, &set);
+  if (rc) return rc;
+  const int grid = min(g.B * g.H, num_sms());
+  launch_pdl(attn_fwd_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)FwdCfg<D>::SMEM, st, mq, mk, mv, mo, g);
+  return check_launch("attention_fwd_mt");
+}
+template <int D, int MODE>
+int launch_bwd(const CUtensorMap& mq128, const CUtensorMap& mdo128, const CUtensorMap& mk64, const CUtensorMap& mv64, const OutMaps& mdq,
+               const CUtensorMap& mk128, const CUtensorMap& mv128, const CUtensorMap& mq64, const CUtensorMap& mdo64, const OutMaps& mdk,
+               const OutMaps& mdv, const MtGeo& g, cudaStream_t st) {
+  static bool set1 = false, set2 = false;
+  int rc = set_smem_once(attn_bwd_dq_mt_kernel<D, MODE>, DqCfg<D>::SMEM, &set1);
+  if (rc) return rc;
+  rc = set_smem_once(attn_bwd_dkv_mt_kernel<D, MODE>, DkvCfg<D>::smem(MODE), &set2);
+  if (rc) return rc;
+  const int grid = min(g.B * g.H, num_sms());
+  launch_pdl(attn_bwd_dq_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DqCfg<D>::SMEM, st, mq128, mdo128, mk64, mv64, mdq, g);
+  rc = check_launch("attention_bwd_dq_mt");
+  if (rc) return rc;
+  launch_pdl(attn_bwd_dkv_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DkvCfg<D>::smem(MODE), st, mk128, mv128, mq64, mdo64, mdk, mdv, g);
+  return check_launch("attention_bwd_dkv_mt");
+}
+
+#define VG_MT_DISPATCH(d_, mode_, CALL)                                                                            \
+  do {                                                                                                             \
+    if (mode_ == VG_ATTN_L2) {                                                                                     \
+      constexpr int MODE = VG_ATTN_L2;                                                                             \
+      if (d_ == 96) { constexpr int D = 96; CALL; } else { constexpr int D = 112; CALL; }                          \
+    } else {                                                                                                       \
+      constexpr int MODE = VG_ATTN_DOT;                                                                            \
+      if (d_ == 96) { constexpr int D = 96; CALL; } else if (d_ == 112) { constexpr int D = 112; CALL; } else { constexpr int D = 192; CALL; } \
+    }                                                                                                              \
+  } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// d = 192 with L2 scores is not instantiated: the dK/dV kernel's smem budget has no room for the |q|^2 table, and no
+// reference configuration uses it (v1's L2 heads are 108 -> 112 wide).
+bool attention_mt_supported(int dtype, int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v,
+                            int64_t ld_qkv, const void* o, int64_t ld_o) {
+  static const int sm100 = vg_device_is_sm100();
+  static const int forced_off = [] { const char* e = getenv("VG_ATTN_PATH"); return (e && !strcmp(e, "simt")) ? 1 : 0; }();
+  if (!sm100 || forced_off) return false;
+  if (dtype != VG_BF16) return false;
+  if (!(d == 96 || d == 112 || (d == 192 && mode == VG_ATTN_DOT))) return false;
+  if (S < 1 || S > MAXNK || B < 1 || H < 1) return false;
+  if (ld_qkv % 8 || ld_o % 8) return false;
+  return aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o);
+}
+
+int attention_fwd_mt(int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                     float* lse, float scale, cudaStream_t st) {
+  const int cols = H * d;
+  CUtensorMap mq, mk, mv;
+  OutMaps mo;
+  int rc;
+  if ((rc = make_map(&mq, q, B, S, cols, ld, 64, 128))) return rc;
+  if ((rc = make_map(&mk, k, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_map(&mv, v, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_out_maps(&mo, o, B, S, cols, ldo, d))) return rc;
+  const MtGeo g = make_geo(B, H, S, ld, ldo, scale, q, k, o, lse, nullptr);
+  VG_MT_DISPATCH(d, mode, (rc = launch_fwd<D, MODE>(mq, mk, mv, mo, g, st)));
+  return rc;
+}
+
+int attention_bwd_mt(int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, const void* o,
+                     const void* d_o, int64_t ldo, const float* lse, void* dq, void* dk, void* dv, int64_t ldd, float scale, float* delta,
+                     cudaStream_t st) {
+  const int cols = H * d;
+  CUtensorMap mq128, mdo128, mk64, mv64, mk128, mv128, mq64, mdo64;
+  OutMaps mdq, mdk, mdv;
+  int rc;
+  if ((rc = make_map(&mq128, q, B, S, cols, ld, 64, 128))) return rc;
+  if ((rc = make_map(&mdo128, d_o, B, S, cols, ldo, 64, 128))) return rc;
+  if ((rc = make_map(&mk64, k, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_map(&mv64, v, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_map(&mk128, k, B, S, cols, ld, 64, 128))) return rc;
+  if ((rc = make_map(&mv128, v, B, S, cols, ld, 64, 128))) return rc;
+  if ((rc = make_map(&mq64, q, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_map(&mdo64, d_o, B, S, cols, ldo, 64, 64))) return rc;
+  if ((rc = make_out_maps(&mdq, dq, B, S, cols, ldd, d))) return rc;
+  if ((rc = make_out_maps(&mdk, dk, B, S, cols, ldd, d))) return rc;
+  if ((rc = make_out_maps(&mdv, dv, B, S, cols, ldd, d))) return rc;
+  const MtGeo g = make_geo(B, H, S, ld, ldo, scale, q, k, o, const_cast<float*>(lse), delta);
+  VG_MT_DISPATCH(d, mode, (rc = launch_bwd<D, MODE>(mq128, mdo128, mk64, mv64, mdq, mk128, mv128, mq64, mdo64, mdk, mdv, g, st)));
+  return rc;
+}
+
+}  // namespace vg
