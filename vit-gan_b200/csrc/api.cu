@@ -79,6 +79,11 @@ extern "C" int vg_gemm(const vg_gemm_args* args, void* stream) {
   return ok ? gemm_tc_launch(a, st) : gemm_simt_launch(a, st);
 }
 
+namespace vg { void attention_mt_set_trace(unsigned long long* p); }
+extern "C" int vg_attention_set_trace(void* buffer) {
+  vg::attention_mt_set_trace(static_cast<unsigned long long*>(buffer));
+  return VG_OK;
+}
 extern "C" int vg_gemm_set_trace(void* buffer) {
   gemm_tc_set_trace(static_cast<unsigned long long*>(buffer));
   return VG_OK;

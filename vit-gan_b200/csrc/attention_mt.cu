@@ -54,6 +54,20 @@ struct MtGeo {
   float* lse;               // [B, H, S]
   float* delta;             // [B, H, S]
   const bf16 *q, *k, *o;
+  unsigned long long* trace;   // bring-up timeline of CTA 0 (vg_attention_set_trace) or NULL
+};
+
+// timeline of CTA 0: per role (0 producer, 1 MMA issuer, 2 compute leader) up to 512 (code, %globaltimer) pairs
+struct Tracer {
+  unsigned long long* p; int n;
+  __device__ __forceinline__ Tracer(unsigned long long* base, int role) : p(base && blockIdx.x == 0 ? base + role * 1024 : nullptr), n(0) {}
+  __device__ __forceinline__ void operator()(int code) {
+    if (p && n < 512) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      p[2 * n] = (unsigned long long)code; p[2 * n + 1] = t; ++n;
+    }
+  }
 };
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -134,6 +148,102 @@ __device__ __forceinline__ uint64_t kdesc(uint32_t tile, uint32_t chunk_bytes, i
   return desc_k(tile + (uint32_t)(k >> 2) * chunk_bytes + (uint32_t)(k & 3) * 32u);
 }
 
+__device__ __forceinline__ float sqrta(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// raw accumulator value -> score: the dot product itself, or the distance sqrt(max(0, |q|^2 + |k|^2 - 2 q.k)) (nn = |q|^2 + |k|^2)
+template <int MODE> __device__ __forceinline__ float score_of(float dot, float nn) {
+  return MODE == VG_ATTN_L2 ? sqrta(fmaxf(fmaf(-2.f, dot, nn), 0.f)) : dot;
+}
+
+// The compute warps run ONE warp per scheduler, so nothing hides instruction latency: the per-element loops below are
+// straight-line for a compile-time column count N (no per-element branches; MASK only for the group that crosses S) and keep
+// four independent accumulator chains.
+// forward pass 1: running row maximum over N accumulator columns starting at key c
+template <int N, bool MASK, int MODE>
+__device__ __forceinline__ void fwd_max(const uint32_t (&v)[32], int c, int S, float qq, const float* kn, float (&m)[4]) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float s = score_of<MODE>(__uint_as_float(v[j]), MODE == VG_ATTN_L2 ? qq + kn[c + j] : 0.f);
+    if (!MASK || c + j < S) m[j & 3] = fmaxf(m[j & 3], s);
+  }
+}
+// forward pass 2: p = exp2(s * sc2 - mb) for N columns, row sum, packed bf16
+template <int N, bool MASK, int MODE>
+__device__ __forceinline__ void fwd_exp(const uint32_t (&v)[32], int c, int S, float qq, const float* kn, float sc2, float mb, float (&l)[4],
+                                        uint32_t (&pk)[16]) {
+  float p[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float s = score_of<MODE>(__uint_as_float(v[j]), MODE == VG_ATTN_L2 ? qq + kn[c + j] : 0.f);
+    p[j] = ex2a(fmaf(s, sc2, -mb));
+    if (MASK && c + j >= S) p[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) l[j & 3] += p[j];
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) pk[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+}
+// backward (q-major): dS (dot) or G (L2) = P (dP - delta) scale [/ dist] for N columns, packed bf16; gsum += row sum (L2)
+template <int N, bool MASK, int MODE>
+__device__ __forceinline__ void dq_group(const uint32_t (&sv)[32], const uint32_t (&dv)[32], int c, int S, float qq, const float* kn, float sc2,
+                                         float lse2, float delta, float scale, float& gsum, uint32_t (&pk)[16]) {
+  float d[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float s = score_of<MODE>(__uint_as_float(sv[j]), MODE == VG_ATTN_L2 ? qq + kn[c + j] : 0.f);
+    float f = scale;
+    if (MODE == VG_ATTN_L2) f = s > 0.f ? scale * rcpa(s) : 0.f;
+    d[j] = ex2a(fmaf(s, sc2, -lse2)) * (__uint_as_float(dv[j]) - delta) * f;
+    if (MASK && c + j >= S) d[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) pk[j] = pack_bf16(d[2 * j], d[2 * j + 1]);
+  if (MODE == VG_ATTN_L2) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) { a[j & 3] += bf16_lo(pk[j]); a[(j + 2) & 3] += bf16_hi(pk[j]); }
+    gsum += (a[0] + a[1]) + (a[2] + a[3]);
+  }
+}
+// backward (key-major) stage A: P^T (packed bf16 -> pk) and the factor f = P scale [/ dist] (packed bf16 -> f) for N query columns
+template <int N, int MODE>
+__device__ __forceinline__ void dkv_stage_a(const uint32_t (&sv)[32], int q0, float kk2, const float* qn_s, const float* lse_s, float sc2, float scale,
+                                            uint32_t (&pk)[16], uint32_t* f) {
+  float p[N], ff[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float s = score_of<MODE>(__uint_as_float(sv[j]), MODE == VG_ATTN_L2 ? kk2 + qn_s[q0 + j] : 0.f);
+    float fs = scale;
+    if (MODE == VG_ATTN_L2) fs = s > 0.f ? scale * rcpa(s) : 0.f;
+    p[j] = ex2a(fmaf(s, sc2, -lse_s[q0 + j]));
+    ff[j] = p[j] * fs;
+  }
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) { pk[j] = pack_bf16(p[2 * j], p[2 * j + 1]); f[j] = pack_bf16(ff[2 * j], ff[2 * j + 1]); }
+}
+// stage B: dS^T = f (dP^T - delta[q]) for N query columns, packed bf16; gsum += row sum (L2)
+template <int N, int MODE>
+__device__ __forceinline__ void dkv_stage_b(const uint32_t (&dv)[32], int q0, const float* del_s, const uint32_t* f, float& gsum, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const float d0 = bf16_lo(f[j]) * (__uint_as_float(dv[2 * j]) - del_s[q0 + 2 * j]);
+    const float d1 = bf16_hi(f[j]) * (__uint_as_float(dv[2 * j + 1]) - del_s[q0 + 2 * j + 1]);
+    pk[j] = pack_bf16(d0, d1);
+  }
+  if (MODE == VG_ATTN_L2) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) { a[j & 3] += bf16_lo(pk[j]); a[(j + 2) & 3] += bf16_hi(pk[j]); }
+    gsum += (a[0] + a[1]) + (a[2] + a[3]);
+  }
+}
+// n / 8 16-byte chunks of packed bf16 -> row `row` of a K-major [128 x 64] SW128 tile, starting at column c
+template <int N>
+__device__ __forceinline__ void put_row(uint32_t tile, int row, int c, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < N / 8; ++i) sts128(swz(tile, row, (c >> 3) + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
+
 __device__ __forceinline__ void tmem_alloc512(uint32_t slot) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -193,10 +303,12 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       uint32_t rc = 0, tc = 0;                       // ring slot counter, tile counter
+      Tracer tr(g.trace, 0);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           mbar_wait(q_empty, (tc & 1u) ^ 1u);
+          tr(1);
           mbar_expect_tx(q_full, DC * QCH);
 #pragma unroll
           for (int c = 0; c < DC; ++c) tma_load_3d(q_t + c * QCH, &map_q, q_full, col0 + 64 * c, t * 128, b);
@@ -204,6 +316,7 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int kb = 0; kb < g.n_b; ++kb, ++rc) {
               const int st = rc % NST;
               mbar_wait(kv_empty(st), ((rc / NST) & 1u) ^ 1u);
+              tr(100 + pass * 10 + kb);
               mbar_expect_tx(kv_full(st), DC * BCH);
 #pragma unroll
               for (int c = 0; c < DC; ++c)
@@ -216,15 +329,19 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (lane == 0) {
       const uint32_t idesc_pv = make_idesc(128, D, 0, 1);            // O = P V : A K-major, B MN-major
       uint32_t rc = 0, tc = 0;
+      Tracer tr(g.trace, 1);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           const uint32_t par = tc & 1u;
           mbar_wait(q_full, par);
+          tr(10);
           mbar_wait(s_free, par ^ 1u);
+          tr(11);
           tc_fence_after();
           for (int kb = 0; kb < g.n_b; ++kb, ++rc) {                  // S[:, 64 kb ..] = Q K_kb^T
             const int st = rc % NST, nk = min(64, g.NK - 64 * kb);
             mbar_wait(kv_full(st), (rc / NST) & 1u);
+            tr(20 + kb);
             tc_fence_after();
             const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = ring + st * DC * BCH;
 #pragma unroll
@@ -233,11 +350,15 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           }
           tc_commit(s_full);
           tc_commit(q_empty);
+          tr(12);
           mbar_wait(o_free, par ^ 1u);
+          tr(13);
           for (int kb = 0; kb < g.n_b; ++kb, ++rc) {                  // O += P_kb V_kb
             const int st = rc % NST, nk = min(64, g.NK - 64 * kb);
             mbar_wait(kv_full(st), (rc / NST) & 1u);
+            tr(30 + kb);
             mbar_wait(p_full(kb), par);
+            tr(40 + kb);
             tc_fence_after();
             const uint32_t vt = ring + st * DC * BCH, pt = p_t + kb * QCH;
             for (int kk = 0; kk < nk / 16; ++kk)
@@ -246,6 +367,7 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tc_commit(p_empty(kb));
           }
           tc_commit(o_full);
+          tr(14);
         }
       }
     }
@@ -256,8 +378,10 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const bool leader = threadIdx.x == 64;
     const float sc2 = g.scale * LOG2E;
     uint32_t tc = 0;
+    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 2);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / g.H, h = w % g.H, col0 = h * D;
+      tr(50);
       if (MODE == VG_ATTN_L2) {                       // |k_j|^2 of this problem's keys -> smem (broadcast reads below)
         named_bar(2, 128);
         for (int j = tid; j < g.NK; j += 128)
@@ -270,71 +394,72 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const bool warp_on = t * 128 + quad * 32 < g.S;               // warp-uniform: this warp owns real query rows
         float qq = 0.f;
         if (MODE == VG_ATTN_L2 && row_g < g.S) qq = row_sqnorm<D>(g.q + ((int64_t)b * g.S + row_g) * g.ld + col0);
+        tr(51);
         mbar_wait(s_full, par);
+        tr(52);
         tc_fence_after();
-        float m = -INFINITY, l = 0.f;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, l4[4] = {0.f, 0.f, 0.f, 0.f};
         // pass 1: row maximum of the raw scores (dot) / distances (L2) over the real keys
         if (warp_on) {
           for (int c = 0; c < g.NK; c += 32) {
             uint32_t v[32];
-            const int n = min(32, g.NK - c);
-            tmem_ldn(t_lane + (uint32_t)c, v, n);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < n) {
-                float s = __uint_as_float(v[j]);
-                if (MODE == VG_ATTN_L2) s = sqrtf(fmaxf(fmaf(-2.f, s, qq + kn[c + j]), 0.f));
-                if (c + j < g.S) m = fmaxf(m, s);
-              }
+            if (g.NK - c >= 32) {
+              tmem_ld32(t_lane + (uint32_t)c, v);
+              tr(80);
+              if (c + 32 <= g.S) fwd_max<32, false, MODE>(v, c, g.S, qq, kn, m4); else fwd_max<32, true, MODE>(v, c, g.S, qq, kn, m4);
+            } else {
+              tmem_ld16p(t_lane + (uint32_t)c, v);
+              tmem_ld_wait();
+              if (c + 16 <= g.S) fwd_max<16, false, MODE>(v, c, g.S, qq, kn, m4); else fwd_max<16, true, MODE>(v, c, g.S, qq, kn, m4);
             }
           }
         }
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         // the previous tile's output store must have finished reading the staging tile (it aliases the P chunks)
+        tr(53);
         if (leader) tma_wait_read();
         named_bar(1, 128);
+        tr(54);
         // pass 2: P = exp2((s - m) scale log2e) -> bf16 -> smem, one 64-key chunk at a time (the PV MMAs trail by one chunk)
         const float mb = m * sc2;
         for (int kb = 0; kb < g.n_b; ++kb) {
           mbar_wait(p_empty(kb), par ^ 1u);
+          tr(70);
           if (warp_on) {
             const int nk = min(64, g.NK - 64 * kb);
+            const uint32_t tile = p_t + kb * QCH;
 #pragma unroll
             for (int c = 0; c < 64; c += 32) {
               if (c >= nk) break;
-              uint32_t v[32];
-              const int n = min(32, nk - c), c0 = 64 * kb + c;
-              tmem_ldn(t_lane + (uint32_t)c0, v, n);
-              uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float p0 = 0.f, p1 = 0.f;
-                if (2 * j < n) {
-                  float s0 = __uint_as_float(v[2 * j]), s1 = __uint_as_float(v[2 * j + 1]);
-                  if (MODE == VG_ATTN_L2) {
-                    s0 = sqrtf(fmaxf(fmaf(-2.f, s0, qq + kn[c0 + 2 * j]), 0.f));
-                    s1 = sqrtf(fmaxf(fmaf(-2.f, s1, qq + kn[c0 + 2 * j + 1]), 0.f));
-                  }
-                  p0 = (c0 + 2 * j < g.S) ? ex2a(fmaf(s0, sc2, -mb)) : 0.f;
-                  p1 = (c0 + 2 * j + 1 < g.S) ? ex2a(fmaf(s1, sc2, -mb)) : 0.f;
-                  l += p0 + p1;
-                }
-                pk[j] = pack_bf16(p0, p1);
+              uint32_t v[32], pk[16];
+              const int c0 = 64 * kb + c;
+              if (nk - c >= 32) {
+                tmem_ld32(t_lane + (uint32_t)c0, v);
+                tr(71);
+                if (c0 + 32 <= g.S) fwd_exp<32, false, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk); else fwd_exp<32, true, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk);
+                put_row<32>(tile, row, c, pk);
+              } else {
+                tmem_ld16p(t_lane + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (c0 + 16 <= g.S) fwd_exp<16, false, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk); else fwd_exp<16, true, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk);
+                put_row<16>(tile, row, c, pk);
               }
-              const uint32_t tile = p_t + kb * QCH;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (8 * i < n) sts128(swz(tile, row, (c >> 3) + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              tr(72);
             }
           }
           fence_async_smem();                          // P chunk visible to the tensor-core (async) proxy
+          tr(73);
           mbar_arrive(p_full(kb));
+          tr(60 + kb);
         }
         tc_fence_before();
         mbar_arrive(s_free);                           // S fully read: the next tile's Q K^T may overwrite it
+        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const float inv_l = 1.0f / l;
         if (row_g < g.S) g.lse[(int64_t)w * g.S + row_g] = m * g.scale + __logf(l);
         // ---- drain O: TMEM -> * 1/l -> bf16 -> staging (over the P chunks, all consumed once o_full fires) -> TMA store
         mbar_wait(o_full, par);
+        tr(55);
         tc_fence_after();
         if (warp_on) {
 #pragma unroll
@@ -352,6 +477,7 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         mbar_arrive(o_free);
         fence_async_smem();
         named_bar(1, 128);
+        tr(56);
         if (leader) { stg_store<D>(map_o, p_t, col0, t * 128, b); tma_commit(); }
       }
     }
@@ -538,39 +664,27 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tc_fence_after();
           mbar_wait(ds_empty(buf), ((c >> 1) & 1u) ^ 1u);           // dQ MMA of block j-2 has consumed this dS buffer
           if (warp_on) {
+            const uint32_t tile = ds_t + buf * QCH;
 #pragma unroll
             for (int cc = 0; cc < 64; cc += 32) {
               if (cc >= nk) break;
-              uint32_t sv[32], dv[32];
-              const int n = min(32, nk - cc), c0 = 64 * j + cc;
-              if (n >= 32) { tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + cc), sv); tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + 64 + cc), dv); }
-              else { tmem_ld16p(t_lane + (uint32_t)(128 * buf + cc), sv); tmem_ld16p(t_lane + (uint32_t)(128 * buf + 64 + cc), dv); }
-              tmem_ld_wait();
-              uint32_t pk[16];
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                float d2[2] = {0.f, 0.f};
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int x = 2 * jj + e;
-                  if (x < n && c0 + x < g.S) {
-                    float s = __uint_as_float(sv[x]);
-                    float f = g.scale;
-                    if (MODE == VG_ATTN_L2) {
-                      s = sqrtf(fmaxf(fmaf(-2.f, s, qq + kn[c0 + x]), 0.f));
-                      f = s > 0.f ? __fdividef(g.scale, s) : 0.f;
-                    }
-                    const float p = ex2a(fmaf(s, sc2, -lse2));
-                    d2[e] = p * (__uint_as_float(dv[x]) - delta) * f;
-                  }
-                }
-                pk[jj] = pack_bf16(d2[0], d2[1]);
-                if (MODE == VG_ATTN_L2) gsum += bf16_lo(pk[jj]) + bf16_hi(pk[jj]);
+              uint32_t sv[32], dv[32], pk[16];
+              const int c0 = 64 * j + cc;
+              if (nk - cc >= 32) {
+                tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + cc), sv);
+                tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + 64 + cc), dv);
+                tmem_ld_wait();
+                if (c0 + 32 <= g.S) dq_group<32, false, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+                else dq_group<32, true, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+                put_row<32>(tile, row, cc, pk);
+              } else {
+                tmem_ld16p(t_lane + (uint32_t)(128 * buf + cc), sv);
+                tmem_ld16p(t_lane + (uint32_t)(128 * buf + 64 + cc), dv);
+                tmem_ld_wait();
+                if (c0 + 16 <= g.S) dq_group<16, false, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+                else dq_group<16, true, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+                put_row<16>(tile, row, cc, pk);
               }
-              const uint32_t tile = ds_t + buf * QCH;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (8 * i < n) sts128(swz(tile, row, (cc >> 3) + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
             }
           }
           tc_fence_before();
@@ -789,33 +903,18 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
 #pragma unroll
             for (int cc = 0; cc < 64; cc += 32) {
               if (cc >= ni) break;
-              uint32_t sv[32];
-              const int n = min(32, ni - cc), q0 = 64 * i + cc;
-              tmem_ldn(t_lane + (uint32_t)(64 * buf + cc), sv, n);
-              uint32_t pk[16];
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                float p2[2] = {0.f, 0.f}, f2[2] = {0.f, 0.f};
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int x = 2 * jj + e;
-                  if (x < n) {
-                    float s = __uint_as_float(sv[x]);
-                    float fs = g.scale;
-                    if (MODE == VG_ATTN_L2) {
-                      s = sqrtf(fmaxf(fmaf(-2.f, s, kk2 + qn_s[q0 + x]), 0.f));
-                      fs = s > 0.f ? __fdividef(g.scale, s) : 0.f;
-                    }
-                    p2[e] = ex2a(fmaf(s, sc2, -lse_s[q0 + x]));
-                    f2[e] = p2[e] * fs;
-                  }
-                }
-                pk[jj] = pack_bf16(p2[0], p2[1]);
-                f[(cc >> 1) + jj] = pack_bf16(f2[0], f2[1]);
+              uint32_t sv[32], pk[16];
+              const int q0 = 64 * i + cc;
+              if (ni - cc >= 32) {
+                tmem_ld32(t_lane + (uint32_t)(64 * buf + cc), sv);
+                dkv_stage_a<32, MODE>(sv, q0, kk2, qn_s, lse_s, sc2, g.scale, pk, &f[cc >> 1]);
+                put_row<32>(pt_t, row, cc, pk);
+              } else {
+                tmem_ld16p(t_lane + (uint32_t)(64 * buf + cc), sv);
+                tmem_ld_wait();
+                dkv_stage_a<16, MODE>(sv, q0, kk2, qn_s, lse_s, sc2, g.scale, pk, &f[cc >> 1]);
+                put_row<16>(pt_t, row, cc, pk);
               }
-#pragma unroll
-              for (int ii = 0; ii < 4; ++ii)
-                if (8 * ii < n) sts128(swz(pt_t, row, (cc >> 3) + ii), pk[4 * ii], pk[4 * ii + 1], pk[4 * ii + 2], pk[4 * ii + 3]);
             }
           }
           tc_fence_before();
@@ -829,24 +928,18 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
 #pragma unroll
             for (int cc = 0; cc < 64; cc += 32) {
               if (cc >= ni) break;
-              uint32_t dv[32];
-              const int n = min(32, ni - cc), q0 = 64 * i + cc;
-              tmem_ldn(t_lane + (uint32_t)(64 * buf + cc), dv, n);
-              uint32_t pk[16];
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                float d0 = 0.f, d1 = 0.f;
-                if (2 * jj < n) {
-                  const uint32_t ff = f[(cc >> 1) + jj];
-                  d0 = bf16_lo(ff) * (__uint_as_float(dv[2 * jj]) - del_s[q0 + 2 * jj]);
-                  d1 = bf16_hi(ff) * (__uint_as_float(dv[2 * jj + 1]) - del_s[q0 + 2 * jj + 1]);
-                }
-                pk[jj] = pack_bf16(d0, d1);
-                if (MODE == VG_ATTN_L2) gsum += bf16_lo(pk[jj]) + bf16_hi(pk[jj]);
+              uint32_t dv[32], pk[16];
+              const int q0 = 64 * i + cc;
+              if (ni - cc >= 32) {
+                tmem_ld32(t_lane + (uint32_t)(64 * buf + cc), dv);
+                dkv_stage_b<32, MODE>(dv, q0, del_s, &f[cc >> 1], gsum, pk);
+                put_row<32>(dst_t, row, cc, pk);
+              } else {
+                tmem_ld16p(t_lane + (uint32_t)(64 * buf + cc), dv);
+                tmem_ld_wait();
+                dkv_stage_b<16, MODE>(dv, q0, del_s, &f[cc >> 1], gsum, pk);
+                put_row<16>(dst_t, row, cc, pk);
               }
-#pragma unroll
-              for (int ii = 0; ii < 4; ++ii)
-                if (8 * ii < n) sts128(swz(dst_t, row, (cc >> 3) + ii), pk[4 * ii], pk[4 * ii + 1], pk[4 * ii + 2], pk[4 * ii + 3]);
             }
           }
           tc_fence_before();
@@ -946,8 +1039,11 @@ int make_out_maps(OutMaps* m, const void* ptr, int B, int S, int cols, int64_t l
   return VG_OK;
 }
 
+unsigned long long* g_mt_trace = nullptr;
+
 MtGeo make_geo(int B, int H, int S, int64_t ld, int64_t ldo, float scale, const void* q, const void* k, const void* o, float* lse, float* delta) {
   MtGeo g;
+  g.trace = g_mt_trace;
   g.B = B; g.H = H; g.S = S; g.NK = (S + 15) / 16 * 16; g.n_t = (S + 127) / 128; g.n_b = (g.NK + 63) / 64; g.ld = ld; g.ldo = ldo;
   g.scale = scale; g.lse = lse; g.delta = delta;
   g.q = static_cast<const bf16*>(q); g.k = static_cast<const bf16*>(k); g.o = static_cast<const bf16*>(o);
@@ -1004,6 +1100,8 @@ int launch_bwd(const CUtensorMap& mq128, const CUtensorMap& mdo128, const CUtens
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+void attention_mt_set_trace(unsigned long long* p) { g_mt_trace = p; }
 
 // d = 192 with L2 scores is not instantiated: the dK/dV kernel's smem budget has no room for the |q|^2 table, and no
 // reference configuration uses it (v1's L2 heads are 108 -> 112 wide).

@@ -51,6 +51,7 @@ SIGNATURES = {
     "vg_attention_fwd": [i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, i64, vp, f32, vp],
     "vg_attention_bwd": [i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, i64, f32, vp, vp],
     "vg_attention_path": [i32, i32, i32, i32, i32, i32],
+    "vg_attention_set_trace": [vp],
     "vg_im2col_patches": [i32, i32, i32, i32, i32, vp, vp, vp],
     "vg_col2im_patches": [i32, i32, i32, i32, i32, vp, vp, vp],
     "vg_v1_tokens_fwd": [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
