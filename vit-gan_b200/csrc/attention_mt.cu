@@ -42,6 +42,10 @@ constexpr int BCH = 64 * 128;             // one [64 rows x 64 bf16] swizzled ch
 constexpr int MAXNK = 272;                // S rounded up to 16 must fit the S region of TMEM
 constexpr int MAXKB = 5;                  // ceil(272 / 64)
 constexpr float LOG2E = 1.4426950408889634f;
+#ifndef VG_MT_P_TMEM
+#define VG_MT_P_TMEM 1
+#endif
+constexpr bool P_TMEM = VG_MT_P_TMEM != 0;   // forward: P as the TMEM-resident A operand of O = P V (tcgen05.mma .ts form)
 
 struct OutMaps { CUtensorMap m64, m32, m16; };
 
@@ -361,8 +365,10 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tr(40 + kb);
             tc_fence_after();
             const uint32_t vt = ring + st * DC * BCH, pt = p_t + kb * QCH;
-            for (int kk = 0; kk < nk / 16; ++kk)
-              tc_mma(tmem + O_COL, desc_k(pt + kk * 32u), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < nk / 16; ++kk) {
+              if (P_TMEM) tc_mma_ts(tmem + O_COL, tmem + (uint32_t)(32 * kb + 8 * kk), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
+              else tc_mma(tmem + O_COL, desc_k(pt + kk * 32u), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
+            }
             tc_commit(kv_empty(st));
             tc_commit(p_empty(kb));
           }
@@ -437,17 +443,17 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tmem_ld32(t_lane + (uint32_t)c0, v);
                 tr(71);
                 if (c0 + 32 <= g.S) fwd_exp<32, false, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk); else fwd_exp<32, true, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk);
-                put_row<32>(tile, row, c, pk);
+                if (P_TMEM) tmem_st16(t_lane + (uint32_t)(c0 >> 1), pk); else put_row<32>(tile, row, c, pk);
               } else {
                 tmem_ld16p(t_lane + (uint32_t)c0, v);
                 tmem_ld_wait();
                 if (c0 + 16 <= g.S) fwd_exp<16, false, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk); else fwd_exp<16, true, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk);
-                put_row<16>(tile, row, c, pk);
+                if (P_TMEM) tmem_st8(t_lane + (uint32_t)(c0 >> 1), pk); else put_row<16>(tile, row, c, pk);
               }
               tr(72);
             }
           }
-          fence_async_smem();                          // P chunk visible to the tensor-core (async) proxy
+          if (P_TMEM) { tmem_st_wait(); tc_fence_before(); } else fence_async_smem();   // P chunk visible to the tensor core
           tr(73);
           mbar_arrive(p_full(kb));
           tr(60 + kb);
