@@ -105,6 +105,13 @@ int vg_gemm_set_trace(void* buffer);
 int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
                   const float* num, const float* den, void* stream);
 
+/* n fp32 [rows, cols] tensors, given as a DEVICE array of n pointers, -> dst [n * rows_pad, cols_pad] in dst_dtype: block t is
+ * srcs[t] * num[t] / den[t] (either may be NULL) zero-padded to rows_pad x cols_pad.  One launch packs the 3H per-head q/k/v
+ * weights of a v1 MultiHeadSelfAttention (src/v1/attention.py:46-48, spectral rescale :60-64) into the grouped projection
+ * operand with head widths padded to the tensor-core granularity (108 -> 112); with n = 1 it pads columns (out-proj weight). */
+int vg_pack_pad(const void* const* srcs, int n, int rows, int cols, int rows_pad, int cols_pad, const float* num,
+                const float* den, void* dst, int dst_dtype, void* stream);
+
 /* out[n] += sum_m x[m,n]   (bias gradients; fp32 out, accumulated: zero it first).
  * workspace (optional): persistent ZERO-INITIALISED [ws_rows = R, N] fp32 replicated accumulators + a zero-initialised
  * ticket `counter`: CTA partial sums go to row blockIdx %% R (same-address atomic contention / R), the last CTA folds the R

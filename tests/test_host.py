@@ -25,6 +25,31 @@ def test_library_exports_every_declared_symbol():
     assert L.lib.vg_version() == 4 and L.lib.vg_last_error() is not None
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every ctypes binding has exactly the parameter list of its prototype in include/vitgan_b200.h (count and kind:
+    pointer / 32-bit int / 64-bit int / float).  A missing trailing pointer is passed by ctypes as a C int, i.e. truncated to
+    32 bits -- the stream handle of vg_sln_bwd was lost that way on non-default streams."""
+    import ctypes as C
+    from vitgan_b200 import lib as L
+    hdr = open(os.path.join(ROOT, "include", "vitgan_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|const char\*)\s+(vg_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(L.SIGNATURES)
+
+    def kind(param):
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        base = p.rsplit(" ", 1)[0] if " " in p else p
+        return {"int": "i32", "int64_t": "i64", "float": "f32", "unsigned": "i32"}[base.replace("const ", "")]
+
+    ck = {C.c_int: "i32", C.c_int64: "i64", C.c_float: "f32", C.c_void_p: "ptr", C.c_char_p: "ptr"}
+    for name, params in protos.items():
+        want = [] if params.strip() in ("", "void") else [kind(x) for x in params.split(",")]
+        got = [ck.get(t, "ptr") for t in L.SIGNATURES[name]]
+        assert got == want, (name, got, want)
+
+
 def test_struct_layout_matches_header():
     """sizeof(vg_gemm_args) as compiled == the ctypes mirror (guards against silent ABI drift)."""
     import ctypes

@@ -35,6 +35,30 @@ __global__ void cast_scale_kernel(const TS* __restrict__ src, TD* __restrict__ d
   }
 }
 
+// n fp32 [rows, cols] tensors (device pointer array) -> one [n * rows_pad, cols_pad] tensor of TD, each block scaled by
+// num[t] / den[t] and zero-padded to rows_pad x cols_pad: the grouped q/k/v weight of the v1 heads (src/v1/attention.py:46-48,
+// 60-64 incl. the spectral rescale) with head widths padded to the tensor-core granularity, in ONE launch.
+template <typename TD>
+__global__ void pack_pad_kernel(const float* const* __restrict__ srcs, int n, int rows, int cols, int rows_pad, int cols_pad,
+                                const float* __restrict__ num, const float* __restrict__ den, TD* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t per = (int64_t)rows_pad * cols_pad, total = per * n;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gtid; i < total; i += gsz) {
+    const int t = (int)(i / per);
+    const int64_t rem = i - (int64_t)t * per;
+    const int r = (int)(rem / cols_pad), c = (int)(rem - (int64_t)r * cols_pad);
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = __ldg(srcs[t] + (int64_t)r * cols + c);
+      if (num) v *= __ldg(num + t);
+      if (den) v /= __ldg(den + t);
+    }
+    out[i] = from_f<TD>(v);
+  }
+}
+
 // out[n] += sum_m x[m,n].  Vector version: thread (tx, ty) owns the 16-byte column group tx of the CTA's 32-group slab
 // and the rows m0+ty, m0+ty+8, ...; a warp reads 512 contiguous bytes per row; 4 rows in flight per thread.
 template <typename T>
@@ -260,6 +284,21 @@ extern "C" int vg_cast_scale(const void* src, int src_dtype, void* dst, int dst_
   else
     VG_REQUIRE(false, VG_ERR_ARG, "cast_scale: bad dtypes %d -> %d", src_dtype, dst_dtype);
   return check_launch("cast_scale");
+}
+
+extern "C" int vg_pack_pad(const void* const* srcs, int n, int rows, int cols, int rows_pad, int cols_pad, const float* num,
+                           const float* den, void* dst, int dst_dtype, void* stream) {
+  VG_REQUIRE(n > 0 && rows > 0 && cols > 0 && rows_pad >= rows && cols_pad >= cols, VG_ERR_SHAPE, "pack_pad: bad shape n=%d %dx%d -> %dx%d", n, rows,
+             cols, rows_pad, cols_pad);
+  cudaStream_t st = as_stream(stream);
+  const int grid = grid1d((int64_t)n * rows_pad * cols_pad, 256);
+  if (dst_dtype == VG_BF16)
+    launch_pdl(pack_pad_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const float* const*)srcs, n, rows, cols, rows_pad, cols_pad, num, den, (bf16*)dst);
+  else if (dst_dtype == VG_F32)
+    launch_pdl(pack_pad_kernel<float>, dim3(grid), dim3(256), 0, st, (const float* const*)srcs, n, rows, cols, rows_pad, cols_pad, num, den, (float*)dst);
+  else
+    VG_REQUIRE(false, VG_ERR_ARG, "pack_pad: bad dst dtype %d", dst_dtype);
+  return check_launch("pack_pad");
 }
 
 extern "C" int vg_colsum(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, float* workspace, int ws_rows,

@@ -47,9 +47,10 @@ SIGNATURES = {
     "vg_layernorm_bwd_partials": [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "vg_fold_partials": [vp, i32, i32, vp, vp, vp, vp, vp],
     "vg_sln_fwd": [i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp],
-    "vg_sln_bwd": [i32, i64, i64, i32] + [vp] * 17,
+    "vg_sln_bwd": [i32, i64, i64, i32] + [vp] * 18,
     "vg_attention_fwd": [i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, i64, vp, f32, vp],
     "vg_attention_bwd": [i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, i64, f32, vp, vp],
+    "vg_pack_pad": [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp],
     "vg_attention_path": [i32, i32, i32, i32, i32, i32],
     "vg_attention_set_trace": [vp],
     "vg_im2col_patches": [i32, i32, i32, i32, i32, vp, vp, vp],

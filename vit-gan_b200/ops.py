@@ -146,6 +146,17 @@ def cast(src: torch.Tensor, dtype: torch.dtype, out=None, num=None, den=None):
     return out
 
 
+def pack_pad(ptrs: torch.Tensor, n: int, rows: int, cols: int, rows_pad: int, cols_pad: int, dtype: torch.dtype, num=None, den=None):
+    """ptrs: int64 device tensor of n fp32 [rows, cols] tensor addresses -> [n * rows_pad, cols_pad] of `dtype`, scaled by
+    num[t] / den[t] and zero padded (one launch)."""
+    _req(ptrs, "ptrs")
+    out = torch.empty(n * rows_pad, cols_pad, dtype=dtype, device=ptrs.device)
+    check(lib.vg_pack_pad(ptrs.data_ptr(), n, rows, cols, rows_pad, cols_pad, _ptr(num), _ptr(den), out.data_ptr(), dt(out), stream()),
+          "vg_pack_pad")
+    _count()
+    return out
+
+
 def colsum(x2d: torch.Tensor, out=None):
     _req(x2d, "x")
     ld = _rowmajor2d(x2d, "x")

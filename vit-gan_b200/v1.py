@@ -95,10 +95,11 @@ class MSAFn(Function):
     flash attention (dot or L2), out-proj GEMM with bias and the block's residual fused in the epilogue.
 
     inputs: x (B,S,F); res None | (B,S,F) | (S,F); sig None | fp32 [2,3H] (row 0 sigma_init, row 1 sigma_now) in the
-    order of `ws`; ws = q_0,k_0,v_0,q_1,... (reference module order)."""
+    PACKING order (q heads | k heads | v heads); ptrs: int64 device tensor of the weight addresses in packing order (used by
+    the padded pack kernel) or None; ws = q_0,k_0,v_0,q_1,... (reference module order)."""
 
     @staticmethod
-    def forward(ctx, x, res, lp, n_heads, train_qkv, sig, wo, bo, *ws):
+    def forward(ctx, x, res, lp, n_heads, train_qkv, sig, ptrs, wo, bo, *ws):
         adt = act_dtype()
         B, S, F_ = x.shape
         x2 = x.reshape(B * S, F_)
@@ -106,13 +107,20 @@ class MSAFn(Function):
             x2 = ops.cast(x2, adt)
         x2 = x2.contiguous()
         H = n_heads
-        d = ws[0].shape[0]
+        d0 = ws[0].shape[0]                                                  # the reference head width (108 in D, 96 in G)
+        # tensor-core attention needs head widths that are multiples of 16: a 108-wide head is computed as a 112-wide one whose
+        # last 4 q/k/v columns are exactly zero (zero weight rows) -- dot products, distances and P V are unchanged.
+        d = (d0 + 15) // 16 * 16 if adt == torch.bfloat16 else d0
         order = [3 * h + j for j in range(3) for h in range(H)]            # q heads | k heads | v heads
-        scales = None if sig is None else [(sig[0, i:i + 1], sig[1, i:i + 1]) for i in order]
-        wqkv = packed([ws[i] for i in order], adt, scales=scales)
-        wo_ = packed([wo], adt)
+        if d == d0:
+            scales = None if sig is None else [(sig[0, i:i + 1], sig[1, i:i + 1]) for i in range(3 * H)]
+            wqkv = packed([ws[i] for i in order], adt, scales=scales)
+            wo_ = packed([wo], adt)
+        else:                                                              # one launch each: pack + rescale + zero padding
+            wqkv = ops.pack_pad(ptrs, 3 * H, d0, F_, d, F_, adt, None if sig is None else sig[0], None if sig is None else sig[1])
+            wo_ = _padded_out_proj(wo, adt, H, d0, d)
         mode = L.ATTN_L2 if lp == 2 else L.ATTN_DOT
-        scale = 1.0 / math.sqrt(H * d)                                       # attention.py:16,51,90 (Q7)
+        scale = 1.0 / math.sqrt(H * d0)                                      # attention.py:16,51,90 (Q7)
         res2, rmod = None, 0
         if res is not None:
             res2 = res.reshape(-1, F_)
@@ -124,8 +132,8 @@ class MSAFn(Function):
         qkv = ops.gemm(x2, wqkv)
         o, lse = ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, scale, mode)
         y = ops.gemm(o, wo_, bias=bo.detach(), residual=res2, res_row_mod=rmod)
-        ctx.save_for_backward(x2, qkv, o, lse, wqkv, wo)
-        ctx.meta = (B, S, F_, H, d, scale, mode, x.dtype, None if res is None else (res.shape, res.dtype), order,
+        ctx.save_for_backward(x2, qkv, o, lse, wqkv, wo_)
+        ctx.meta = (B, S, F_, H, d, d0, scale, mode, x.dtype, None if res is None else (res.shape, res.dtype), order,
                     train_qkv, [w.shape for w in ws])
         ctx.skip_pg = Fn._SKIP_PARAM_GRADS
         return y.reshape(B, S, F_)
@@ -133,8 +141,8 @@ class MSAFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x2, qkv, o, lse, wqkv, wo = ctx.saved_tensors
-        B, S, F_, H, d, scale, mode, xdtype, resinfo, order, train_qkv, wshapes = ctx.meta
+        x2, qkv, o, lse, wqkv, wo_ = ctx.saved_tensors
+        B, S, F_, H, d, d0, scale, mode, xdtype, resinfo, order, train_qkv, wshapes = ctx.meta
         adt = x2.dtype
         hd = H * d
         pg = not ctx.skip_pg
@@ -144,14 +152,16 @@ class MSAFn(Function):
         dwo = dbo = None
         if pg:
             dwo = ops.gemm(dy2, o, trans_a=True, trans_b=False, accumulate=True)
+            if d != d0:                                                   # drop the padding columns of the out-proj gradient
+                dwo = dwo.view(F_, H, d)[:, :, :d0].reshape(F_, H * d0)
             dbo = ops.colsum(dy2)
-        d_o = ops.gemm(dy2, packed([wo], adt), trans_b=False)
+        d_o = ops.gemm(dy2, wo_, trans_b=False)
         dqkv = ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, d_o, lse, B, H, S, d, scale, mode)
         dws = [None] * len(wshapes)
         if pg and train_qkv:
             dw = ops.gemm(dqkv, x2, trans_a=True, trans_b=False, accumulate=True)          # [3*H*d, F]
             for pos, i in enumerate(order):
-                dws[i] = dw[pos * d:(pos + 1) * d]
+                dws[i] = dw[pos * d:pos * d + d0]
         dx = ops.gemm(dqkv, wqkv, trans_b=False)
         if dx.dtype != xdtype:
             dx = ops.cast(dx, xdtype)
@@ -164,7 +174,22 @@ class MSAFn(Function):
                 dres = dy2.reshape(rshape)
             if dres.dtype != rdtype:
                 dres = ops.cast(dres, rdtype)
-        return (dx.reshape(B, S, F_), dres, None, None, None, None, dwo, dbo, *dws)
+        return (dx.reshape(B, S, F_), dres, None, None, None, None, None, dwo, dbo, *dws)
+
+
+_wo_ptr_cache: dict = {}
+
+
+def _padded_out_proj(wo, dtype, H, d0, dpad):
+    """out-proj weight [F, H*d0] -> [F, H*dpad] with zero columns behind every head (matches the padded attention output):
+    the [F*H, d0] view of the weight padded along its columns by vg_pack_pad."""
+    key = wo.data_ptr()
+    ptr = _wo_ptr_cache.get(key)
+    if ptr is None or ptr.device != wo.device:
+        ptr = torch.tensor([key], dtype=torch.int64).to(wo.device)
+        _wo_ptr_cache[key] = ptr
+    F_ = wo.shape[0]
+    return ops.pack_pad(ptr, 1, F_ * H, d0, F_ * H, dpad, dtype).view(F_, H * dpad)
 
 
 class LinearResFn(Function):
@@ -251,17 +276,24 @@ SIGMA_COLD_ITERS = 400     # first call per module: cold-start power iteration (
 SIGMA_WARM_ITERS = 4       # afterwards the persistent vector is already converged
 
 
-def _msa_sigma(self, ws):
-    """[2, 3H] fp32 table (row 0 sigma_init, row 1 sigma_now) for the spectral rescale (attention.py:54-64), or None."""
+def _msa_sigma(self, ws, order):
+    """ws: the 3H q/k/v weights in PACKING order (ws[pos] = reference weight number order[pos]).  Returns (sig, ptrs): sig = fp32
+    [2, 3H] table in packing order (row 0 sigma_init, row 1 sigma_now) for the spectral rescale (attention.py:54-64) or None,
+    ptrs = int64 device tensor of the weight addresses in packing order."""
     heads = self.attention_heads
-    if not heads[0].spectral_scaling:
-        return None
     dev = ws[0].device
     key = tuple(w.data_ptr() for w in ws)
+    if not heads[0].spectral_scaling:
+        st = getattr(self, "_vg_ptr_state", None)
+        if st is None or st[0] != key:
+            st = (key, torch.tensor(key, dtype=torch.int64).to(dev))
+            object.__setattr__(self, "_vg_ptr_state", st)
+        return None, st[1]
     st = getattr(self, "_vg_sigma_state", None)
     if st is None or st["key"] != key:
         with torch.no_grad():
-            init = torch.tensor([float(s) for hd in heads for s in hd.init_spectrum], dtype=torch.float32)
+            ref_init = [float(s) for hd in heads for s in hd.init_spectrum]
+            init = torch.tensor([ref_init[i] for i in order], dtype=torch.float32)
             sig = torch.empty(2, len(ws), dtype=torch.float32, device=dev)
             sig[0] = init.to(dev)
             st = {"key": key, "u": torch.zeros(len(ws), ws[0].shape[0], dtype=torch.float32, device=dev), "sig": sig,
@@ -270,7 +302,7 @@ def _msa_sigma(self, ws):
     ops.sigma_max(st["ptrs"], len(ws), ws[0].shape[0], ws[0].shape[1], st["u"],
                   SIGMA_WARM_ITERS if st["warm"] else SIGMA_COLD_ITERS, out=st["sig"][1])
     st["warm"] = True
-    return st["sig"]
+    return st["sig"], st["ptrs"]
 
 
 def msa_forward(self, x, res=None):
@@ -278,9 +310,11 @@ def msa_forward(self, x, res=None):
     heads = self.attention_heads
     ws = [w for hd in heads for w in (hd.q.weight, hd.k.weight, hd.v.weight)]
     lp = 2 if heads[0].attention_func.__name__ == "_l2att" else 1
-    sig = _msa_sigma(self, [w.detach() for w in ws])
+    H = len(heads)
+    order = [3 * h + j for j in range(3) for h in range(H)]                   # packing order: q heads | k heads | v heads
+    sig, ptrs = _msa_sigma(self, [ws[i].detach() for i in order], order)
     train_qkv = getattr(self, "train_qkv", not heads[0].spectral_scaling)     # Q4: spectral heads are frozen
-    return MSAFn.apply(x, res, lp, len(heads), train_qkv, sig, self.output_linear.weight, self.output_linear.bias, *ws)
+    return MSAFn.apply(x, res, lp, H, train_qkv, sig, ptrs, self.output_linear.weight, self.output_linear.bias, *ws)
 
 
 def sln_forward(self, h, w):
