@@ -173,8 +173,8 @@ int vg_attention_bwd(int dtype, int mode, int B, int H, int S, int d, const void
  * 0 = CUDA-core flash kernel (fp32 parity path, odd head sizes), 1 = single-tile tcgen05 (S <= 128, d in {32, 64}, dot),
  * 2 = multi-tile tcgen05 (d in {96, 112, 192}, S <= 272; L2-distance scores for d = 96 / 112).  Test / bench introspection. */
 int vg_attention_path(int dtype, int mode, int B, int H, int S, int d);
-/* Development aid (like vg_gemm_set_trace): while `buffer` (device memory, 3 * 1024 u64, caller-zeroed) is set, CTA 0 of the
- * multi-tile forward kernel logs (event code, %globaltimer) pairs per role -- producer, MMA issuer, compute leader -- at
+/* Development aid (like vg_gemm_set_trace): while `buffer` (device memory, 9 * 1024 u64, caller-zeroed) is set, CTA 0 of the
+ * multi-tile attention kernels (roles 0-2 forward, 3-5 backward dQ, 6-8 backward dK/dV) logs (event code, %globaltimer) pairs per role -- producer, MMA issuer, compute leader -- at
  * buffer[role * 1024 + 2 i].  NULL switches it off.  Process-global, not thread-safe (profiles/trace_attn.py). */
 int vg_attention_set_trace(void* buffer);
 

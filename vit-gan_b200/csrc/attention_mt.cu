@@ -553,28 +553,32 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       uint32_t bc = 0, tc = 0;                       // key-block counter, tile counter
+      Tracer tr(g.trace, 3);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           mbar_wait(q_free, (tc & 1u) ^ 1u);           // the previous tile's dQ store has read the staging tile (= the Q tile)
           mbar_wait(do_empty, (tc & 1u) ^ 1u);
+          tr(1);
           mbar_expect_tx(qdo_full, 2 * DC * QCH);
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
             tma_load_3d(q_t + c * QCH, &map_q, qdo_full, col0 + 64 * c, t * 128, b);
             tma_load_3d(do_t + c * QCH, &map_do, qdo_full, col0 + 64 * c, t * 128, b);
           }
-          for (int kb = 0; kb < g.n_b; ++kb, ++bc) {
+          for (int kb = 0; kb < g.n_b; ++kb, ++bc) {           // V stages are released first (after dP), K stages after dQ
             const int st = bc % NS;
             const uint32_t par = ((bc / NS) & 1u) ^ 1u;
-            mbar_wait(k_empty(st), par);
-            mbar_expect_tx(k_full(st), DC * BCH);
-#pragma unroll
-            for (int c = 0; c < DC; ++c) tma_load_3d(kr + (st * DC + c) * BCH, &map_k, k_full(st), col0 + 64 * c, kb * 64, b);
             mbar_wait(v_empty(st), par);
+            tr(110 + kb);
             mbar_expect_tx(v_full(st), DC * BCH);
 #pragma unroll
             for (int c = 0; c < DC; ++c) tma_load_3d(vr + (st * DC + c) * BCH, &map_v, v_full(st), col0 + 64 * c, kb * 64, b);
+            mbar_wait(k_empty(st), par);
+            tr(100 + kb);
+            mbar_expect_tx(k_full(st), DC * BCH);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(kr + (st * DC + c) * BCH, &map_k, k_full(st), col0 + 64 * c, kb * 64, b);
           }
         }
       }
@@ -583,40 +587,51 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (lane == 0) {
       const uint32_t idesc_dq = make_idesc(128, D, 0, 1);            // dQ = dS K : A K-major (dS), B MN-major (K block)
       uint32_t bc0 = 0, tc = 0;
+      Tracer tr(g.trace, 4);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           const uint32_t tpar = tc & 1u;
           mbar_wait(qdo_full, tpar);
+          tr(10);
           tc_fence_after();
-          auto issue_dq = [&](int j) {
-            const uint32_t c = bc0 + j;
-            const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * j);
-            mbar_wait(ds_full(buf), (c >> 1) & 1u);
-            if (j == 0) mbar_wait(dq_free, tpar ^ 1u);
-            tc_fence_after();
-            const uint32_t kt = kr + st * DC * BCH, dst = ds_t + buf * QCH;
-            for (int kk = 0; kk < nk / 16; ++kk)
-              tc_mma(tmem + DQ_COL, desc_k(dst + kk * 32u), desc_mn(kt + kk * 2048u, BCH), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
-            tc_commit(ds_empty(buf));
-            tc_commit(k_empty(st));
-          };
-          for (int j = 0; j < g.n_b; ++j) {
-            const uint32_t c = bc0 + j;
-            const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * j);
-            mbar_wait(k_full(st), (c / NS) & 1u);
-            mbar_wait(v_full(st), (c / NS) & 1u);
-            mbar_wait(sdp_free(buf), ((c >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = kr + st * DC * BCH, vt = vr + st * DC * BCH;
+          // event loop: dQ(j) as soon as its dS block is written (it releases the K stage the next load is waiting for),
+          // otherwise the next S / dP pair as soon as its K, V blocks have landed and its TMEM buffer has been read
+          int js = 0, jq = 0;                                         // next block to issue S/dP for, next block to issue dQ for
+          while (jq < g.n_b) {
+            if (jq < js) {
+              const uint32_t c = bc0 + jq;
+              const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * jq);
+              if (mbar_try_wait(ds_full(buf), (c >> 1) & 1u) && (jq > 0 || mbar_try_wait(dq_free, tpar ^ 1u))) {
+                tr(40 + jq);
+                tc_fence_after();
+                const uint32_t kt = kr + st * DC * BCH, dst = ds_t + buf * QCH;
+                for (int kk = 0; kk < nk / 16; ++kk)
+                  tc_mma(tmem + DQ_COL, desc_k(dst + kk * 32u), desc_mn(kt + kk * 2048u, BCH), idesc_dq, (jq > 0 || kk > 0) ? 1u : 0u);
+                tc_commit(ds_empty(buf));
+                tc_commit(k_empty(st));
+                ++jq;
+                continue;
+              }
+            }
+            if (js < g.n_b && js < jq + 2) {
+              const uint32_t c = bc0 + js;
+              const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * js);
+              if (mbar_try_wait(k_full(st), (c / NS) & 1u) && mbar_try_wait(v_full(st), (c / NS) & 1u) &&
+                  mbar_try_wait(sdp_free(buf), ((c >> 1) & 1u) ^ 1u)) {
+                tr(20 + js);
+                tc_fence_after();
+                const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = kr + st * DC * BCH, vt = vr + st * DC * BCH;
 #pragma unroll
-            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf), kdesc(q_t, QCH, k), kdesc(kt, BCH, k), idesc_s, k > 0);
+                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf), kdesc(q_t, QCH, k), kdesc(kt, BCH, k), idesc_s, k > 0);
 #pragma unroll
-            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf + 64), kdesc(do_t, QCH, k), kdesc(vt, BCH, k), idesc_s, k > 0);
-            tc_commit(sdp_full(buf));
-            tc_commit(v_empty(st));
-            if (j > 0) issue_dq(j - 1);
+                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf + 64), kdesc(do_t, QCH, k), kdesc(vt, BCH, k), idesc_s, k > 0);
+                tc_commit(sdp_full(buf));
+                tc_commit(v_empty(st));
+                ++js;
+              }
+            }
           }
-          issue_dq(g.n_b - 1);
+          tr(14);
           tc_commit(dq_full);
           tc_commit(do_empty);
           bc0 += g.n_b;
@@ -630,6 +645,7 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const bool leader = threadIdx.x == 64;
     const float sc2 = g.scale * LOG2E;
     uint32_t bc0 = 0, tc = 0;
+    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 5);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / g.H, h = w % g.H, col0 = h * D;
       if (MODE == VG_ATTN_L2) {
@@ -643,21 +659,30 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int row_g = t * 128 + row;
         const bool row_on = row_g < g.S;
         const bool warp_on = t * 128 + quad * 32 < g.S;
+        // delta = rowsum(dO * O): this row of O comes from global memory (D contiguous bf16) and is requested BEFORE the wait
+        // for the Q / dO tiles so that its latency overlaps theirs; dO is read from the smem tile
+        uint4 orow[D / 8];
+        if (row_on) {
+          const bf16* op = g.o + ((int64_t)b * g.S + row_g) * g.ldo + col0;
+#pragma unroll
+          for (int c8 = 0; c8 < D / 8; ++c8) orow[c8] = __ldg(reinterpret_cast<const uint4*>(op + 8 * c8));
+        }
         mbar_wait(qdo_full, tpar);
-        // delta = rowsum(dO * O): dO from the smem tile, O from global (this thread's own row, D contiguous bf16)
+        tr(50);
         float delta = 0.f, lse2 = 1e30f, qq = 0.f;
         if (row_on) {
-          const bf16* orow = g.o + ((int64_t)b * g.S + row_g) * g.ldo + col0;
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c8 = 0; c8 < D / 8; ++c8) {
             uint32_t a0, a1, a2, a3;
             lds128(swz(do_t + (uint32_t)(c8 >> 3) * QCH, row, c8 & 7), a0, a1, a2, a3);
-            const uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow + 8 * c8));
-            delta = fmaf(bf16_lo(a0), bf16_lo(ov.x), delta); delta = fmaf(bf16_hi(a0), bf16_hi(ov.x), delta);
-            delta = fmaf(bf16_lo(a1), bf16_lo(ov.y), delta); delta = fmaf(bf16_hi(a1), bf16_hi(ov.y), delta);
-            delta = fmaf(bf16_lo(a2), bf16_lo(ov.z), delta); delta = fmaf(bf16_hi(a2), bf16_hi(ov.z), delta);
-            delta = fmaf(bf16_lo(a3), bf16_lo(ov.w), delta); delta = fmaf(bf16_hi(a3), bf16_hi(ov.w), delta);
+            const uint4 ov = orow[c8];
+            d4[0] = fmaf(bf16_lo(a0), bf16_lo(ov.x), d4[0]); d4[1] = fmaf(bf16_hi(a0), bf16_hi(ov.x), d4[1]);
+            d4[2] = fmaf(bf16_lo(a1), bf16_lo(ov.y), d4[2]); d4[3] = fmaf(bf16_hi(a1), bf16_hi(ov.y), d4[3]);
+            d4[0] = fmaf(bf16_lo(a2), bf16_lo(ov.z), d4[0]); d4[1] = fmaf(bf16_hi(a2), bf16_hi(ov.z), d4[1]);
+            d4[2] = fmaf(bf16_lo(a3), bf16_lo(ov.w), d4[2]); d4[3] = fmaf(bf16_hi(a3), bf16_hi(ov.w), d4[3]);
           }
+          delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
           g.delta[(int64_t)w * g.S + row_g] = delta;
           lse2 = __ldg(g.lse + (int64_t)w * g.S + row_g) * LOG2E;
           if (MODE == VG_ATTN_L2) qq = row_sqnorm<D>(g.q + ((int64_t)b * g.S + row_g) * g.ld + col0);
@@ -666,9 +691,12 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int j = 0; j < g.n_b; ++j) {
           const uint32_t c = bc0 + j;
           const int buf = c & 1, nk = min(64, g.NK - 64 * j);
+          if (j == 0) tr(51);
           mbar_wait(sdp_full(buf), (c >> 1) & 1u);
+          tr(60 + j);
           tc_fence_after();
           mbar_wait(ds_empty(buf), ((c >> 1) & 1u) ^ 1u);           // dQ MMA of block j-2 has consumed this dS buffer
+          tr(70 + j);
           if (warp_on) {
             const uint32_t tile = ds_t + buf * QCH;
 #pragma unroll
@@ -697,10 +725,12 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           mbar_arrive(sdp_free(buf));
           fence_async_smem();
           mbar_arrive(ds_full(buf));
+          tr(80 + j);
         }
         bc0 += g.n_b;
         // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> staging over the Q tile -> TMA store
         mbar_wait(dq_full, tpar);                       // every MMA of the tile is complete: Q tile no longer read
+        tr(55);
         tc_fence_after();
         float qrow[MODE == VG_ATTN_L2 ? D : 1];
         if (MODE == VG_ATTN_L2) {
@@ -726,6 +756,7 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_arrive(dq_free);
         fence_async_smem();
         named_bar(1, 128);
+        tr(56);
         if (leader) {
           stg_store<D>(map_dq, q_t, col0, t * 128, b);
           tma_commit();
@@ -803,10 +834,12 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       uint32_t bc = 0, ic = 0;                       // query-block counter, item (key tile) counter
+      Tracer tr(g.trace, 6);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++ic) {
           mbar_wait(kvt_free, (ic & 1u) ^ 1u);         // previous item's dK/dV stores have read the staging (= the K, V tiles)
+          tr(1);
           mbar_expect_tx(kvt_full, 2 * DC * QCH);
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
@@ -816,6 +849,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
           for (int i = 0; i < g.n_b; ++i, ++bc) {
             const int st = bc % NS;
             mbar_wait(qdo_empty(st), ((bc / NS) & 1u) ^ 1u);
+            tr(100 + i);
             mbar_expect_tx(qdo_full(st), 2 * DC * BCH);
 #pragma unroll
             for (int c = 0; c < DC; ++c) {
@@ -830,45 +864,65 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     if (lane == 0) {
       const uint32_t idesc_kv = make_idesc(128, D, 0, 1);            // dV = P^T dO, dK = dS^T Q : A K-major, B MN-major
       uint32_t bc0 = 0, ic = 0;
+      Tracer tr(g.trace, 7);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int t = 0; t < g.n_t; ++t, ++ic) {
           const uint32_t ipar = ic & 1u;
           mbar_wait(kvt_full, ipar);
+          tr(10);
           tc_fence_after();
-          auto issue_st = [&](int i) {                                // S^T[:, block i] = K_tile Q_i^T
-            const uint32_t c = bc0 + i;
-            const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * i);
-            mbar_wait(qdo_full(st), (c / NS) & 1u);
-            mbar_wait(st_free(buf), ((c >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t idesc_s = make_idesc(128, ni, 0, 0), qt = qr + st * DC * BCH;
+          // event loop over three kinds of work, oldest dependency first: dK(i) once dS^T(i) is written (it releases the ring
+          // stage), dP^T(i) + dV(i) once P^T(i) is written, S^T(i) once its Q / dO block has landed and its TMEM buffer is free
+          int is = 0, ip = 0, ik = 0;                                 // next block for S^T, for dP^T + dV, for dK
+          while (ik < g.n_b) {
+            if (ik < ip) {
+              const uint32_t c = bc0 + ik;
+              const int st = c % NS, ni = min(64, g.NK - 64 * ik);
+              if (mbar_try_wait(dst_full, c & 1u)) {
+                tr(45 + ik);
+                tc_fence_after();
+                const uint32_t qt = qr + st * DC * BCH;
+                for (int kk = 0; kk < ni / 16; ++kk)
+                  tc_mma(tmem + DK_COL, desc_k(dst_t + kk * 32u), desc_mn(qt + kk * 2048u, BCH), idesc_kv, (ik > 0 || kk > 0) ? 1u : 0u);
+                tc_commit(dst_empty);
+                tc_commit(qdo_empty(st));
+                ++ik;
+                continue;
+              }
+            }
+            if (ip < is) {
+              const uint32_t c = bc0 + ip;
+              const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * ip);
+              if (mbar_try_wait(pt_full, c & 1u) && (ip > 0 || mbar_try_wait(out_free, ipar ^ 1u))) {   // P^T in smem; S^T fully read
+                tr(40 + ip);
+                tc_fence_after();
+                const uint32_t dot = dor + st * DC * BCH, idesc_s = make_idesc(128, ni, 0, 0);
 #pragma unroll
-            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(k_t, QCH, k), kdesc(qt, BCH, k), idesc_s, k > 0);
-            tc_commit(st_full(buf));
-          };
-          issue_st(0);
-          for (int i = 0; i < g.n_b; ++i) {
-            if (i + 1 < g.n_b) issue_st(i + 1);
-            const uint32_t c = bc0 + i;
-            const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * i);
-            const uint32_t qt = qr + st * DC * BCH, dot = dor + st * DC * BCH, idesc_s = make_idesc(128, ni, 0, 0);
-            mbar_wait(pt_full, c & 1u);                               // P^T in smem; S^T of this block fully read from TMEM
-            tc_fence_after();
+                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(v_t, QCH, k), kdesc(dot, BCH, k), idesc_s, k > 0);
+                tc_commit(dpt_full(buf));
+                for (int kk = 0; kk < ni / 16; ++kk)
+                  tc_mma(tmem + DV_COL, desc_k(pt_t + kk * 32u), desc_mn(dot + kk * 2048u, BCH), idesc_kv, (ip > 0 || kk > 0) ? 1u : 0u);
+                tc_commit(pt_empty);
+                ++ip;
+                continue;
+              }
+            }
+            if (is < g.n_b && is < ip + 2) {
+              const uint32_t c = bc0 + is;
+              const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * is);
+              if (mbar_try_wait(qdo_full(st), (c / NS) & 1u) && mbar_try_wait(st_free(buf), ((c >> 1) & 1u) ^ 1u)) {
+                tr(20 + is);
+                tc_fence_after();
+                const uint32_t idesc_s = make_idesc(128, ni, 0, 0), qt = qr + st * DC * BCH;
 #pragma unroll
-            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(v_t, QCH, k), kdesc(dot, BCH, k), idesc_s, k > 0);
-            tc_commit(dpt_full(buf));
-            if (i == 0) { mbar_wait(out_free, ipar ^ 1u); tc_fence_after(); }
-            for (int kk = 0; kk < ni / 16; ++kk)
-              tc_mma(tmem + DV_COL, desc_k(pt_t + kk * 32u), desc_mn(dot + kk * 2048u, BCH), idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
-            tc_commit(pt_empty);
-            mbar_wait(dst_full, c & 1u);
-            tc_fence_after();
-            for (int kk = 0; kk < ni / 16; ++kk)
-              tc_mma(tmem + DK_COL, desc_k(dst_t + kk * 32u), desc_mn(qt + kk * 2048u, BCH), idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
-            tc_commit(dst_empty);
-            tc_commit(qdo_empty(st));
+                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(k_t, QCH, k), kdesc(qt, BCH, k), idesc_s, k > 0);
+                tc_commit(st_full(buf));
+                ++is;
+              }
+            }
           }
           tc_commit(out_full);
+          tr(14);
           bc0 += g.n_b;
         }
       }
@@ -880,8 +934,10 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     const bool leader = threadIdx.x == 64;
     const float sc2 = g.scale * LOG2E;
     uint32_t bc0 = 0, ic = 0;
+    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 8);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / g.H, h = w % g.H, col0 = h * D;
+      tr(50);
       // per-query statistics of this problem -> smem: lse * log2e (+huge for padding queries: P = 0), delta, (L2) |q|^2
       named_bar(2, 128);
       for (int q = tid; q < g.n_b * 64 && q < MAXNK; q += 128) {
@@ -903,8 +959,10 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
           uint32_t f[32];                               // P * scale (dot) or P * scale / dist (L2) of this key row, packed bf16
           // stage A: S^T -> P^T (smem, A operand of dV) and the factor f kept in registers
           mbar_wait(st_full(buf), (c >> 1) & 1u);
+          tr(60 + i);
           tc_fence_after();
           mbar_wait(pt_empty, (c & 1u) ^ 1u);             // dV MMA of the previous block has consumed the P^T buffer
+          tr(65 + i);
           if (warp_on) {
 #pragma unroll
             for (int cc = 0; cc < 64; cc += 32) {
@@ -926,10 +984,13 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
           tc_fence_before();
           fence_async_smem();
           mbar_arrive(pt_full);
+          tr(70 + i);
           // stage B: dP^T -> dS^T = f (dP^T - delta) -> smem (A operand of dK)
           mbar_wait(dpt_full(buf), (c >> 1) & 1u);
+          tr(75 + i);
           tc_fence_after();
           mbar_wait(dst_empty, (c & 1u) ^ 1u);
+          tr(80 + i);
           if (warp_on) {
 #pragma unroll
             for (int cc = 0; cc < 64; cc += 32) {
@@ -952,10 +1013,12 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
           mbar_arrive(st_free(buf));
           fence_async_smem();
           mbar_arrive(dst_full);
+          tr(85 + i);
         }
         bc0 += g.n_b;
         // ---- drain dK, dV: TMEM -> (L2: colsum(G) k - G^T Q) -> bf16 -> staging over the K and V tiles -> TMA stores
         mbar_wait(out_full, ipar);
+        tr(55);
         tc_fence_after();
         float krow[MODE == VG_ATTN_L2 ? D : 1];
         if (MODE == VG_ATTN_L2) {
@@ -991,6 +1054,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
         mbar_arrive(out_free);
         fence_async_smem();
         named_bar(1, 128);
+        tr(56);
         if (leader) {
           stg_store<D>(map_dk, k_t, col0, t * 128, b);
           stg_store<D>(map_dv, v_t, col0, t * 128, b);
