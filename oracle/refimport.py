@@ -1,7 +1,9 @@
-"""Import the REAL reference (``/root/reference``) in the build container.  Test infrastructure.
+"""Import the REAL reference.  Test infrastructure.
 
-Only usable where ``/root/reference`` exists (not on the GPU box): used by ``make_golden.py`` and
-``tests/test_oracle_vs_reference.py`` to pin the oracle against the reference itself.
+In the build container the reference is imported from ``/root/reference``; on the GPU box (where that path does not exist) from
+the git-ignored staged copy ``oracle/_ref`` made by ``oracle/stage_ref.py``.  Used by ``make_golden.py`` and
+``tests/test_oracle_vs_reference.py`` to pin the oracle against the reference itself, by the GPU tests that patch instances of
+the real reference classes, and by ``bench.py --impl reference``.
 No reference file is edited; the shims are the external ones listed in SURVEY.md section 3.5/8c.
 """
 from __future__ import annotations
@@ -10,7 +12,19 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("VITGAN_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("VITGAN_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/src/v2"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:

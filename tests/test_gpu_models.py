@@ -17,8 +17,13 @@ GTOL = {"fp32": 2e-4, "bf16": 6e-2}
 
 @pytest.fixture(scope="module")
 def vb():
+    """The parity protocol runs both sides with every nn.Dropout at p = 0: the oracle has no dropout and the mirrors
+    are built with the reference's default rates, so the policy is switched to 'off' explicitly for this module
+    (test_dropout_in_training_mode_is_an_error checks the default)."""
     import vitgan_b200
-    return vitgan_b200
+    vitgan_b200.set_dropout_policy("off")
+    yield vitgan_b200
+    vitgan_b200.set_dropout_policy("error")
 
 
 @pytest.fixture(params=["fp32", "bf16"])
@@ -518,3 +523,85 @@ def test_v2_fused_layernorm_epilogue_matches_unfused(vb):
             vb.functional.set_fused_layernorm_epilogue(True)
     assert rel(res[True][0], res[False][0]) < 1e-2 and rel(res[True][1], res[False][1]) < 2e-2
     cmp_grads(res[True][2], res[False][2], 2e-2, "fused LayerNorm epilogue")
+
+
+def test_dropout_in_training_mode_is_an_error(vb):
+    """Default policy: a block in training mode that owns nn.Dropout(p > 0) must raise instead of silently running a different
+    model from the reference (src/v2/modules.py:99,179-180; src/v1/transformer.py:42,86); eval mode and p = 0 are fine."""
+    vb.set_dropout_policy("error")
+    try:
+        gan = vb.v2.ViTGAN(vb.v2.Config(embeddings_dimension=32, attention_heads_count=2, transformer_blocks_count=1, image_size=16,
+                                        patch_size=4, batch_size=768)).cuda()
+        x = torch.randn(2, 3, 16, 16).cuda()
+        with pytest.raises(NotImplementedError, match="Dropout"):
+            gan.discriminator(x)
+        gan.eval()
+        assert torch.isfinite(gan.discriminator(x)).all()
+        gan.train()
+        for m in gan.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        assert torch.isfinite(gan.discriminator(x)).all()
+        D = vb.v1.Discriminator(vb.v1.V1Config(image_size=32)).cuda()
+        with pytest.raises(NotImplementedError, match="Dropout"):
+            D(torch.randn(2, 3, 32, 32).cuda())
+    finally:
+        vb.set_dropout_policy("off")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The drop-in itself: instances of the REAL reference classes (imported from the staged copy oracle/_ref on the GPU box,
+# from /root/reference in the build container), forwards re-bound by patch.patch_v2 / patch_v1, driven by the reference's own
+# loop body (src/v2/training.py:177-211, src/v1/gan.py:222-252 as restated in oracle.harness.gan_step) with stock torch
+# optimizers -- against the SAME classes, unpatched, on the CPU.
+# ---------------------------------------------------------------------------------------------------------------
+def _reference_or_skip():
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference sources not staged: run `python -m oracle.stage_ref` where /root/reference exists")
+    return refimport
+
+
+def test_patched_reference_v2_three_step_curve(vb):
+    ref = _reference_or_skip()
+    over = dict(embeddings_dimension=64, attention_heads_count=2, transformer_blocks_count=2, image_size=16, patch_size=4)
+    gan_cpu, c = ref.build_v2(seed=3, **over)
+    mods = ref.v2_modules()
+    assert type(gan_cpu) is mods.ViTGAN                               # the reference's own class, not the mirror
+    ocfg = o2.V2Config(**over, batch_size=c.batch_size)
+    batches = harness.synthetic_batches_v2(ocfg, 4, 3, seed=77)
+    mk_opts = lambda gan: (torch.optim.AdamW(gan.generator.parameters(), lr=c.generator_learning_rate, weight_decay=1e-3),
+                           torch.optim.AdamW(gan.discriminator.parameters(), lr=c.discriminator_learning_rate, weight_decay=1e-3))
+    go, do = mk_opts(gan_cpu)
+    want = torch.stack([torch.stack(harness.gan_step(gan_cpu.generator, gan_cpu.discriminator, go, do, r, n, "ce")) for r, n in batches])
+    for prec, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        vb.set_precision(prec)
+        gan, _ = ref.build_v2(seed=3, **over)
+        keys = list(gan.state_dict())
+        gan = gan.cuda()
+        assert vb.patch.patch_v2(gan) >= 9 and type(gan.generator.vit.encoder[0]) is mods.Encoder
+        assert list(gan.state_dict()) == keys                         # checkpoints keep their names
+        go, do = mk_opts(gan)
+        got = torch.stack([torch.stack(harness.gan_step(gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce")).cpu()
+                           for r, n in batches])
+        assert rel(got, want) < tol, (prec, got, want)
+    vb.set_precision("bf16")
+
+
+def test_patched_reference_v1_two_step_curve(vb):
+    ref = _reference_or_skip()
+    G0, D0 = ref.build_v1(image_size=32, seed=5)
+    ocfg = o1.V1Config(image_size=32)
+    batches = harness.synthetic_batches_v1(ocfg, 3, 2, seed=78)
+    mk_opts = lambda G, D: (torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999)), torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999)))
+    go, do = mk_opts(G0, D0)          # built before the first forward, like GAN.__init__ (gan.py:39): D's q/k/v get orphaned (Q4)
+    want = torch.stack([torch.stack(harness.gan_step(G0, D0, go, do, r, z, "bce")) for r, z in batches])
+    for prec, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        vb.set_precision(prec)
+        G, D = ref.build_v1(image_size=32, seed=5)
+        G, D = G.cuda(), D.cuda()
+        assert vb.patch.patch_v1(G, D) > 20
+        go, do = mk_opts(G, D)
+        got = torch.stack([torch.stack(harness.gan_step(G, D, go, do, r.cuda(), z.cuda(), "bce")).cpu() for r, z in batches])
+        assert rel(got, want) < tol, (prec, got, want)
+    vb.set_precision("bf16")

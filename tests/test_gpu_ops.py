@@ -411,6 +411,12 @@ def test_denorm_u8_is_byte_exact(vb):
     assert torch.equal(vb.ops.denorm_u8(x.cuda()).cpu(), o2.convert_to_uint8(x))
     xb = x.bfloat16()
     assert torch.equal(vb.ops.denorm_u8(xb.cuda()).cpu(), o2.convert_to_uint8(xb.float()))
+    # more elements than one pass of the capped launch grid covers (148 SMs x 16 CTAs x 256 threads x 4 = 2.4 M): the c5 sampling
+    # batch (4096 x 3 x 32 x 32 = 12.6 M) must be written completely, odd tail included
+    big = torch.randn(4096 * 3 * 32 * 32 + 3, generator=g)
+    got = vb.ops.denorm_u8(big.cuda()).cpu()
+    assert torch.equal(got, o2.convert_to_uint8(big))
+    assert torch.equal(vb.ops.denorm_u8(big.bfloat16().cuda()).cpu(), o2.convert_to_uint8(big.bfloat16().float()))
 
 
 @pytest.mark.parametrize("M,K,res", [(33280 // 8, 128, True), (300, 256, True), (65, 128, False)])

@@ -13,7 +13,7 @@ Importing this package requires the built CUDA library; there is no fallback pat
 """
 from . import lib  # noqa: F401  (raises ImportError loudly if the .so is missing)
 from . import ops, functional, v2, v1, patch, train  # noqa: F401
-from .functional import set_precision, get_precision, skip_param_grads, set_operand_cache  # noqa: F401
+from .functional import set_precision, get_precision, skip_param_grads, set_operand_cache, set_dropout_policy  # noqa: F401
 
 __all__ = ["lib", "ops", "functional", "v2", "v1", "patch", "train", "set_precision", "get_precision",
-           "skip_param_grads", "set_operand_cache"]
+           "skip_param_grads", "set_operand_cache", "set_dropout_policy"]

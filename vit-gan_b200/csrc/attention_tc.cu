@@ -1050,7 +1050,7 @@ bool attention_tc_supported(int dtype, int mode, int B, int H, int S, int d, con
   if (!sm100 || forced_off) return false;
   if (dtype != VG_BF16 || mode != VG_ATTN_DOT) return false;
   if (!(d == 32 || d == 64) || S < 1 || S > 128) return false;
-  if ((H * d) % 128 != 0 && !((H * d) % 64 == 0 && S <= HP_MAX_S)) return false;   // head-parallel kernels work on 64-column items
+  if ((H * d) % 128 != 0 && !((H * d) % 64 == 0 && S <= HP_MAX_S && !hp_disabled())) return false;   // head-parallel kernels work on 64-column items; the single-tile ones on 128
   if (ld_qkv % 8 || ld_o % 8) return false;
   return aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o);
 }

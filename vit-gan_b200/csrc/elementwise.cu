@@ -251,16 +251,17 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
 __device__ __forceinline__ uint8_t to_u8(float v) { return (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(v, 127.5f), 127.5f), 0.f), 255.f); }
 template <typename T>
 __global__ void denorm_u8_kernel(const T* __restrict__ x, int64_t n, uint8_t* __restrict__ out) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i + 3 < n) {
+  // grid-stride over groups of 4 elements (the launch grid is capped at 16 CTAs per SM), scalar tail by the last groups' owner
+  const int64_t n4 = n / 4;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = gtid; g < n4; g += gsz) {
     float v[4];
-    Vec4<T>::load(x + i, v);
+    Vec4<T>::load(x + 4 * g, v);
     uchar4 o;
     o.x = to_u8(v[0]); o.y = to_u8(v[1]); o.z = to_u8(v[2]); o.w = to_u8(v[3]);
-    *reinterpret_cast<uchar4*>(out + i) = o;
-  } else {
-    for (int64_t j = i; j < n; ++j) out[j] = to_u8(to_f<T>(x[j]));
+    *reinterpret_cast<uchar4*>(out + 4 * g) = o;
   }
+  for (int64_t j = 4 * n4 + gtid; j < n; j += gsz) out[j] = to_u8(to_f<T>(x[j]));
 }
 
 }  // namespace

@@ -63,6 +63,41 @@ _cache: dict = {}
 _cache_enabled = True
 
 
+# --------------------------------------------------------------------------------------------------
+# dropout policy.  The reference applies nn.Dropout in training mode (src/v2/modules.py:99,179-180, p = 0.1;
+# src/v1/transformer.py:42,86 and muilti_layer_perceptron.py:27, p = 0.2).  The fused blocks do not implement it, so a
+# module in training mode whose dropout probability is > 0 is an ERROR by default ("unsupported => error") --
+# never a silently different model.  "off" is the parity protocol of SURVEY Q11 (p = 0 on both sides) made explicit.
+# --------------------------------------------------------------------------------------------------
+_DROPOUT_POLICY = "error"
+
+
+def set_dropout_policy(policy: str):
+    """'error' (default): raise when a patched block in training mode owns an nn.Dropout with p > 0;
+    'off': treat every dropout as p = 0 (what zeroing nn.Dropout.p on both sides does in the parity runs)."""
+    global _DROPOUT_POLICY
+    if policy not in ("error", "off"):
+        raise ValueError("dropout policy must be 'error' or 'off'")
+    _DROPOUT_POLICY = policy
+
+
+def check_dropout(module, *extra):
+    """Raise if `module` (training mode) owns an active nn.Dropout, directly or through `extra` sub-modules."""
+    if _DROPOUT_POLICY == "off" or not module.training:
+        return
+    for holder in (module,) + extra:
+        for name, child in holder._modules.items():
+            if isinstance(child, torch.nn.Dropout) and child.p > 0:
+                raise NotImplementedError(
+                    f"vitgan_b200: {type(module).__name__}.{name} is nn.Dropout(p={child.p}) in training mode, which the fused CUDA "
+                    "blocks do not implement.  Set p = 0 (as the parity protocol does), call .eval(), or "
+                    "vitgan_b200.set_dropout_policy('off') to run the blocks without dropout explicitly.")
+
+
+def operand_cache_enabled() -> bool:
+    return _cache_enabled
+
+
 def set_operand_cache(enabled: bool):
     global _cache_enabled
     _cache_enabled = enabled
@@ -78,11 +113,37 @@ def invalidate_operands(param_ids):
 # parameters re-homed by train.FlatNet: id(param) -> (flatnet, element offset).  When the parameters asked for sit back to
 # back in the flat buffer, the packed operand is a VIEW of the flat fp32 buffer or of its bf16 shadow (kept in sync by the
 # fused Adam kernel): no cast, no copy, no launch -- also under CUDA-graph capture, where the version-keyed cache is off.
-flat_registry: dict = {}
+# The registry holds WEAK references and every lookup re-checks that the parameter's storage really is the slot it was
+# registered with: ids of freed Parameters get recycled, and a stale entry must never hand out another network's buffer.
+flat_registry: dict = {}       # id(param) -> (weakref to the FlatNet, element offset)
+
+
+def register_flat(net, params, offsets):
+    import weakref
+    ref = weakref.ref(net)
+    ids = [id(p) for p in params]
+    for i, o in zip(ids, offsets):
+        flat_registry[i] = (ref, o)
+
+    def _drop(ids=ids, ref=ref):
+        for i in ids:
+            if flat_registry.get(i, (None,))[0] is ref:
+                del flat_registry[i]
+    weakref.finalize(net, _drop)
+
+
+def _flat_entry(p):
+    ent = flat_registry.get(id(p))
+    if ent is None:
+        return None
+    net = ent[0]()
+    if net is None or p.data_ptr() != net.flat_param.data_ptr() + 4 * ent[1]:      # dead network, or a recycled id
+        return None
+    return net, ent[1]
 
 
 def _flat_view(params, dtype):
-    ent = flat_registry.get(id(params[0]))
+    ent = _flat_entry(params[0])
     if ent is None:
         return None
     net, off0 = ent
@@ -91,7 +152,7 @@ def _flat_view(params, dtype):
         return None
     off = off0
     for p in params:
-        e = flat_registry.get(id(p))
+        e = _flat_entry(p)
         if e is None or e[0] is not net or e[1] != off:
             return None
         off += p.numel()
@@ -261,7 +322,9 @@ def acc_wgrad(dy2, x2, params, bias_params=None):
             _notify(params)
             _notify(bias_params)
             return None, None
-        except L.VitganError:          # rejected before any launch (shape / alignment): separate column-sum kernel
+        except L.VitganError as ex:    # rejected before any launch (shape / alignment): separate column-sum kernel
+            if not ex.rejected:
+                raise                  # a launch / CUDA error is not a reason to try another path
             _wgrad_bias_unsupported.add(key)
     return acc_wgrad(dy2, x2, params), acc_colsum(dy2, bias_params)
 
@@ -483,7 +546,9 @@ def gemm_ln(a, w, bias, residual, ln):
         try:
             y, xn, mean, rstd = ops.gemm(a, w, bias=bias, residual=residual, ln=(gamma, beta, eps))
             return y, (xn, mean, rstd)
-        except L.VitganError:          # rejected before any launch
+        except L.VitganError as ex:    # rejected before any launch
+            if not ex.rejected:
+                raise
             _gemm_ln_unsupported.add(key)
     y = ops.gemm(a, w, bias=bias, residual=residual)
     return y, ops.layernorm_fwd(y, gamma, beta, eps)

@@ -88,11 +88,23 @@ def _load():
 lib = _load()
 
 
+ERR_SHAPE, ERR_ALIGN, ERR_UNSUPPORTED, ERR_LAUNCH, ERR_ARG = -1, -2, -3, -4, -5      # vg_status (include/vitgan_b200.h)
+
+
 class VitganError(RuntimeError):
-    pass
+    """`status` is the vg_status code.  `rejected` = the call was refused before anything was launched (shape / alignment /
+    unsupported combination): only those may be answered by taking another path of THIS library; launch errors must surface."""
+
+    def __init__(self, message, status=ERR_LAUNCH):
+        super().__init__(message)
+        self.status = status
+
+    @property
+    def rejected(self):
+        return self.status in (ERR_SHAPE, ERR_ALIGN, ERR_UNSUPPORTED)
 
 
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = lib.vg_last_error()
-        raise VitganError(f"{what or 'libvitgan_b200'} failed (status {rc}): {msg.decode() if msg else ''}")
+        raise VitganError(f"{what or 'libvitgan_b200'} failed (status {rc}): {msg.decode() if msg else ''}", rc)

@@ -51,8 +51,7 @@ class FlatNet:
         if dev.type == "cuda":
             self.flat_shadow = torch.empty(off, dtype=torch.bfloat16, device=dev)
             self.sync_shadow()
-            for p, o in zip(self.params, self.offsets):
-                Fn.flat_registry[id(p)] = (self, o)
+            Fn.register_flat(self, self.params, self.offsets)
 
     def sync_shadow(self):
         """Re-derive the bf16 shadow from the fp32 parameters (after construction / load_state_dict)."""
@@ -134,9 +133,16 @@ class GradBuckets:
         self.pending = [0] * self.n
         self.works = []
         self.index = {id(p): i for i, p in enumerate(net.params)}
-        for i, p in enumerate(net.params):
-            p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self._hook_handles = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(net.params)]
         Fn.grad_ready_hooks.append(self._fused_ready)      # gradients accumulated in place by the kernels
+
+    def close(self):
+        """Detach from the parameters and from the fused-accumulation notification list (the hooks hold this object alive)."""
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles = []
+        if self._fused_ready in Fn.grad_ready_hooks:
+            Fn.grad_ready_hooks.remove(self._fused_ready)
 
     def _make_hook(self, i):
         def hook(param):
@@ -316,6 +322,7 @@ class GraphedStep:
         step = gan_step_microbatched if kw.get("n_micro", 1) > 1 else gan_step
         if step is gan_step:
             self.kw.pop("n_micro", None)
+        prev_cache = Fn.operand_cache_enabled()
         Fn.set_operand_cache(False)        # casts/packs must be part of the captured work
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -329,6 +336,7 @@ class GraphedStep:
                 self.losses = step(*self.args, self.real, self.noise, **self.kw)
         finally:
             Fn.set_param_grad_stream(prev_pg)             # the fork is baked into the graph; eager callers keep their setting
+            Fn.set_operand_cache(prev_cache)              # eager callers get their cached operand copies back
 
     def __call__(self, real, noise):
         self.real.copy_(real, non_blocking=True)

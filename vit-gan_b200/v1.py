@@ -324,6 +324,7 @@ def sln_forward(self, h, w):
 def _mlp_single(mlp):
     if len(mlp.model) != 1:
         raise NotImplementedError("vitgan_b200.v1: only the reference default MLP (layers=[]: one Linear) is implemented")
+    Fn.check_dropout(mlp, mlp.model[0])            # Sequential(Linear, Dropout): muilti_layer_perceptron.py:27
     return mlp.model[0][0]
 
 
@@ -335,6 +336,7 @@ def mlp_forward(self, x):
 
 def transformer_sln_forward(self, h, x):
     """TransformerSLN.forward (transformer.py:85-88) -> (x, hf)."""
+    Fn.check_dropout(self)
     htmp = msa_forward(self.msha, sln_forward(self.layer_norm_1, h, x), res=h)
     lin = _mlp_single(self.mlp)
     hf = LinearResFn.apply(sln_forward(self.layer_norm_2, htmp, x), htmp, lin.weight, lin.bias)
@@ -343,6 +345,7 @@ def transformer_sln_forward(self, h, x):
 
 def transformer_forward(self, x):
     """Transformer.forward (transformer.py:40-45)."""
+    Fn.check_dropout(self)
     if x.dtype != act_dtype():
         x = x.to(act_dtype())
     x1 = Fn.LayerNormFn.apply(x, self.layer_norm_1.weight, self.layer_norm_1.bias, self.layer_norm_1.eps)
@@ -360,6 +363,7 @@ def siren_forward(self, x):
 
 def patch_encoder_forward(self, images):
     """PatchEncoder.forward (patch_encoder.py:39-52)."""
+    Fn.check_dropout(self)
     if images.dim() != 4:
         raise AssertionError("Expected input image tensor to be of shape BxCxHxW")
     if images.shape[2] != images.shape[3]:

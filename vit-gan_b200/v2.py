@@ -4,7 +4,8 @@ Same class names, constructor arguments, parameter names / shapes / init and ``s
 reference, so checkpoints and the training-loop call sites (src/v2/training.py:177-211) work unchanged;
 only the body of each ``forward`` differs: it is one ``torch.autograd.Function`` backed by the sm_100a
 kernels of libvitgan_b200.  ``patch.patch_v2(gan)`` applies the same forwards to instances of the real
-reference classes.  Dropout (p>0) is not applied inside the fused blocks: parity runs use p=0.
+reference classes.  Dropout is not implemented inside the fused blocks: a block in training mode with p > 0 raises
+(functional.check_dropout) unless the caller opts into the p = 0 parity protocol (set_dropout_policy('off')).
 """
 from __future__ import annotations
 
@@ -43,6 +44,7 @@ class Config:
 
 def embed_forward(self, x):
     """EmbedLayer.forward (modules.py:82-100)."""
+    Fn.check_dropout(self)
     return Fn.EmbedV2Fn.apply(x, self.conv1.weight, self.conv1.bias, self.pos_embedding, self.cls_token,
                               self.conv1.kernel_size[0])
 
@@ -58,6 +60,7 @@ def encoder_forward_chained(self, x, ln1=None, next_norm=None):
     """Encoder.forward (modules.py:178-183) as one autograd Function.  ln1 = (xn, mean, rstd) of this block's first LayerNorm if
     the previous block's fc2 epilogue already produced it; next_norm = the next block's norm1 module, whose LayerNorm is then
     computed by this block's fc2 epilogue.  -> (y, ln1-of-next-block | None)."""
+    Fn.check_dropout(self)
     a = self.attention
     c = ln1 if ln1 is not None else (None, None, None)
     ng, nb = (next_norm.weight, next_norm.bias) if next_norm is not None else (None, None)
