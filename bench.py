@@ -478,6 +478,7 @@ def measure(args, name, steps, warmup, full, rank, world, local):
         torch.cuda.synchronize()
         launches_per_step = vb.ops.launch_count
         step_fn, graph_used = eager, False
+        torch.cuda.empty_cache()
         if not args.no_graph:
             try:
                 gs = vb.train.GraphedStep(gen, disc, gopt, dopt, devb[0][0], devb[0][1], loss_kind, warmup=2, d_buckets=d_b,

@@ -286,6 +286,8 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
         loss = crit(disc(fake).float(), zeros) * inv
         loss.backward()
         l_fake = l_fake + loss.detach()
+        if i + 1 < n_micro:
+            Fn.join_param_grad_stream()     # releases the activations the side-stream weight-gradient GEMMs keep alive (one micro-batch at a time)
     if d_buckets is not None:
         d_buckets.finish()
     Fn.join_param_grad_stream()
@@ -301,6 +303,8 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
         loss = crit(out.float(), ones) * inv
         loss.backward()
         l_g = l_g + loss.detach()
+        if i + 1 < n_micro:
+            Fn.join_param_grad_stream()
     if g_buckets is not None:
         g_buckets.finish()
     Fn.join_param_grad_stream()
@@ -330,6 +334,8 @@ class GraphedStep:
             for _ in range(warmup):
                 step(*self.args, self.real, self.noise, **self.kw)
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()           # the warm-up's cached blocks belong to other streams / pools than the capture's private pool
         self.graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(self.graph):
