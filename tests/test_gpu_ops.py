@@ -459,3 +459,117 @@ def test_gemm_gelu_epilogue_large_arguments(vb):
     xr = bias.bfloat16().float().requires_grad_(True)
     F.gelu(xr).sum().backward()
     assert torch.isfinite(dgrad).all() and (dgrad.float().cpu()[0] - xr.grad).abs().max() < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Production shapes of BASELINE configs[1] (C2): M = 512 x 65 = 33 280 rows (66 560 for the merged discriminator pass), i.e. 5-11
+# tiles per CTA through the persistent loop of the 128-wide tcgen05 GEMM: accumulator-stage phase wrap, the alternating epilogue
+# staging tiles (`wait_group.read 1`), and the fused epilogues at more than one tile per CTA.  Checker: the fp32 formula on the
+# same bf16-rounded operands, evaluated by torch on the device.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [33280, 66560])
+def test_gemm_production_rows_all_epilogues(vb, M):
+    L = vb.lib
+    g = gen(M)
+    E, m = 128, 2
+    dev = "cuda"
+    x = (torch.randn(M, E, generator=g) * 0.7).bfloat16().to(dev)
+    res = torch.randn(M, E, generator=g).bfloat16().to(dev)
+    wqkv = (torch.randn(3 * E, E, generator=g) * 0.1).bfloat16().to(dev)
+    w1 = (torch.randn(m * E, E, generator=g) * 0.1).bfloat16().to(dev)
+    w2 = (torch.randn(E, m * E, generator=g) * 0.1).bfloat16().to(dev)
+    bq, b1, b2 = (torch.randn(n, generator=g).to(dev) for n in (3 * E, m * E, E))
+    gam, bet = (1 + 0.1 * torch.randn(E, generator=g)).to(dev), (0.1 * torch.randn(E, generator=g)).to(dev)
+    xf = x.float()
+    # forward, bias
+    qkv = vb.ops.gemm(x, wqkv, bias=bq, path=L.GEMM_TCGEN05)
+    assert rel(qkv, xf @ wqkv.float().t() + bq) < BF16_TOL
+    # forward, GELU + pre-activation
+    h, u = vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)
+    u_ref = xf @ w1.float().t() + b1
+    assert rel(u, u_ref) < BF16_TOL and rel(h, F.gelu(u_ref)) < BF16_TOL
+    # forward, residual + fused LayerNorm epilogue (N = 128: one tile is one complete row)
+    y, xn, mean, rstd = vb.ops.gemm(h, w2, bias=b2, residual=res, ln=(gam, bet, 1e-5), path=L.GEMM_TCGEN05)
+    y_ref = h.float() @ w2.float().t() + b2 + res.float()
+    assert rel(y, y_ref) < BF16_TOL
+    yb = y.float()                                                     # the kernel normalises the bf16-rounded row
+    assert rel(mean, yb.mean(1)) < 1e-3 and rel(rstd, (yb.var(1, unbiased=False) + 1e-5).rsqrt()) < 1e-3
+    assert rel(xn, F.layer_norm(yb, (E,), gam, bet, 1e-5)) < BF16_TOL
+    # dgrad with GELU' epilogue:  dU = (dH W2) * gelu'(u)
+    dy = torch.randn(M, E, generator=g).bfloat16().to(dev)
+    du = vb.ops.gemm(dy, w2, trans_b=False, act=L.ACT_MUL_DGELU, aux=u, path=L.GEMM_TCGEN05)
+    du_ref = act_ref(5, dy.float() @ w2.float(), u.float(), 0.0)
+    assert rel(du, du_ref) < BF16_TOL
+    # wgrad + fused bias gradient (a_rowsum), accumulating
+    dw0, db0 = torch.randn(3 * E, E, generator=g).to(dev), torch.randn(3 * E, generator=g).to(dev)
+    dw, db = dw0.clone(), db0.clone()
+    vb.ops.gemm(qkv, x, trans_a=True, trans_b=False, accumulate=True, out=dw, rowsum_out=db, path=L.GEMM_TCGEN05)
+    assert rel(dw, dw0 + qkv.float().t() @ xf) < 1e-4
+    assert rel(db, db0 + qkv.float().sum(0)) < 1e-4
+
+
+MT_SHAPES = [(2, 4, 257, 192, 0), (40, 4, 257, 192, 0), (1, 1, 128, 192, 0), (1, 2, 129, 192, 0), (3, 4, 64, 96, 0), (2, 4, 65, 112, 0),
+             (2, 4, 65, 112, 1), (300, 4, 65, 112, 1), (2, 4, 64, 96, 1), (1, 2, 200, 112, 1), (2, 2, 272, 96, 0), (2, 2, 17, 96, 0),
+             (3, 2, 1, 112, 1)]
+
+
+@pytest.mark.parametrize("B,H,S,d,mode", MT_SHAPES)
+def test_attention_multi_tile_tensor_core_path(vb, B, H, S, d, mode):
+    """bf16 attention with head widths 96 / 112 / 192 runs on the multi-tile tcgen05 kernels (attention_mt.cu) -- the scaled v2
+    config (S = 257, d = 192; src/v2/modules.py:142-159) and both v1 head shapes incl. the L2-distance scores of the
+    discriminator (src/v1/attention.py:43-52,66-70; torch.cdist matmul-path semantics): forward (o, lse) and the backward
+    (dq, dk, dv) against the fp32 formula at 2e-2, and against this library's CUDA-core flash kernel in fp32."""
+    assert vb.lib.lib.vg_attention_path(1, mode, B, H, S, d) == 2
+    g = gen(B + S + d + mode)
+    hd = H * d
+    qkv = (torch.randn(B * S, 3 * hd, generator=g) * (1.0 if mode else 0.7)).bfloat16()
+    d_o = torch.randn(B * S, hd, generator=g).bfloat16()
+    scale = 1.0 / math.sqrt(d if mode == 0 else hd)
+    ref_in = qkv.float().cuda().requires_grad_(True)                    # fp32 formula, evaluated by torch on the device
+    q, k, v = [ref_in[:, i * hd:(i + 1) * hd].reshape(B, S, H, d).permute(0, 2, 1, 3) for i in range(3)]
+    if mode == 1:
+        s = ((q * q).sum(-1, keepdim=True) + (k * k).sum(-1, keepdim=True).transpose(-1, -2) - 2 * q @ k.transpose(-1, -2)).clamp_min(0).sqrt() * scale
+    else:
+        s = (q @ k.transpose(-1, -2)) * scale
+    oref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, hd)
+    lse_ref = torch.logsumexp(s, -1).reshape(-1)
+    oref.backward(d_o.float().cuda())
+    qc = qkv.cuda()
+    o, lse = vb.ops.attention_fwd(qc[:, :hd], qc[:, hd:2 * hd], qc[:, 2 * hd:], B, H, S, d, scale, mode)
+    assert rel(o, oref) < BF16_TOL and rel(lse, lse_ref) < 1e-3
+    dqkv = vb.ops.attention_bwd(qc[:, :hd], qc[:, hd:2 * hd], qc[:, 2 * hd:], o, d_o.cuda(), lse, B, H, S, d, scale, mode)
+    assert torch.isfinite(dqkv).all()
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, i * hd:(i + 1) * hd], ref_in.grad[:, i * hd:(i + 1) * hd]) < BF16_TOL, name
+    if B * H * S * S < 5e7:                                             # same inputs through the CUDA-core kernel in fp32
+        qf = qkv.float().cuda()
+        o32, lse32 = vb.ops.attention_fwd(qf[:, :hd], qf[:, hd:2 * hd], qf[:, 2 * hd:], B, H, S, d, scale, mode)
+        assert rel(o, o32) < BF16_TOL and rel(lse, lse32) < 1e-3
+
+
+def test_attention_multi_tile_l2_zero_distance_is_finite(vb):
+    """q == k rows give dist = 0 on the diagonal: the guarded 1/dist of the tcgen05 L2 backward keeps the gradients finite (Q6)."""
+    B, H, S, d = 2, 2, 65, 112
+    x = torch.randn(B * S, H * d, generator=gen(1)).bfloat16().cuda()
+    qkv = torch.cat([x, x, x], 1).contiguous()
+    hd = H * d
+    assert vb.lib.lib.vg_attention_path(1, 1, B, H, S, d) == 2
+    o, lse = vb.ops.attention_fwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], B, H, S, d, 0.1, 1)
+    dqkv = vb.ops.attention_bwd(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], o, torch.ones_like(o), lse, B, H, S, d, 0.1, 1)
+    assert torch.isfinite(o).all() and torch.isfinite(dqkv).all()
+
+
+def test_pack_pad_grouped_heads(vb):
+    """vg_pack_pad: 3H per-head [108, 432] weights (pointer array) -> one bf16 [3H x 112, 432] operand, rescaled per head by
+    sigma_init / sigma_now and zero padded, in one launch; with n = 1 it pads the columns of the out-proj weight."""
+    g = gen(9)
+    ws = [torch.randn(108, 432, generator=g).cuda() for _ in range(12)]
+    num, den = (torch.rand(12, generator=g) + 0.5).cuda(), (torch.rand(12, generator=g) + 0.5).cuda()
+    ptrs = torch.tensor([w.data_ptr() for w in ws], dtype=torch.int64).cuda()
+    out = vb.ops.pack_pad(ptrs, 12, 108, 432, 112, 432, torch.bfloat16, num, den).view(12, 112, 432)
+    for i, w in enumerate(ws):
+        assert torch.equal(out[i, :108], (w * num[i] / den[i]).bfloat16()) and not out[i, 108:].any()
+    wo = torch.randn(432, 432, generator=g).cuda()
+    ptr = torch.tensor([wo.data_ptr()], dtype=torch.int64).cuda()
+    pad = vb.ops.pack_pad(ptr, 1, 432 * 4, 108, 432 * 4, 112, torch.float32).view(432, 4, 112)
+    assert torch.equal(pad[:, :, :108], wo.view(432, 4, 108)) and not pad[:, :, 108:].any()
