@@ -165,7 +165,7 @@ def test_gemm_tc_rejects_and_errors(vb):
 
 
 @pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
-@pytest.mark.parametrize("rows,E", [(33, 32), (130, 128), (65 * 4, 432), (50, 768)])
+@pytest.mark.parametrize("rows,E", [(33, 32), (130, 128), (65 * 4, 432), (50, 768), (5000, 768), (4099, 384), (2500, 432), (3001, 512)])
 def test_layernorm(vb, dt, tol, rows, E):
     g = gen(rows + E)
     x = (torch.randn(rows, E, generator=g) * 2 + 0.5).to(dt)

@@ -209,6 +209,124 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LN backward, wide rows (bf16)
+// E > 256 (the scaled config's 768, v1's 384 / 432).  The generic kernel above keeps ONE row per warp in flight (3 tensors x E in
+// fp32 registers + four E-wide column accumulators = 255 registers, 1 CTA / SM): 8 rows = 37 KB of loads in flight per SM, below
+// the ~44 KB that 6.5 TB/s x 1 us of latency needs -- it measured 30 % of the HBM roofline at E = 768.  Here the operands stay
+// PACKED (bf16) in registers until they are used and the next row of the warp is requested before the current one is reduced
+// (two static buffers, loop unrolled by two), so every warp has two rows in flight; x-hat and gamma*dy are recomputed in the
+// second pass instead of being kept.  Same outputs as ln_bwd_kernel (dx, dgamma, dbeta, optional colsum(dres) / colsum(dx)).
+template <int NV>
+struct PackedRow { uint2 x[NV], dy[NV], dr[NV]; float mu, rs; };
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+ln_bwd_wide_kernel(int64_t rows, int E, const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                   const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dres_colsum, float* __restrict__ dx_colsum, float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
+  __shared__ float s_all[4 * MAXE];
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+  const bool acc = dgamma != nullptr, has_res = dres != nullptr;
+  float g[NV][4], adg[NV][4], adb[NV][4], adr[NV][4], adx[NV][4];
+  load_vec(gamma, E, lane, g);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { adg[i][j] = 0.f; adb[i][j] = 0.f; adr[i][j] = 0.f; adx[i][j] = 0.f; }
+  const float invE = 1.0f / (float)E;
+
+  auto fetch = [&](PackedRow<NV>& b, int64_t r) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < E) {
+        b.x[i] = __ldg(reinterpret_cast<const uint2*>(x + r * E + c));
+        b.dy[i] = __ldg(reinterpret_cast<const uint2*>(dy + r * E + c));
+        b.dr[i] = has_res ? __ldg(reinterpret_cast<const uint2*>(dres + r * E + c)) : make_uint2(0u, 0u);
+      } else {
+        b.x[i] = b.dy[i] = b.dr[i] = make_uint2(0u, 0u);
+      }
+    }
+    b.mu = __ldg(mean + r); b.rs = __ldg(rstd + r);
+  };
+  auto unpack = [](uint2 u, float (&v)[4]) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  };
+  auto process = [&](const PackedRow<NV>& b, int64_t r) {
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float xv[4], dv[4];
+      unpack(b.x[i], xv); unpack(b.dy[i], dv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xv[j] - b.mu) * b.rs;              // padded lanes: dy = 0, gamma = 0 -> contribute nothing
+        const float gd = dv[j] * g[i][j];
+        adg[i][j] = fmaf(dv[j], xh, adg[i][j]);
+        adb[i][j] += dv[j];
+        c1 += gd;
+        c2 = fmaf(gd, xh, c2);
+      }
+    }
+    c1 = warp_sum(c1) * invE;
+    c2 = warp_sum(c2) * invE;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float xv[4], dv[4], rv[4], o[4];
+      unpack(b.x[i], xv); unpack(b.dy[i], dv); unpack(b.dr[i], rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xv[j] - b.mu) * b.rs;
+        const float t = b.rs * (dv[j] * g[i][j] - c1 - xh * c2);
+        adr[i][j] += rv[j];
+        o[j] = rv[j] + t;
+        adx[i][j] += o[j];
+      }
+      if (c < E) Vec4<bf16>::store(dx + r * E + c, o);
+    }
+  };
+
+  PackedRow<NV> A, B;
+  int64_t r = warp;
+  if (r < rows) fetch(A, r);
+  while (r < rows) {
+    const int64_t rn = r + nwarps;
+    if (rn < rows) fetch(B, rn);
+    process(A, r);
+    const int64_t r2 = rn + nwarps;
+    if (r2 < rows) fetch(A, r2);
+    if (rn < rows) process(B, rn);
+    r = r2;
+  }
+  if (!acc) return;                  // dx only (dgrad-only pass): no column reductions at all
+  for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) s_all[i] = 0.f;
+  __syncthreads();
+  flush_cols(s_all, nullptr, adg, E, lane);
+  flush_cols(s_all + E, nullptr, adb, E, lane);
+  flush_cols(s_all + 2 * E, nullptr, adr, E, lane);
+  flush_cols(s_all + 3 * E, nullptr, adx, E, lane);
+  __syncthreads();
+  if (ws != nullptr) {               // replicated accumulators, folded by the last CTA (same layout as ln_bwd_kernel)
+    float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
+    const int offs[4] = {0, E, 2 * E, 3 * E};
+    cta_replica_reduce(ws, ws_rows, counter, s_all, 4 * E, outs, offs, 4);
+    return;
+  }
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_all[i]);
+    atomicAdd(&dbeta[i], s_all[E + i]);
+    if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[2 * E + i]);
+    if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[3 * E + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LN backward, E <= 128
 // Same math as ln_bwd_kernel<T, 1>, restructured for memory-level parallelism: a warp keeps RPI = 8 (bf16) / 4 (fp32) rows
 // of all three inputs in flight as PACKED registers (one 8/16-byte load per lane per tensor per row) before any conversion
@@ -779,6 +897,16 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
     else
       launch_pdl(ln_bwd_e128_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
                  rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter, (float*)nullptr);
+    return check_launch("layernorm_bwd");
+  }
+  if (dtype == VG_BF16 && E > 256 && E <= 768 && E % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                                                   reinterpret_cast<uintptr_t>(dres)) & 7) == 0) {
+    // wide rows: packed operands, two rows per warp in flight, one CTA per SM
+    const int gridw = grid_for_rows(rows, 1);
+#define VG_LN_WIDE(NV_) launch_pdl(ln_bwd_wide_kernel<NV_>, dim3(gridw), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean, \
+                                   rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)
+    if (E <= 384) VG_LN_WIDE(3); else if (E <= 512) VG_LN_WIDE(4); else VG_LN_WIDE(6);
+#undef VG_LN_WIDE
     return check_launch("layernorm_bwd");
   }
   int grid = grid_for_rows((rows + 3) / 4, per_sm);   // CTAs/SM x 8 warps x 4 rows x 3 tensors of 16 B loads in flight
