@@ -257,30 +257,39 @@ __device__ __forceinline__ void tmem_free512(uint32_t tmem) {
 }
 
 // ================================================================================================ forward
+// K of the (batch, head) problem stays resident in smem for all of its query tiles (loaded once: [NK rows x 64 col] SW128 chunks),
+// so S = Q K^T is ONE N = 256 MMA (+ one N = NK - 256) per k-step -- an SS-MMA pays 64 B/clk of operand fetch, i.e. the
+// 128 x 16 A tile costs as much as 128 columns of B, and N = 64 blocks were 3x off the tensor pipe's rate.  V streams through a
+// ring of 64-key blocks.  P is written back to TMEM as bf16 over the consumed S columns and feeds O += P V as the TMEM-resident
+// A operand (tcgen05.mma .ts): no P tile in smem, no A fetch.  The output staging tile aliases the V ring; the producer warp
+// issues the TMA store (it is idle then), so no compute thread ever waits for a store.
 template <int D> struct FwdCfg {
   static constexpr int DC = (D + 63) / 64, KS = D / 16;
-  static constexpr int NST = 4;                              // ring stages of one 64-key K or V block
-  static constexpr int O_COL = 288;                          // S in TMEM columns [0, 272), O in [288, 288 + D)
-  static constexpr int Q_OFF = 0, P_OFF = DC * QCH, RING_OFF = P_OFF + MAXKB * QCH, KN_OFF = RING_OFF + NST * DC * BCH;
-  static constexpr int BAR_OFF = KN_OFF + MAXNK * 4, NBAR = 6 + 2 * NST + 2 * MAXKB;
+  static constexpr int NSTV = 3;                             // ring stages of one 64-key V block
+  static constexpr int KCH = MAXNK * 128;                    // one resident K chunk: [272 rows x 64 col]
+  static constexpr int O_COL = 288;                          // S (fp32) / P (bf16, in place) in TMEM columns [0, 272), O in [288, 288 + D)
+  static constexpr int Q_OFF = 0, K_OFF = DC * QCH, V_OFF = K_OFF + DC * KCH, KN_OFF = V_OFF + NSTV * DC * BCH;
+  static constexpr int BAR_OFF = KN_OFF + MAXNK * 4, NBAR = 8 + 2 * NSTV + MAXKB;
   static constexpr int SMEM = BAR_OFF + NBAR * 8 + 16;
+  static_assert(NSTV * DC * BCH >= 128 * D * 2, "the output staging tile aliases the V ring");
 };
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ OutMaps map_o, const MtGeo g) {
+attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k64,
+                   const __grid_constant__ CUtensorMap map_k16, const __grid_constant__ CUtensorMap map_v,
+                   const __grid_constant__ OutMaps map_o, const MtGeo g) {
   using C = FwdCfg<D>;
-  constexpr int DC = C::DC, KS = C::KS, NST = C::NST, O_COL = C::O_COL;
+  constexpr int DC = C::DC, KS = C::KS, NSTV = C::NSTV, O_COL = C::O_COL, KCH = C::KCH;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t base = smem_u32(smem_dyn);
-  const uint32_t q_t = base + C::Q_OFF, p_t = base + C::P_OFF, ring = base + C::RING_OFF, bar = base + C::BAR_OFF;
+  const uint32_t q_t = base + C::Q_OFF, k_t = base + C::K_OFF, vring = base + C::V_OFF, stg = vring, bar = base + C::BAR_OFF;
   float* kn = reinterpret_cast<float*>(smem_dyn + C::KN_OFF);
-  const uint32_t q_full = bar, q_empty = bar + 8, s_full = bar + 16, s_free = bar + 24, o_full = bar + 32, o_free = bar + 40;
-  auto kv_full = [&](int i) { return bar + 8u * (6 + i); };
-  auto kv_empty = [&](int i) { return bar + 8u * (6 + NST + i); };
-  auto p_full = [&](int i) { return bar + 8u * (6 + 2 * NST + i); };
-  auto p_empty = [&](int i) { return bar + 8u * (6 + 2 * NST + MAXKB + i); };
+  const uint32_t q_full = bar, q_empty = bar + 8, k_full = bar + 16, k_empty = bar + 24, s_full = bar + 32, o_full = bar + 40,
+                 o_free = bar + 48, stg_full = bar + 56;
+  auto v_full = [&](int i) { return bar + 8u * (8 + i); };
+  auto v_empty = [&](int i) { return bar + 8u * (8 + NSTV + i); };
+  auto p_full = [&](int i) { return bar + 8u * (8 + 2 * NSTV + i); };
   const uint32_t tmem_slot = bar + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + C::BAR_OFF + 8 * C::NBAR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,11 +297,12 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (threadIdx.x == 0) {
     if (base & 1023u) { printf("attention_mt: dynamic smem base not 1024-aligned\n"); __trap(); }
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k64) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(o_full, 1); mbar_init(o_free, 128);
-    for (int i = 0; i < NST; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_empty(i), 1); }
-    for (int i = 0; i < MAXKB; ++i) { mbar_init(p_full(i), 128); mbar_init(p_empty(i), 1); }
+    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(s_full, 1);
+    mbar_init(o_full, 1); mbar_init(o_free, 128); mbar_init(stg_full, 128);
+    for (int i = 0; i < NSTV; ++i) { mbar_init(v_full(i), 1); mbar_init(v_empty(i), 1); }
+    for (int i = 0; i < MAXKB; ++i) mbar_init(p_full(i), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc512(tmem_slot);
@@ -303,77 +313,87 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   pdl_trigger();
   pdl_wait();
   const int total = g.B * g.H;
+  const int n64 = g.NK / 64, n16 = (g.NK % 64) / 16;              // K is loaded as n64 boxes of 64 rows + n16 boxes of 16 rows per chunk
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t rc = 0, tc = 0;                       // ring slot counter, tile counter
-      Tracer tr(g.trace, 0);
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      uint32_t vc = 0, tc = 0, ic = 0;              // V-block, tile and item counters
+      auto load_k = [&](int w) {
+        const int b = w / g.H, col0 = (w % g.H) * D;
+        mbar_expect_tx(k_full, (uint32_t)(DC * g.NK * 128));
+        for (int c = 0; c < DC; ++c) {
+          for (int i = 0; i < n64; ++i) tma_load_3d(k_t + c * KCH + i * BCH, &map_k64, k_full, col0 + 64 * c, 64 * i, b);
+          for (int i = 0; i < n16; ++i) tma_load_3d(k_t + c * KCH + n64 * BCH + i * 2048, &map_k16, k_full, col0 + 64 * c, 64 * n64 + 16 * i, b);
+        }
+      };
+      int pend_w = -1, pend_t = 0;                  // tile whose output the compute threads are about to stage
+      auto store_pending = [&]() {                  // the staging tile (over the V ring) is written: store it, wait for the read
+        if (pend_w < 0) return;
+        mbar_wait(stg_full, (tc - 1) & 1u);
+        stg_store<D>(map_o, stg, (pend_w % g.H) * D, pend_t * 128, pend_w / g.H);
+        tma_commit();
+        tma_wait_read();
+        pend_w = -1;
+      };
+      if ((int)blockIdx.x < total) load_k(blockIdx.x);
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++ic) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           mbar_wait(q_empty, (tc & 1u) ^ 1u);
-          tr(1);
           mbar_expect_tx(q_full, DC * QCH);
 #pragma unroll
           for (int c = 0; c < DC; ++c) tma_load_3d(q_t + c * QCH, &map_q, q_full, col0 + 64 * c, t * 128, b);
-          for (int pass = 0; pass < 2; ++pass)
-            for (int kb = 0; kb < g.n_b; ++kb, ++rc) {
-              const int st = rc % NST;
-              mbar_wait(kv_empty(st), ((rc / NST) & 1u) ^ 1u);
-              tr(100 + pass * 10 + kb);
-              mbar_expect_tx(kv_full(st), DC * BCH);
-#pragma unroll
-              for (int c = 0; c < DC; ++c)
-                tma_load_3d(ring + (st * DC + c) * BCH, pass == 0 ? &map_k : &map_v, kv_full(st), col0 + 64 * c, kb * 64, b);
+          store_pending();                           // previous tile's O: its V blocks are all consumed, none of this tile's is issued yet
+          const bool last = t + 1 == g.n_t;
+          for (int kb = 0; kb < g.n_b; ++kb, ++vc) {
+            if (last && kb == min(g.n_b, NSTV) && w + (int)gridDim.x < total) {   // next problem's K, as soon as this one's last S is done
+              mbar_wait(k_empty, ic & 1u);
+              load_k(w + gridDim.x);
             }
+            const int st = vc % NSTV;
+            mbar_wait(v_empty(st), ((vc / NSTV) & 1u) ^ 1u);
+            mbar_expect_tx(v_full(st), DC * BCH);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(vring + (st * DC + c) * BCH, &map_v, v_full(st), col0 + 64 * c, kb * 64, b);
+          }
+          if (last && g.n_b <= NSTV && w + (int)gridDim.x < total) { mbar_wait(k_empty, ic & 1u); load_k(w + gridDim.x); }
+          pend_w = w; pend_t = t;
         }
       }
+      store_pending();
+      tma_wait_all();
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_pv = make_idesc(128, D, 0, 1);            // O = P V : A K-major, B MN-major
-      uint32_t rc = 0, tc = 0;
-      Tracer tr(g.trace, 1);
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const uint32_t idesc_pv = make_idesc(128, D, 0, 1);            // O = P V : A from TMEM, B MN-major
+      uint32_t vc = 0, tc = 0, ic = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++ic) {
+        mbar_wait(k_full, ic & 1u);
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           const uint32_t par = tc & 1u;
           mbar_wait(q_full, par);
-          tr(10);
-          mbar_wait(s_free, par ^ 1u);
-          tr(11);
           tc_fence_after();
-          for (int kb = 0; kb < g.n_b; ++kb, ++rc) {                  // S[:, 64 kb ..] = Q K_kb^T
-            const int st = rc % NST, nk = min(64, g.NK - 64 * kb);
-            mbar_wait(kv_full(st), (rc / NST) & 1u);
-            tr(20 + kb);
-            tc_fence_after();
-            const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = ring + st * DC * BCH;
+          for (int n0 = 0; n0 < g.NK; n0 += 256) {                    // S[:, n0 ..] = Q K[n0 ..]^T, whole key range, in program order
+            const uint32_t idesc_s = make_idesc(128, min(256, g.NK - n0), 0, 0);     // behind the previous tile's P V (same TMEM columns)
 #pragma unroll
-            for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * kb), kdesc(q_t, QCH, k), kdesc(kt, BCH, k), idesc_s, k > 0);
-            tc_commit(kv_empty(st));
+            for (int k = 0; k < KS; ++k)
+              tc_mma(tmem + (uint32_t)n0, kdesc(q_t, QCH, k), desc_k(k_t + (uint32_t)(k >> 2) * KCH + (uint32_t)n0 * 128u + (uint32_t)(k & 3) * 32u), idesc_s, k > 0);
           }
           tc_commit(s_full);
           tc_commit(q_empty);
-          tr(12);
+          if (t + 1 == g.n_t) tc_commit(k_empty);
           mbar_wait(o_free, par ^ 1u);
-          tr(13);
-          for (int kb = 0; kb < g.n_b; ++kb, ++rc) {                  // O += P_kb V_kb
-            const int st = rc % NST, nk = min(64, g.NK - 64 * kb);
-            mbar_wait(kv_full(st), (rc / NST) & 1u);
-            tr(30 + kb);
+          for (int kb = 0; kb < g.n_b; ++kb, ++vc) {                  // O += P_kb V_kb
+            const int st = vc % NSTV, nk = min(64, g.NK - 64 * kb);
+            mbar_wait(v_full(st), (vc / NSTV) & 1u);
             mbar_wait(p_full(kb), par);
-            tr(40 + kb);
             tc_fence_after();
-            const uint32_t vt = ring + st * DC * BCH, pt = p_t + kb * QCH;
-            for (int kk = 0; kk < nk / 16; ++kk) {
-              if (P_TMEM) tc_mma_ts(tmem + O_COL, tmem + (uint32_t)(32 * kb + 8 * kk), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
-              else tc_mma(tmem + O_COL, desc_k(pt + kk * 32u), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
-            }
-            tc_commit(kv_empty(st));
-            tc_commit(p_empty(kb));
+            const uint32_t vt = vring + st * DC * BCH;
+            for (int kk = 0; kk < nk / 16; ++kk)
+              tc_mma_ts(tmem + O_COL, tmem + (uint32_t)(32 * kb + 8 * kk), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(v_empty(st));
           }
           tc_commit(o_full);
-          tr(14);
         }
       }
     }
@@ -381,13 +401,11 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // ---------------------------------------------------------------- softmax + output drain: thread = query row
     const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    const bool leader = threadIdx.x == 64;
     const float sc2 = g.scale * LOG2E;
     uint32_t tc = 0;
     Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 2);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / g.H, h = w % g.H, col0 = h * D;
-      tr(50);
       if (MODE == VG_ATTN_L2) {                       // |k_j|^2 of this problem's keys -> smem (broadcast reads below)
         named_bar(2, 128);
         for (int j = tid; j < g.NK; j += 128)
@@ -400,7 +418,6 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const bool warp_on = t * 128 + quad * 32 < g.S;               // warp-uniform: this warp owns real query rows
         float qq = 0.f;
         if (MODE == VG_ATTN_L2 && row_g < g.S) qq = row_sqnorm<D>(g.q + ((int64_t)b * g.S + row_g) * g.ld + col0);
-        tr(51);
         mbar_wait(s_full, par);
         tr(52);
         tc_fence_after();
@@ -411,7 +428,6 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             uint32_t v[32];
             if (g.NK - c >= 32) {
               tmem_ld32(t_lane + (uint32_t)c, v);
-              tr(80);
               if (c + 32 <= g.S) fwd_max<32, false, MODE>(v, c, g.S, qq, kn, m4); else fwd_max<32, true, MODE>(v, c, g.S, qq, kn, m4);
             } else {
               tmem_ld16p(t_lane + (uint32_t)c, v);
@@ -421,49 +437,56 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           }
         }
         const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        // the previous tile's output store must have finished reading the staging tile (it aliases the P chunks)
         tr(53);
-        if (leader) tma_wait_read();
-        named_bar(1, 128);
-        tr(54);
-        // pass 2: P = exp2((s - m) scale log2e) -> bf16 -> smem, one 64-key chunk at a time (the PV MMAs trail by one chunk)
+        // pass 2: P = exp2((s - m) scale log2e) -> bf16 -> TMEM in place (P of keys [2c, 2c + 2) lands in column c, already read),
+        // one 64-key chunk at a time: the P V MMAs trail by one chunk
         const float mb = m * sc2;
         for (int kb = 0; kb < g.n_b; ++kb) {
-          mbar_wait(p_empty(kb), par ^ 1u);
-          tr(70);
           if (warp_on) {
-            const int nk = min(64, g.NK - 64 * kb);
-            const uint32_t tile = p_t + kb * QCH;
-#pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-              if (c >= nk) break;
-              uint32_t v[32], pk[16];
-              const int c0 = 64 * kb + c;
-              if (nk - c >= 32) {
-                tmem_ld32(t_lane + (uint32_t)c0, v);
-                tr(71);
-                if (c0 + 32 <= g.S) fwd_exp<32, false, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk); else fwd_exp<32, true, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk);
-                if (P_TMEM) tmem_st16(t_lane + (uint32_t)(c0 >> 1), pk); else put_row<32>(tile, row, c, pk);
+            const int nk = min(64, g.NK - 64 * kb), c0 = 64 * kb;
+            uint32_t va[32], vb2[32], pk[16];
+            if (nk == 64) {                          // both halves requested before either is exponentiated
+              tmem_ld32_nowait(t_lane + (uint32_t)c0, va);
+              tmem_ld32_nowait(t_lane + (uint32_t)(c0 + 32), vb2);
+              tmem_ld_wait();
+              if (c0 + 64 <= g.S) {
+                fwd_exp<32, false, MODE>(va, c0, g.S, qq, kn, sc2, mb, l4, pk);
+                tmem_st16(t_lane + (uint32_t)(c0 >> 1), pk);
+                fwd_exp<32, false, MODE>(vb2, c0 + 32, g.S, qq, kn, sc2, mb, l4, pk);
+                tmem_st16(t_lane + (uint32_t)((c0 >> 1) + 16), pk);
               } else {
-                tmem_ld16p(t_lane + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (c0 + 16 <= g.S) fwd_exp<16, false, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk); else fwd_exp<16, true, MODE>(v, c0, g.S, qq, kn, sc2, mb, l4, pk);
-                if (P_TMEM) tmem_st8(t_lane + (uint32_t)(c0 >> 1), pk); else put_row<16>(tile, row, c, pk);
+                fwd_exp<32, true, MODE>(va, c0, g.S, qq, kn, sc2, mb, l4, pk);
+                tmem_st16(t_lane + (uint32_t)(c0 >> 1), pk);
+                fwd_exp<32, true, MODE>(vb2, c0 + 32, g.S, qq, kn, sc2, mb, l4, pk);
+                tmem_st16(t_lane + (uint32_t)((c0 >> 1) + 16), pk);
               }
-              tr(72);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 64; c += 32) {
+                if (c >= nk) break;
+                if (nk - c >= 32) {
+                  tmem_ld32(t_lane + (uint32_t)(c0 + c), va);
+                  fwd_exp<32, true, MODE>(va, c0 + c, g.S, qq, kn, sc2, mb, l4, pk);
+                  tmem_st16(t_lane + (uint32_t)((c0 + c) >> 1), pk);
+                } else {
+                  tmem_ld16p(t_lane + (uint32_t)(c0 + c), va);
+                  tmem_ld_wait();
+                  fwd_exp<16, true, MODE>(va, c0 + c, g.S, qq, kn, sc2, mb, l4, pk);
+                  tmem_st8(t_lane + (uint32_t)((c0 + c) >> 1), pk);
+                }
+              }
             }
+            tmem_st_wait();
           }
-          if (P_TMEM) { tmem_st_wait(); tc_fence_before(); } else fence_async_smem();   // P chunk visible to the tensor core
-          tr(73);
+          tc_fence_before();                           // P chunk written (and its S columns read) before the tensor core touches them
           mbar_arrive(p_full(kb));
           tr(60 + kb);
         }
-        tc_fence_before();
-        mbar_arrive(s_free);                           // S fully read: the next tile's Q K^T may overwrite it
         const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const float inv_l = 1.0f / l;
         if (row_g < g.S) g.lse[(int64_t)w * g.S + row_g] = m * g.scale + __logf(l);
-        // ---- drain O: TMEM -> * 1/l -> bf16 -> staging (over the P chunks, all consumed once o_full fires) -> TMA store
+        // ---- drain O: TMEM -> * 1/l -> bf16 -> staging over the V ring (every V block of the tile is consumed once o_full fires,
+        //      and the producer issues no V load of the next tile before it has stored this one)
         mbar_wait(o_full, par);
         tr(55);
         tc_fence_after();
@@ -476,18 +499,16 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * inv_l;
-            stg_write<D>(p_t, row, c, o, n);
+            stg_write<D>(stg, row, c, o, n);
           }
         }
         tc_fence_before();
         mbar_arrive(o_free);
         fence_async_smem();
-        named_bar(1, 128);
+        mbar_arrive(stg_full);
         tr(56);
-        if (leader) { stg_store<D>(map_o, p_t, col0, t * 128, b); tma_commit(); }
       }
     }
-    if (leader) tma_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -1131,12 +1152,13 @@ int set_smem_once(K kern, int bytes, bool* done) {
 }
 
 template <int D, int MODE>
-int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const OutMaps& mo, const MtGeo& g, cudaStream_t st) {
+int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk64, const CUtensorMap& mk16, const CUtensorMap& mv, const OutMaps& mo, const MtGeo& g,
+               cudaStream_t st) {
   static bool set = false;
   int rc = set_smem_once(attn_fwd_mt_kernel<D, MODE>, FwdCfg<D>::SMEM, &set);
   if (rc) return rc;
   const int grid = min(g.B * g.H, num_sms());
-  launch_pdl(attn_fwd_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)FwdCfg<D>::SMEM, st, mq, mk, mv, mo, g);
+  launch_pdl(attn_fwd_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)FwdCfg<D>::SMEM, st, mq, mk64, mk16, mv, mo, g);
   return check_launch("attention_fwd_mt");
 }
 template <int D, int MODE>
@@ -1190,15 +1212,16 @@ bool attention_mt_supported(int dtype, int mode, int B, int H, int S, int d, con
 int attention_fwd_mt(int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
                      float* lse, float scale, cudaStream_t st) {
   const int cols = H * d;
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk64, mk16, mv;
   OutMaps mo;
   int rc;
   if ((rc = make_map(&mq, q, B, S, cols, ld, 64, 128))) return rc;
-  if ((rc = make_map(&mk, k, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_map(&mk64, k, B, S, cols, ld, 64, 64))) return rc;
+  if ((rc = make_map(&mk16, k, B, S, cols, ld, 64, 16))) return rc;
   if ((rc = make_map(&mv, v, B, S, cols, ld, 64, 64))) return rc;
   if ((rc = make_out_maps(&mo, o, B, S, cols, ldo, d))) return rc;
   const MtGeo g = make_geo(B, H, S, ld, ldo, scale, q, k, o, lse, nullptr);
-  VG_MT_DISPATCH(d, mode, (rc = launch_fwd<D, MODE>(mq, mk, mv, mo, g, st)));
+  VG_MT_DISPATCH(d, mode, (rc = launch_fwd<D, MODE>(mq, mk64, mk16, mv, mo, g, st)));
   return rc;
 }
 
