@@ -364,8 +364,11 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tma_wait_all();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issue: the whole warp runs the loop (warp-uniform control flow and operands), one elected lane issues
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_pv = make_idesc(128, D, 0, 1);            // O = P V : A from TMEM, B MN-major
+      const SDesc qd = sdesc_k(q_t), kd0 = sdesc_k(k_t);
       uint32_t vc = 0, tc = 0, ic = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++ic) {
         mbar_wait(k_full, ic & 1u);
@@ -375,25 +378,36 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tc_fence_after();
           for (int n0 = 0; n0 < g.NK; n0 += 256) {                    // S[:, n0 ..] = Q K[n0 ..]^T, whole key range, in program order
             const uint32_t idesc_s = make_idesc(128, min(256, g.NK - n0), 0, 0);     // behind the previous tile's P V (same TMEM columns)
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KS; ++k)
-              tc_mma(tmem + (uint32_t)n0, kdesc(q_t, QCH, k), desc_k(k_t + (uint32_t)(k >> 2) * KCH + (uint32_t)n0 * 128u + (uint32_t)(k & 3) * 32u), idesc_s, k > 0);
+              for (int k = 0; k < KS; ++k)
+                tc_mma_d(tm + (uint32_t)n0, qd, kstep_off(k, QCH), kd0, kstep_off(k, KCH) + (uint32_t)n0 * 8u, idesc_s, k > 0);
+            }
+            __syncwarp();
           }
-          tc_commit(s_full);
-          tc_commit(q_empty);
-          if (t + 1 == g.n_t) tc_commit(k_empty);
+          if (elect_one()) {
+            tc_commit(s_full);
+            tc_commit(q_empty);
+            if (t + 1 == g.n_t) tc_commit(k_empty);
+          }
+          __syncwarp();
           mbar_wait(o_free, par ^ 1u);
           for (int kb = 0; kb < g.n_b; ++kb, ++vc) {                  // O += P_kb V_kb
             const int st = vc % NSTV, nk = min(64, g.NK - 64 * kb);
             mbar_wait(v_full(st), (vc / NSTV) & 1u);
             mbar_wait(p_full(kb), par);
             tc_fence_after();
-            const uint32_t vt = vring + st * DC * BCH;
-            for (int kk = 0; kk < nk / 16; ++kk)
-              tc_mma_ts(tmem + O_COL, tmem + (uint32_t)(32 * kb + 8 * kk), desc_mn(vt + kk * 2048u, BCH), idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
-            tc_commit(v_empty(st));
+            const SDesc vd = sdesc_mn(vring + st * DC * BCH, BCH);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                if (kk < nk / 16) tc_mma_ts_d(tm + O_COL, tm + (uint32_t)(32 * kb + 8 * kk), vd, kk * 128u, idesc_pv, (kb > 0 || kk > 0) ? 1u : 0u);
+              tc_commit(v_empty(st));
+            }
+            __syncwarp();
           }
-          tc_commit(o_full);
+          if (elect_one()) tc_commit(o_full);
+          __syncwarp();
         }
       }
     }
@@ -516,15 +530,43 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 // ================================================================================================ backward: dQ (+ delta)
+// The Q and dO tiles are A operands of 2 x n_b MMAs each.  From smem every MMA pays 64 clk of A fetch on top of N / 2 clk of B
+// (operand fetch runs at 64 B/clk), which at N = 64 is three times the tensor pipe's rate; so the compute threads -- which read
+// their dO row anyway for delta = rowsum(dO * O) -- copy both rows into TMEM once per tile (tcgen05.st, two bf16 per column) and
+// S = Q K_j^T, dP = dO V_j^T run as TS-MMAs.  TMEM: Q | dO as operands (D columns), one [S | dP] pair of 64-key blocks (128 columns;
+// released as soon as the block sits in registers, so the next pair is computed while this one is exponentiated), dQ (D columns).
+// dS goes to smem (double buffered) as the A operand of dQ += dS K_j.  The dQ staging tile is the Q smem tile (free once copied);
+// the producer warp stores it and then fetches the next tile's Q into it, while the next dO tile was already prefetched.
 template <int D> struct DqCfg {
   static constexpr int DC = (D + 63) / 64, KS = D / 16;
   static constexpr int NS = D > 128 ? 2 : 3;                 // ring stages per operand (K blocks, V blocks)
-  static constexpr int DQ_COL = 256;                         // [S | dP] x 2 buffers in columns [0, 256), dQ in [256, 256 + D)
+  static constexpr int QA_COL = 0, DOA_COL = D / 2, S_COL = D, DP_COL = D + 64, DQ_COL = D + 128;
+  static_assert(DQ_COL + D <= 512, "TMEM layout");
   static constexpr int Q_OFF = 0, DO_OFF = DC * QCH, KR_OFF = 2 * DC * QCH, VR_OFF = KR_OFF + NS * DC * BCH;
   static constexpr int DS_OFF = VR_OFF + NS * DC * BCH, KN_OFF = DS_OFF + 2 * QCH, BAR_OFF = KN_OFF + MAXNK * 4;
-  static constexpr int NBAR = 5 + 4 * NS + 8;
+  static constexpr int NBAR = 9 + 4 * NS + 4;
   static constexpr int SMEM = BAR_OFF + NBAR * 8 + 16;
 };
+
+// this thread's row of a K-major [128 x D] SW128 operand tile -> TMEM columns [col, col + D / 2) of its lane (bf16 A operand of a
+// TS-MMA: element k of the row in column k / 2, low half first), 32 elements (16 columns) at a time; `f(c, r)` sees every chunk
+// (c = first TMEM column of the chunk, r = its 16 -- or 8 for the tail -- packed registers)
+template <int D, typename F>
+__device__ __forceinline__ void row_to_tmem(uint32_t tile, int row, uint32_t taddr, F&& f) {
+#pragma unroll
+  for (int c = 0; c < D / 2; c += 16) {
+    uint32_t r[16];
+    const int n = (D / 2 - c) >= 16 ? 16 : 8;            // D / 2 is a multiple of 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * i < n) {
+        const int c8 = (c >> 2) + i;                       // 16-byte chunk = 8 elements = 4 columns
+        lds128(swz(tile + (uint32_t)(c8 >> 3) * QCH, row, c8 & 7), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+      }
+    if (n == 16) tmem_st16(taddr + (uint32_t)c, r); else tmem_st8(taddr + (uint32_t)c, r);
+    f(c, r, n);
+  }
+}
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -532,19 +574,18 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                       const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                       const __grid_constant__ OutMaps map_dq, const MtGeo g) {
   using C = DqCfg<D>;
-  constexpr int DC = C::DC, KS = C::KS, NS = C::NS, DQ_COL = C::DQ_COL;
+  constexpr int DC = C::DC, KS = C::KS, NS = C::NS, QA_COL = C::QA_COL, DOA_COL = C::DOA_COL, S_COL = C::S_COL, DP_COL = C::DP_COL, DQ_COL = C::DQ_COL;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t base = smem_u32(smem_dyn);
   const uint32_t q_t = base + C::Q_OFF, do_t = base + C::DO_OFF, kr = base + C::KR_OFF, vr = base + C::VR_OFF, ds_t = base + C::DS_OFF;
   const uint32_t bar = base + C::BAR_OFF;
   float* kn = reinterpret_cast<float*>(smem_dyn + C::KN_OFF);
-  const uint32_t qdo_full = bar, q_free = bar + 8, do_empty = bar + 16, dq_full = bar + 24, dq_free = bar + 32;
-  auto k_full = [&](int i) { return bar + 8u * (5 + i); };
-  auto k_empty = [&](int i) { return bar + 8u * (5 + NS + i); };
-  auto v_full = [&](int i) { return bar + 8u * (5 + 2 * NS + i); };
-  auto v_empty = [&](int i) { return bar + 8u * (5 + 3 * NS + i); };
-  auto sdp_full = [&](int i) { return bar + 8u * (5 + 4 * NS + i); };
-  auto sdp_free = [&](int i) { return bar + 8u * (7 + 4 * NS + i); };
+  const uint32_t q_full = bar, do_full = bar + 8, do_free = bar + 16, a_ready = bar + 24, stg_full = bar + 32, dq_full = bar + 40,
+                 dq_free = bar + 48, sdp_full = bar + 56, sdp_free = bar + 64;
+  auto k_full = [&](int i) { return bar + 8u * (9 + i); };
+  auto k_empty = [&](int i) { return bar + 8u * (9 + NS + i); };
+  auto v_full = [&](int i) { return bar + 8u * (9 + 2 * NS + i); };
+  auto v_empty = [&](int i) { return bar + 8u * (9 + 3 * NS + i); };
   auto ds_full = [&](int i) { return bar + 8u * (9 + 4 * NS + i); };
   auto ds_empty = [&](int i) { return bar + 8u * (11 + 4 * NS + i); };
   const uint32_t tmem_slot = bar + 8u * C::NBAR;
@@ -557,9 +598,10 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-    mbar_init(qdo_full, 1); mbar_init(q_free, 1); mbar_init(do_empty, 1); mbar_init(dq_full, 1); mbar_init(dq_free, 128);
+    mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(do_free, 128); mbar_init(a_ready, 128); mbar_init(stg_full, 128);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 128); mbar_init(sdp_full, 1); mbar_init(sdp_free, 128);
     for (int i = 0; i < NS; ++i) { mbar_init(k_full(i), 1); mbar_init(k_empty(i), 1); mbar_init(v_full(i), 1); mbar_init(v_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(sdp_full(i), 1); mbar_init(sdp_free(i), 128); mbar_init(ds_full(i), 128); mbar_init(ds_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ds_full(i), 128); mbar_init(ds_empty(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc512(tmem_slot);
@@ -575,18 +617,27 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (lane == 0) {
       uint32_t bc = 0, tc = 0;                       // key-block counter, tile counter
       Tracer tr(g.trace, 3);
+      int pend_w = -1, pend_t = 0;                   // tile whose dQ the compute threads stage into the Q smem tile
+      auto store_pending = [&]() {
+        if (pend_w < 0) return;
+        mbar_wait(stg_full, (tc - 1) & 1u);
+        stg_store<D>(map_dq, q_t, (pend_w % g.H) * D, pend_t * 128, pend_w / g.H);
+        tma_commit();
+        tma_wait_read();
+        pend_w = -1;
+      };
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++tc) {
-          mbar_wait(q_free, (tc & 1u) ^ 1u);           // the previous tile's dQ store has read the staging tile (= the Q tile)
-          mbar_wait(do_empty, (tc & 1u) ^ 1u);
-          tr(1);
-          mbar_expect_tx(qdo_full, 2 * DC * QCH);
+          mbar_wait(do_free, (tc & 1u) ^ 1u);          // the previous tile's dO rows sit in TMEM: its smem tile is free
+          mbar_expect_tx(do_full, DC * QCH);
 #pragma unroll
-          for (int c = 0; c < DC; ++c) {
-            tma_load_3d(q_t + c * QCH, &map_q, qdo_full, col0 + 64 * c, t * 128, b);
-            tma_load_3d(do_t + c * QCH, &map_do, qdo_full, col0 + 64 * c, t * 128, b);
-          }
+          for (int c = 0; c < DC; ++c) tma_load_3d(do_t + c * QCH, &map_do, do_full, col0 + 64 * c, t * 128, b);
+          store_pending();                             // previous tile's dQ leaves the Q smem tile ...
+          tr(1);
+          mbar_expect_tx(q_full, DC * QCH);            // ... and this tile's Q enters it
+#pragma unroll
+          for (int c = 0; c < DC; ++c) tma_load_3d(q_t + c * QCH, &map_q, q_full, col0 + 64 * c, t * 128, b);
           for (int kb = 0; kb < g.n_b; ++kb, ++bc) {           // V stages are released first (after dP), K stages after dQ
             const int st = bc % NS;
             const uint32_t par = ((bc / NS) & 1u) ^ 1u;
@@ -601,22 +652,27 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
             for (int c = 0; c < DC; ++c) tma_load_3d(kr + (st * DC + c) * BCH, &map_k, k_full(st), col0 + 64 * c, kb * 64, b);
           }
+          pend_w = w; pend_t = t;
         }
       }
+      store_pending();
+      tma_wait_all();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issue: the whole warp runs the loop (warp-uniform control flow and operands), one elected lane issues
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_dq = make_idesc(128, D, 0, 1);            // dQ = dS K : A K-major (dS), B MN-major (K block)
       uint32_t bc0 = 0, tc = 0;
-      Tracer tr(g.trace, 4);
+      Tracer tr(lane == 0 ? g.trace : nullptr, 4);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int t = 0; t < g.n_t; ++t, ++tc) {
           const uint32_t tpar = tc & 1u;
-          mbar_wait(qdo_full, tpar);
+          mbar_wait(a_ready, tpar);                                   // Q and dO rows of this tile are in TMEM
           tr(10);
           tc_fence_after();
           // event loop: dQ(j) as soon as its dS block is written (it releases the K stage the next load is waiting for),
-          // otherwise the next S / dP pair as soon as its K, V blocks have landed and its TMEM buffer has been read
+          // otherwise the next S / dP pair as soon as its K, V blocks have landed and the previous pair sits in registers
           int js = 0, jq = 0;                                         // next block to issue S/dP for, next block to issue dQ for
           while (jq < g.n_b) {
             if (jq < js) {
@@ -625,36 +681,43 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               if (mbar_try_wait(ds_full(buf), (c >> 1) & 1u) && (jq > 0 || mbar_try_wait(dq_free, tpar ^ 1u))) {
                 tr(40 + jq);
                 tc_fence_after();
-                const uint32_t kt = kr + st * DC * BCH, dst = ds_t + buf * QCH;
-                for (int kk = 0; kk < nk / 16; ++kk)
-                  tc_mma(tmem + DQ_COL, desc_k(dst + kk * 32u), desc_mn(kt + kk * 2048u, BCH), idesc_dq, (jq > 0 || kk > 0) ? 1u : 0u);
-                tc_commit(ds_empty(buf));
-                tc_commit(k_empty(st));
+                const SDesc kd = sdesc_mn(kr + st * DC * BCH, BCH), dsd = sdesc_k(ds_t + buf * QCH);
+                if (elect_one()) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    if (kk < nk / 16) tc_mma_d(tm + DQ_COL, dsd, kk * 2u, kd, kk * 128u, idesc_dq, (jq > 0 || kk > 0) ? 1u : 0u);
+                  tc_commit(ds_empty(buf));
+                  tc_commit(k_empty(st));
+                }
+                __syncwarp();
                 ++jq;
                 continue;
               }
             }
             if (js < g.n_b && js < jq + 2) {
               const uint32_t c = bc0 + js;
-              const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * js);
-              if (mbar_try_wait(k_full(st), (c / NS) & 1u) && mbar_try_wait(v_full(st), (c / NS) & 1u) &&
-                  mbar_try_wait(sdp_free(buf), ((c >> 1) & 1u) ^ 1u)) {
+              const int st = c % NS, nk = min(64, g.NK - 64 * js);
+              if (mbar_try_wait(k_full(st), (c / NS) & 1u) && mbar_try_wait(v_full(st), (c / NS) & 1u) && mbar_try_wait(sdp_free, (c & 1u) ^ 1u)) {
                 tr(20 + js);
                 tc_fence_after();
-                const uint32_t idesc_s = make_idesc(128, nk, 0, 0), kt = kr + st * DC * BCH, vt = vr + st * DC * BCH;
+                const uint32_t idesc_s = make_idesc(128, nk, 0, 0);
+                const SDesc kd = sdesc_k(kr + st * DC * BCH), vd = sdesc_k(vr + st * DC * BCH);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf), kdesc(q_t, QCH, k), kdesc(kt, BCH, k), idesc_s, k > 0);
+                  for (int k = 0; k < KS; ++k) tc_mma_ts_d(tm + S_COL, tm + (uint32_t)(QA_COL + 8 * k), kd, kstep_off(k, BCH), idesc_s, k > 0);
 #pragma unroll
-                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(128 * buf + 64), kdesc(do_t, QCH, k), kdesc(vt, BCH, k), idesc_s, k > 0);
-                tc_commit(sdp_full(buf));
-                tc_commit(v_empty(st));
+                  for (int k = 0; k < KS; ++k) tc_mma_ts_d(tm + DP_COL, tm + (uint32_t)(DOA_COL + 8 * k), vd, kstep_off(k, BCH), idesc_s, k > 0);
+                  tc_commit(sdp_full);
+                  tc_commit(v_empty(st));
+                }
+                __syncwarp();
                 ++js;
               }
             }
           }
           tr(14);
-          tc_commit(dq_full);
-          tc_commit(do_empty);
+          if (elect_one()) tc_commit(dq_full);
+          __syncwarp();
           bc0 += g.n_b;
         }
       }
@@ -663,7 +726,6 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // ---------------------------------------------------------------- thread = query row
     const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    const bool leader = threadIdx.x == 64;
     const float sc2 = g.scale * LOG2E;
     uint32_t bc0 = 0, tc = 0;
     Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 5);
@@ -680,95 +742,114 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int row_g = t * 128 + row;
         const bool row_on = row_g < g.S;
         const bool warp_on = t * 128 + quad * 32 < g.S;
-        // delta = rowsum(dO * O): this row of O comes from global memory (D contiguous bf16) and is requested BEFORE the wait
-        // for the Q / dO tiles so that its latency overlaps theirs; dO is read from the smem tile
+        // this row of O comes from global memory and is requested BEFORE the wait for the dO tile so that the latencies overlap
         uint4 orow[D / 8];
         if (row_on) {
           const bf16* op = g.o + ((int64_t)b * g.S + row_g) * g.ldo + col0;
 #pragma unroll
           for (int c8 = 0; c8 < D / 8; ++c8) orow[c8] = __ldg(reinterpret_cast<const uint4*>(op + 8 * c8));
         }
-        mbar_wait(qdo_full, tpar);
-        tr(50);
         float delta = 0.f, lse2 = 1e30f, qq = 0.f;
-        if (row_on) {
+        mbar_wait(do_full, tpar);
+        tr(50);
+        {                                                // dO row -> TMEM (rows beyond S were zero-filled by TMA); delta = rowsum(dO * O)
           float d4[4] = {0.f, 0.f, 0.f, 0.f};
+          row_to_tmem<D>(do_t, row, t_lane + DOA_COL, [&](int c, const uint32_t (&r)[16], int n) {
+            if (row_on) {
 #pragma unroll
-          for (int c8 = 0; c8 < D / 8; ++c8) {
-            uint32_t a0, a1, a2, a3;
-            lds128(swz(do_t + (uint32_t)(c8 >> 3) * QCH, row, c8 & 7), a0, a1, a2, a3);
-            const uint4 ov = orow[c8];
-            d4[0] = fmaf(bf16_lo(a0), bf16_lo(ov.x), d4[0]); d4[1] = fmaf(bf16_hi(a0), bf16_hi(ov.x), d4[1]);
-            d4[2] = fmaf(bf16_lo(a1), bf16_lo(ov.y), d4[2]); d4[3] = fmaf(bf16_hi(a1), bf16_hi(ov.y), d4[3]);
-            d4[0] = fmaf(bf16_lo(a2), bf16_lo(ov.z), d4[0]); d4[1] = fmaf(bf16_hi(a2), bf16_hi(ov.z), d4[1]);
-            d4[2] = fmaf(bf16_lo(a3), bf16_lo(ov.w), d4[2]); d4[3] = fmaf(bf16_hi(a3), bf16_hi(ov.w), d4[3]);
-          }
+              for (int i = 0; i < 4; ++i)
+                if (4 * i < n) {
+                  const uint4 ov = orow[(c >> 2) + i];
+                  d4[0] = fmaf(bf16_lo(r[4 * i]), bf16_lo(ov.x), d4[0]); d4[1] = fmaf(bf16_hi(r[4 * i]), bf16_hi(ov.x), d4[1]);
+                  d4[2] = fmaf(bf16_lo(r[4 * i + 1]), bf16_lo(ov.y), d4[2]); d4[3] = fmaf(bf16_hi(r[4 * i + 1]), bf16_hi(ov.y), d4[3]);
+                  d4[0] = fmaf(bf16_lo(r[4 * i + 2]), bf16_lo(ov.z), d4[0]); d4[1] = fmaf(bf16_hi(r[4 * i + 2]), bf16_hi(ov.z), d4[1]);
+                  d4[2] = fmaf(bf16_lo(r[4 * i + 3]), bf16_lo(ov.w), d4[2]); d4[3] = fmaf(bf16_hi(r[4 * i + 3]), bf16_hi(ov.w), d4[3]);
+                }
+            }
+          });
           delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        }
+        if (row_on) {
           g.delta[(int64_t)w * g.S + row_g] = delta;
           lse2 = __ldg(g.lse + (int64_t)w * g.S + row_g) * LOG2E;
-          if (MODE == VG_ATTN_L2) qq = row_sqnorm<D>(g.q + ((int64_t)b * g.S + row_g) * g.ld + col0);
         }
+        mbar_arrive(do_free);                            // the dO smem tile has been read: the next tile's may be fetched
+        mbar_wait(q_full, tpar);
+        row_to_tmem<D>(q_t, row, t_lane + QA_COL, [&](int c, const uint32_t (&r)[16], int n) {
+          if (MODE == VG_ATTN_L2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < n) { const float a = bf16_lo(r[i]), bb = bf16_hi(r[i]); qq = fmaf(a, a, qq); qq = fmaf(bb, bb, qq); }
+          }
+        });
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(a_ready);                            // both operand rows are in TMEM; the Q smem tile is free (dQ staging)
+        tr(51);
         float gsum = 0.f;
         for (int j = 0; j < g.n_b; ++j) {
           const uint32_t c = bc0 + j;
-          const int buf = c & 1, nk = min(64, g.NK - 64 * j);
-          if (j == 0) tr(51);
-          mbar_wait(sdp_full(buf), (c >> 1) & 1u);
+          const int buf = c & 1, nk = min(64, g.NK - 64 * j), c0 = 64 * j;
+          uint32_t s0[32], s1[32], p0[32], p1[32], pk[16];
+          mbar_wait(sdp_full, c & 1u);
           tr(60 + j);
           tc_fence_after();
+          if (warp_on) {                                 // the whole block into registers, then the TMEM pair is released at once
+            if (nk >= 32) { tmem_ld32_nowait(t_lane + S_COL, s0); tmem_ld32_nowait(t_lane + DP_COL, p0); }
+            else { tmem_ld16p(t_lane + S_COL, s0); tmem_ld16p(t_lane + DP_COL, p0); }
+            if (nk == 64) { tmem_ld32_nowait(t_lane + S_COL + 32, s1); tmem_ld32_nowait(t_lane + DP_COL + 32, p1); }
+            else if (nk == 48) { tmem_ld16p(t_lane + S_COL + 32, s1); tmem_ld16p(t_lane + DP_COL + 32, p1); }
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          mbar_arrive(sdp_free);                         // the next S / dP pair is computed while this one is exponentiated
           mbar_wait(ds_empty(buf), ((c >> 1) & 1u) ^ 1u);           // dQ MMA of block j-2 has consumed this dS buffer
           tr(70 + j);
           if (warp_on) {
             const uint32_t tile = ds_t + buf * QCH;
-#pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
-              if (cc >= nk) break;
-              uint32_t sv[32], dv[32], pk[16];
-              const int c0 = 64 * j + cc;
-              if (nk - cc >= 32) {
-                tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + cc), sv);
-                tmem_ld32_nowait(t_lane + (uint32_t)(128 * buf + 64 + cc), dv);
-                tmem_ld_wait();
-                if (c0 + 32 <= g.S) dq_group<32, false, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-                else dq_group<32, true, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-                put_row<32>(tile, row, cc, pk);
-              } else {
-                tmem_ld16p(t_lane + (uint32_t)(128 * buf + cc), sv);
-                tmem_ld16p(t_lane + (uint32_t)(128 * buf + 64 + cc), dv);
-                tmem_ld_wait();
-                if (c0 + 16 <= g.S) dq_group<16, false, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-                else dq_group<16, true, MODE>(sv, dv, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-                put_row<16>(tile, row, cc, pk);
-              }
+            if (nk >= 32) {
+              if (c0 + 32 <= g.S) dq_group<32, false, MODE>(s0, p0, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+              else dq_group<32, true, MODE>(s0, p0, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+              put_row<32>(tile, row, 0, pk);
+            } else {
+              dq_group<16, true, MODE>(s0, p0, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+              put_row<16>(tile, row, 0, pk);
+            }
+            if (nk == 64) {
+              if (c0 + 64 <= g.S) dq_group<32, false, MODE>(s1, p1, c0 + 32, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+              else dq_group<32, true, MODE>(s1, p1, c0 + 32, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+              put_row<32>(tile, row, 32, pk);
+            } else if (nk == 48) {
+              dq_group<16, true, MODE>(s1, p1, c0 + 32, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
+              put_row<16>(tile, row, 32, pk);
             }
           }
-          tc_fence_before();
-          mbar_arrive(sdp_free(buf));
           fence_async_smem();
           mbar_arrive(ds_full(buf));
           tr(80 + j);
         }
         bc0 += g.n_b;
-        // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> staging over the Q tile -> TMA store
-        mbar_wait(dq_full, tpar);                       // every MMA of the tile is complete: Q tile no longer read
+        // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> staging over the Q smem tile -> TMA store by the producer warp
+        mbar_wait(dq_full, tpar);                       // every MMA of the tile is complete (the TMEM operand rows may be replaced)
         tr(55);
         tc_fence_after();
-        float qrow[MODE == VG_ATTN_L2 ? D : 1];
-        if (MODE == VG_ATTN_L2) {
-          if (warp_on) read_tile_row<D>(q_t, QCH, row, qrow);
-          named_bar(1, 128);                            // staging sub-tiles do not coincide with the operand chunks
-        }
         if (warp_on) {
 #pragma unroll
           for (int c = 0; c < D; c += 32) {
-            uint32_t v[32];
+            uint32_t v[32], qv[16];
             const int n = (D - c) >= 32 ? 32 : 16;
+            if (MODE == VG_ATTN_L2) {                    // the q row is still in TMEM (operand columns, two bf16 per column)
+              if (n == 32) tmem_ld16p(t_lane + (uint32_t)(QA_COL + (c >> 1)), qv);
+              else asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                : "=r"(qv[0]), "=r"(qv[1]), "=r"(qv[2]), "=r"(qv[3]), "=r"(qv[4]), "=r"(qv[5]), "=r"(qv[6]), "=r"(qv[7])
+                                : "r"(t_lane + (uint32_t)(QA_COL + (c >> 1))));
+            }
             tmem_ldn(t_lane + (uint32_t)(DQ_COL + c), v, n);
             float o[32];
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
               o[jj] = __uint_as_float(v[jj]);
-              if (MODE == VG_ATTN_L2 && jj < n) o[jj] = fmaf(gsum, qrow[(c + jj) < D ? (c + jj) : 0], -o[jj]);
+              if (MODE == VG_ATTN_L2 && jj < n) o[jj] = fmaf(gsum, (jj & 1) ? bf16_hi(qv[jj >> 1]) : bf16_lo(qv[jj >> 1]), -o[jj]);
             }
             stg_write<D>(q_t, row, c, o, n);
           }
@@ -776,17 +857,10 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tc_fence_before();
         mbar_arrive(dq_free);
         fence_async_smem();
-        named_bar(1, 128);
+        mbar_arrive(stg_full);
         tr(56);
-        if (leader) {
-          stg_store<D>(map_dq, q_t, col0, t * 128, b);
-          tma_commit();
-          tma_wait_read();
-          mbar_arrive(q_free);
-        }
       }
     }
-    if (leader) tma_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -801,8 +875,9 @@ template <int D> struct DkvCfg {
   static constexpr int K_OFF = 0, V_OFF = DC * QCH, QR_OFF = 2 * DC * QCH, DOR_OFF = QR_OFF + NS * DC * BCH;
   static constexpr int PT_OFF = DOR_OFF + NS * DC * BCH, DST_OFF = PT_OFF + QCH;
   static constexpr int LSE_OFF = DST_OFF + QCH, DEL_OFF = LSE_OFF + MAXNK * 4, QN_OFF = DEL_OFF + MAXNK * 4;
-  static constexpr int NBAR = 8 + 2 * NS + 6;
+  static constexpr int NBAR = 8 + 2 * NS + 7;
   static constexpr int smem(int mode) { return (mode == VG_ATTN_L2 ? QN_OFF + MAXNK * 4 : QN_OFF) + NBAR * 8 + 16; }
+  static_assert(NS * DC * BCH >= 128 * D * 2, "the dK / dV staging tiles alias the Q and dO rings");
 };
 
 template <int D, int MODE>
@@ -820,13 +895,14 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   float* lse_s = reinterpret_cast<float*>(smem_dyn + C::LSE_OFF);
   float* del_s = reinterpret_cast<float*>(smem_dyn + C::DEL_OFF);
   float* qn_s = reinterpret_cast<float*>(smem_dyn + C::QN_OFF);      // L2 mode only
-  const uint32_t kvt_full = bar, kvt_free = bar + 8, out_full = bar + 16, out_free = bar + 24;
+  const uint32_t kvt_full = bar, kvt_empty = bar + 8, out_full = bar + 16, out_free = bar + 24;
   const uint32_t pt_full = bar + 32, pt_empty = bar + 40, dst_full = bar + 48, dst_empty = bar + 56;
   auto qdo_full = [&](int i) { return bar + 8u * (8 + i); };
   auto qdo_empty = [&](int i) { return bar + 8u * (8 + NS + i); };
   auto st_full = [&](int i) { return bar + 8u * (8 + 2 * NS + i); };
   auto st_free = [&](int i) { return bar + 8u * (10 + 2 * NS + i); };
   auto dpt_full = [&](int i) { return bar + 8u * (12 + 2 * NS + i); };
+  const uint32_t stg_full = bar + 8u * (14 + 2 * NS);
   const uint32_t tmem_slot = bar + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + BAR_OFF + 8 * C::NBAR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -837,7 +913,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
-    mbar_init(kvt_full, 1); mbar_init(kvt_free, 1); mbar_init(out_full, 1); mbar_init(out_free, 128);
+    mbar_init(kvt_full, 1); mbar_init(kvt_empty, 1); mbar_init(out_full, 1); mbar_init(out_free, 128); mbar_init(stg_full, 128);
     mbar_init(pt_full, 128); mbar_init(pt_empty, 1); mbar_init(dst_full, 128); mbar_init(dst_empty, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(qdo_full(i), 1); mbar_init(qdo_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(st_full(i), 1); mbar_init(st_free(i), 128); mbar_init(dpt_full(i), 1); }
@@ -856,17 +932,28 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     if (lane == 0) {
       uint32_t bc = 0, ic = 0;                       // query-block counter, item (key tile) counter
       Tracer tr(g.trace, 6);
+      int pend_w = -1, pend_t = 0;                   // item whose dK / dV the compute threads stage over the (then idle) Q / dO ring
+      auto store_pending = [&]() {
+        if (pend_w < 0) return;
+        mbar_wait(stg_full, (ic - 1) & 1u);
+        stg_store<D>(map_dk, qr, (pend_w % g.H) * D, pend_t * 128, pend_w / g.H);
+        stg_store<D>(map_dv, dor, (pend_w % g.H) * D, pend_t * 128, pend_w / g.H);
+        tma_commit();
+        tma_wait_read();
+        pend_w = -1;
+      };
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++ic) {
-          mbar_wait(kvt_free, (ic & 1u) ^ 1u);         // previous item's dK/dV stores have read the staging (= the K, V tiles)
+          mbar_wait(kvt_empty, (ic & 1u) ^ 1u);        // every MMA of the previous item is complete: its K, V tiles are dead ...
           tr(1);
-          mbar_expect_tx(kvt_full, 2 * DC * QCH);
+          mbar_expect_tx(kvt_full, 2 * DC * QCH);      // ... and the next ones are fetched while its dK / dV are drained and stored
 #pragma unroll
           for (int c = 0; c < DC; ++c) {
             tma_load_3d(k_t + c * QCH, &map_k, kvt_full, col0 + 64 * c, t * 128, b);
             tma_load_3d(v_t + c * QCH, &map_v, kvt_full, col0 + 64 * c, t * 128, b);
           }
+          store_pending();                             // the ring is refilled only after the staged outputs have been read from it
           for (int i = 0; i < g.n_b; ++i, ++bc) {
             const int st = bc % NS;
             mbar_wait(qdo_empty(st), ((bc / NS) & 1u) ^ 1u);
@@ -878,14 +965,20 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
               tma_load_3d(dor + (st * DC + c) * BCH, &map_do, qdo_full(st), col0 + 64 * c, i * 64, b);
             }
           }
+          pend_w = w; pend_t = t;
         }
       }
+      store_pending();
+      tma_wait_all();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issue: the whole warp runs the loop (warp-uniform control flow and operands), one elected lane issues
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_kv = make_idesc(128, D, 0, 1);            // dV = P^T dO, dK = dS^T Q : A K-major, B MN-major
+      const SDesc ktd = sdesc_k(k_t), vtd = sdesc_k(v_t), ptd = sdesc_k(pt_t), dstd = sdesc_k(dst_t);
       uint32_t bc0 = 0, ic = 0;
-      Tracer tr(g.trace, 7);
+      Tracer tr(lane == 0 ? g.trace : nullptr, 7);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int t = 0; t < g.n_t; ++t, ++ic) {
           const uint32_t ipar = ic & 1u;
@@ -902,11 +995,15 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
               if (mbar_try_wait(dst_full, c & 1u)) {
                 tr(45 + ik);
                 tc_fence_after();
-                const uint32_t qt = qr + st * DC * BCH;
-                for (int kk = 0; kk < ni / 16; ++kk)
-                  tc_mma(tmem + DK_COL, desc_k(dst_t + kk * 32u), desc_mn(qt + kk * 2048u, BCH), idesc_kv, (ik > 0 || kk > 0) ? 1u : 0u);
-                tc_commit(dst_empty);
-                tc_commit(qdo_empty(st));
+                const SDesc qd = sdesc_mn(qr + st * DC * BCH, BCH);
+                if (elect_one()) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    if (kk < ni / 16) tc_mma_d(tm + DK_COL, dstd, kk * 2u, qd, kk * 128u, idesc_kv, (ik > 0 || kk > 0) ? 1u : 0u);
+                  tc_commit(dst_empty);
+                  tc_commit(qdo_empty(st));
+                }
+                __syncwarp();
                 ++ik;
                 continue;
               }
@@ -917,13 +1014,18 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
               if (mbar_try_wait(pt_full, c & 1u) && (ip > 0 || mbar_try_wait(out_free, ipar ^ 1u))) {   // P^T in smem; S^T fully read
                 tr(40 + ip);
                 tc_fence_after();
-                const uint32_t dot = dor + st * DC * BCH, idesc_s = make_idesc(128, ni, 0, 0);
+                const uint32_t idesc_s = make_idesc(128, ni, 0, 0);
+                const SDesc dok = sdesc_k(dor + st * DC * BCH), dom = sdesc_mn(dor + st * DC * BCH, BCH);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(v_t, QCH, k), kdesc(dot, BCH, k), idesc_s, k > 0);
-                tc_commit(dpt_full(buf));
-                for (int kk = 0; kk < ni / 16; ++kk)
-                  tc_mma(tmem + DV_COL, desc_k(pt_t + kk * 32u), desc_mn(dot + kk * 2048u, BCH), idesc_kv, (ip > 0 || kk > 0) ? 1u : 0u);
-                tc_commit(pt_empty);
+                  for (int k = 0; k < KS; ++k) tc_mma_d(tm + (uint32_t)(64 * buf), vtd, kstep_off(k, QCH), dok, kstep_off(k, BCH), idesc_s, k > 0);
+                  tc_commit(dpt_full(buf));
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    if (kk < ni / 16) tc_mma_d(tm + DV_COL, ptd, kk * 2u, dom, kk * 128u, idesc_kv, (ip > 0 || kk > 0) ? 1u : 0u);
+                  tc_commit(pt_empty);
+                }
+                __syncwarp();
                 ++ip;
                 continue;
               }
@@ -934,15 +1036,20 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
               if (mbar_try_wait(qdo_full(st), (c / NS) & 1u) && mbar_try_wait(st_free(buf), ((c >> 1) & 1u) ^ 1u)) {
                 tr(20 + is);
                 tc_fence_after();
-                const uint32_t idesc_s = make_idesc(128, ni, 0, 0), qt = qr + st * DC * BCH;
+                const uint32_t idesc_s = make_idesc(128, ni, 0, 0);
+                const SDesc qk = sdesc_k(qr + st * DC * BCH);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < KS; ++k) tc_mma(tmem + (uint32_t)(64 * buf), kdesc(k_t, QCH, k), kdesc(qt, BCH, k), idesc_s, k > 0);
-                tc_commit(st_full(buf));
+                  for (int k = 0; k < KS; ++k) tc_mma_d(tm + (uint32_t)(64 * buf), ktd, kstep_off(k, QCH), qk, kstep_off(k, BCH), idesc_s, k > 0);
+                  tc_commit(st_full(buf));
+                }
+                __syncwarp();
                 ++is;
               }
             }
           }
-          tc_commit(out_full);
+          if (elect_one()) { tc_commit(out_full); tc_commit(kvt_empty); }
+          __syncwarp();
           tr(14);
           bc0 += g.n_b;
         }
@@ -952,7 +1059,6 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     // ---------------------------------------------------------------- thread = key row
     const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    const bool leader = threadIdx.x == 64;
     const float sc2 = g.scale * LOG2E;
     uint32_t bc0 = 0, ic = 0;
     Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 8);
@@ -1041,24 +1147,29 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
         mbar_wait(out_full, ipar);
         tr(55);
         tc_fence_after();
-        float krow[MODE == VG_ATTN_L2 ? D : 1];
-        if (MODE == VG_ATTN_L2) {
-          if (warp_on) read_tile_row<D>(k_t, QCH, row, krow);
-          named_bar(1, 128);
-        }
+        const bf16* kg = g.k + ((int64_t)b * g.S + min(key_g, g.S - 1)) * g.ld + col0;    // L2: this key's row (the smem K tile is being refilled)
         if (warp_on) {
 #pragma unroll
           for (int c = 0; c < D; c += 32) {
             uint32_t v[32];
             const int n = (D - c) >= 32 ? 32 : 16;
+            uint4 kv4[4];
+            if (MODE == VG_ATTN_L2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) if (8 * i < n) kv4[i] = __ldg(reinterpret_cast<const uint4*>(kg + c + 8 * i));
+            }
             tmem_ldn(t_lane + (uint32_t)(DK_COL + c), v, n);
             float o[32];
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
               o[jj] = __uint_as_float(v[jj]);
-              if (MODE == VG_ATTN_L2 && jj < n) o[jj] = fmaf(gsum, krow[(c + jj) < D ? (c + jj) : 0], -o[jj]);
+              if (MODE == VG_ATTN_L2 && jj < n) {
+                const uint4 q4 = kv4[jj >> 3];
+                const uint32_t u = ((jj >> 1) & 3) == 0 ? q4.x : ((jj >> 1) & 3) == 1 ? q4.y : ((jj >> 1) & 3) == 2 ? q4.z : q4.w;
+                o[jj] = fmaf(gsum, (jj & 1) ? bf16_hi(u) : bf16_lo(u), -o[jj]);
+              }
             }
-            stg_write<D>(k_t, row, c, o, n);
+            stg_write<D>(qr, row, c, o, n);
           }
 #pragma unroll
           for (int c = 0; c < D; c += 32) {
@@ -1068,24 +1179,16 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             float o[32];
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(v[jj]);
-            stg_write<D>(v_t, row, c, o, n);
+            stg_write<D>(dor, row, c, o, n);
           }
         }
         tc_fence_before();
         mbar_arrive(out_free);
         fence_async_smem();
-        named_bar(1, 128);
+        mbar_arrive(stg_full);
         tr(56);
-        if (leader) {
-          stg_store<D>(map_dk, k_t, col0, t * 128, b);
-          stg_store<D>(map_dv, v_t, col0, t * 128, b);
-          tma_commit();
-          tma_wait_read();
-          mbar_arrive(kvt_free);
-        }
       }
     }
-    if (leader) tma_wait_all();
   }
   tc_fence_before();
   __syncthreads();

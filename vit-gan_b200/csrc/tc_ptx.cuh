@@ -144,6 +144,50 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 
+// ---- cheap descriptor arithmetic for MMA issue loops.  One thread issues every MMA of a CTA, and at N <= 128 an MMA lasts only
+// 32-64 clk, so rebuilding the 64-bit shared-memory descriptor (shift / mask / or on the uniform datapath: a ~60 clk dependent
+// chain per instruction) made the issue loop, not the tensor pipe, the bound.  A descriptor is kept as (lo, hi) words: the tile
+// address (>> 4) and LBO live in lo, everything else in hi, so stepping through a tile is ONE 32-bit add of a compile-time
+// constant (tiles are < 256 KB and 16 B aligned: the 14-bit address field never carries).
+// one lane of a converged warp (the form CUTLASS uses around every tcgen05.mma / commit: the rest of the issue loop then runs
+// warp-uniformly, and the compiler keeps descriptors and TMEM addresses in uniform registers instead of re-electing per operand)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, lane_id = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+               "elect.sync rx|px, %2;\n\t"
+               "@px mov.s32 %1, 1;\n\t"
+               "mov.s32 %0, rx;\n\t}" : "+r"(lane_id), "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+struct SDesc { uint32_t lo, hi; };
+__device__ __forceinline__ SDesc sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  SDesc d;
+  d.lo = ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);      // SBO, descriptor version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+  return d;
+}
+__device__ __forceinline__ SDesc sdesc_k(uint32_t addr) { return sdesc(addr, 16u, 1024u); }                  // K-major operand tile
+__device__ __forceinline__ SDesc sdesc_mn(uint32_t addr, uint32_t lbo) { return sdesc(addr, lbo, 1024u); }   // MN-major operand tile
+// byte offset (>> 4) of k-step k inside a K-major tile made of 64-column chunks `chunk_bytes` apart
+__host__ __device__ constexpr uint32_t kstep_off(int k, uint32_t chunk_bytes) { return (uint32_t)(((k >> 2) * chunk_bytes + (k & 3) * 32u) >> 4); }
+__device__ __forceinline__ void tc_mma_d(uint32_t d_tmem, SDesc a, uint32_t a_off, SDesc b, uint32_t b_off, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a.lo + a_off), "r"(a.hi), "r"(b.lo + b_off), "r"(b.hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_d(uint32_t d_tmem, uint32_t a_tmem, SDesc b, uint32_t b_off, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b.lo + b_off), "r"(b.hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // ---- attention-side helpers: 3-D tensor copies, 16-column TMEM loads, descriptor shorthands, swizzled tile addressing
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
