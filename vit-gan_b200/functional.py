@@ -316,7 +316,12 @@ def acc_wgrad(dy2, x2, params, bias_params=None):
         return ops.gemm(dy2, x2, trans_a=True, trans_b=False, accumulate=True)
     bview = _grad_view(bias_params, 1, dy2.shape[1]) if view is not None else None
     key = (dy2.dtype, dy2.shape[1], x2.shape[1])
-    if _FUSE_BIAS_IN_WGRAD and bview is not None and dy2.dtype == torch.bfloat16 and key not in _wgrad_bias_unsupported:
+    # The fused bias gradient (a_rowsum: 16 more TMEM columns) only exists in the 128-wide GEMM.  Compute-bound weight gradients
+    # (the scaled config: K = 65 792 tokens, N = 768 a multiple of 256) run ~1.6x faster on the 256-wide tile, whose two accumulator
+    # stages fill the TMEM -- there the bias gradient is the memory-bound column-sum kernel, issued like the GEMM on the
+    # parameter-gradient stream where it overlaps compute-bound work.  Mirrors the tile heuristic of gemm_tc_launch.
+    wide = (x2.shape[1] % 256 == 0 and dy2.shape[0] >= 4096 and ((dy2.shape[1] + 127) // 128) * (x2.shape[1] // 256) >= 8)
+    if _FUSE_BIAS_IN_WGRAD and not wide and bview is not None and dy2.dtype == torch.bfloat16 and key not in _wgrad_bias_unsupported:
         try:
             _wgrad_gemm(dy2, x2, view, bview.view(-1))
             _notify(params)
@@ -332,7 +337,16 @@ def acc_wgrad(dy2, x2, params, bias_params=None):
 def acc_colsum(dy2, params):
     view = _grad_view(params, 1, dy2.shape[1])
     if view is not None:
-        ops.colsum(dy2, out=view.view(-1))
+        if _PG_STREAM_ON and dy2.shape[1] > 256:    # feeds nothing but .grad: off the critical path, like the weight-gradient GEMMs
+            # (wider than 256 columns the kernel takes no shared replica workspace, so it may overlap a main-stream column sum)
+            idx, side = _pg_side(dy2.device)
+            side.wait_stream(torch.cuda.current_stream(idx))
+            with torch.cuda.stream(side):
+                ops.colsum(dy2, out=view.view(-1))
+            _pg_forked.add(idx)
+            _pg_keepalive.append((dy2,))
+        else:
+            ops.colsum(dy2, out=view.view(-1))
         _notify(params)
         return None
     return ops.colsum(dy2)
