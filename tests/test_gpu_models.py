@@ -11,8 +11,8 @@ from oracle import harness, v1 as o1, v2 as o2
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
-# gradients pass through more roundings than outputs; bf16 gradient tensors are compared at 3x the block tolerance
-GTOL = {"fp32": 2e-4, "bf16": 6e-2}
+# gradients are held to the same BASELINE.json tolerances as the outputs (per tensor, max|a-b| / max|b|)
+GTOL = {"fp32": 1e-4, "bf16": 2e-2}
 
 
 @pytest.fixture(scope="module")
@@ -303,13 +303,14 @@ def test_v1_default_vs_reference_golden_and_oracle(vb, prec, golden):
         assert rel(D(real.cuda()), fx["d_out"]) < TOL[prec]
         g = G(z.cuda())
     assert g.shape == (fx["batch"], 3, I, I)
-    # sin(30*(.)) twice: the bf16 path's activation rounding is amplified by omega_0 = 30 per SIREN layer
-    assert rel(g[:, :, :4, :4], fx["g_out_slice"]) < (TOL[prec] if prec == "fp32" else 0.25)
+    # sin(30 (.)) twice (SIREN, omega_0 = 30): measured 1.2e-6 (fp32) / 7.9e-3 (bf16); the bf16 figure is the rounding of the parameters
+    # and inputs themselves (the fp32 oracle on bf16-rounded parameters differs from the fp32 oracle by 9.5e-3)
+    assert rel(g[:, :, :4, :4], fx["g_out_slice"]) < TOL[prec]
     go = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
     do = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
     losses = torch.stack([torch.stack(vb.train.gan_step(G, D, go, do, r.cuda(), zz.cuda(), "bce"))
                           for r, zz in harness.synthetic_batches_v1(ocfg, fx["batch"], 2)])
-    assert rel(losses, fx["losses"]) < (5e-4 if prec == "fp32" else 5e-2)
+    assert rel(losses, fx["losses"]) < TOL[prec]          # measured 2.8e-7 (fp32) / 4.3e-3 (bf16)
     # Q4: the discriminator's q/k/v never receive gradients / updates
     assert all(p.grad is None for n, p in D.named_parameters() if n.endswith((".q.weight", ".k.weight", ".v.weight")))
 
@@ -339,7 +340,7 @@ def test_v1_full_grads_vs_oracle_64px(vb):
     loss = F.binary_cross_entropy(out, torch.ones(2, 1, device="cuda")) + F.binary_cross_entropy(D(fake), torch.ones(2, 1, device="cuda"))
     loss.backward()
     for name, mod in (("generator.", G), ("discriminator.", D)):
-        cmp_grads({k: p.grad for k, p in mod.named_parameters()}, {k: orc.p[name + k].grad for k, _ in mod.named_parameters()}, 5e-4, name)
+        cmp_grads({k: p.grad for k, p in mod.named_parameters()}, {k: orc.p[name + k].grad for k, _ in mod.named_parameters()}, GTOL["fp32"], name)
     vb.set_precision("bf16")
 
 
@@ -380,9 +381,14 @@ def test_v2_200_step_loss_curve(vb):
     horizon = int((ref_dev < 1e-2).sum())
     assert horizon >= 40
     assert (gpu_dev[:horizon] <= 30 * ref_dev[:horizon] + 1e-5).all(), (gpu_dev[:horizon] / (ref_dev[:horizon] + 1e-12)).max()
-    # after decorrelation only the regime can be compared: mean losses of the last 50 steps within a factor 3
-    ratio = gpu[-50:].mean(0) / f64[-50:].mean(0)
-    assert ((ratio > 1 / 3) & (ratio < 3)).all(), ratio
+    # after decorrelation only the regime can be compared, and even that only loosely: the fp32 path's own run-to-run variation
+    # (split-K / atomic accumulation order) is amplified by the same chaotic dynamics, and the generator loss of a collapsing
+    # discriminator swings by a factor of several between two runs of the SAME code.  Mean losses of the last 80 steps within a
+    # factor 6, and the CUDA curve stays in the range the fp32 and fp64 references themselves visit.
+    ratio = gpu[-80:].mean(0) / f64[-80:].mean(0)
+    assert ((ratio > 1 / 6) & (ratio < 6)).all(), ratio
+    hi = 3 * torch.maximum(f32.amax(0), f64.amax(0))
+    assert (gpu.amax(0) <= hi).all(), (gpu.amax(0), hi)
     bf = run_cuda("bf16", 40)
     assert torch.isfinite(bf).all() and rel(bf[:10], f32[:10]) < 2e-2
     vb.set_precision("bf16")
@@ -605,3 +611,129 @@ def test_patched_reference_v1_two_step_curve(vb):
         got = torch.stack([torch.stack(harness.gan_step(G, D, go, do, r.cuda(), z.cuda(), "bce")).cpu() for r, z in batches])
         assert rel(got, want) < tol, (prec, got, want)
     vb.set_precision("bf16")
+
+
+def test_v1_full_grads_vs_oracle_64px_bf16(vb):
+    """Config C3 geometry (64 px: G S=64 F=384 d=96, D S=65 F=432 d=108 -> 112 on the tcgen05 attention path) in bf16: outputs and
+    every parameter gradient of one D pass and one G pass against the fp32 oracle on bf16-rounded parameters and inputs, 2e-2."""
+    vb.set_precision("bf16")
+    cfg = o1.V1Config(image_size=64)
+    base = harness.OracleV1(cfg, seed=3)
+    orc = harness.OracleV1(cfg, seed=3, params={k: bf16_round(v.detach()) for k, v in base.p.items()})
+    G = vb.v1.Generator(vb.v1.V1Config(image_size=64)); D = vb.v1.Discriminator(vb.v1.V1Config(image_size=64))
+    G.load_state_dict({k[len("generator."):]: v.detach() for k, v in orc.p.items() if k.startswith("generator.")})
+    D.load_state_dict({k[len("discriminator."):]: v.detach() for k, v in orc.p.items() if k.startswith("discriminator.")})
+    for blk in D.transformer_layers:
+        for hd in blk.msha.attention_heads:
+            hd.init_spectrum = [torch.linalg.svdvals(w.weight.detach()).max() for w in (hd.q, hd.k, hd.v)]
+        blk.msha.train_qkv = True
+    G, D = G.cuda(), D.cuda()
+    (real, z), = harness.synthetic_batches_v1(cfg, 2, 1, seed=5)
+    real, z = bf16_round(real), bf16_round(z)
+    out_o = orc.discriminator(real)
+    fake_o = orc.generator(z)
+    loss_o = F.binary_cross_entropy(out_o, torch.ones(2, 1)) + F.binary_cross_entropy(orc.discriminator(fake_o), torch.ones(2, 1))
+    loss_o.backward()
+    assert vb.lib.lib.vg_attention_path(1, 1, 2, 4, 65, 112) == 2 and vb.lib.lib.vg_attention_path(1, 0, 2, 4, 64, 96) == 2
+    out = D(real.cuda())
+    fake = G(z.cuda())
+    assert rel(out, out_o) < TOL["bf16"] and rel(fake, fake_o) < TOL["bf16"]
+    loss = F.binary_cross_entropy(out.float(), torch.ones(2, 1, device="cuda")) + F.binary_cross_entropy(D(fake).float(), torch.ones(2, 1, device="cuda"))
+    loss.backward()
+    for name, mod in (("generator.", G), ("discriminator.", D)):
+        cmp_grads({k: p.grad for k, p in mod.named_parameters()}, {k: orc.p[name + k].grad for k, _ in mod.named_parameters()}, GTOL["bf16"], name)
+
+
+def test_v2_c4_geometry_encoder_block_grads(vb):
+    """One Encoder block at the geometry of BASELINE configs[3] (E=768, H=4 -> d=192, S=257, mlp 1536) in bf16: output, input gradient
+    and every parameter gradient against the fp32 oracle on bf16-rounded parameters / inputs at 2e-2.  The attention core runs on
+    the multi-tile tcgen05 kernels (three query tiles, five key blocks, the 16-key tail), the GEMMs on the tcgen05 GEMM."""
+    vb.set_precision("bf16")
+    g = torch.Generator().manual_seed(21)
+    B, S, E, H = 6, 257, 768, 4
+    blk = vb.v2.Encoder(E, H, 2, dropout=0.0)
+    for prm in blk.parameters():                       # trunc-normal-sized weights, non-zero biases
+        prm.data = torch.randn(prm.shape, generator=g) * (0.02 if prm.dim() > 1 else 0.05) + (1.0 if prm.dim() == 1 and "norm" in "" else 0.0)
+    with torch.no_grad():
+        blk.norm1.weight.add_(1.0); blk.norm2.weight.add_(1.0)
+    params = {k: bf16_round(v.detach().clone()) for k, v in blk.state_dict().items()}
+    x, dy = bf16_round(torch.randn(B, S, E, generator=g)), bf16_round(torch.randn(B, S, E, generator=g) * 0.1)
+    y_ref, (dx_ref,), g_ref = oracle_block(lambda p, t: o2.encoder(p, "", t, H), params, x, dy)
+    assert vb.lib.lib.vg_attention_path(1, 0, B, H, S, E // H) == 2
+    blk.load_state_dict(params)
+    blk = blk.cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = blk(xg)
+    assert rel(y, y_ref) < TOL["bf16"]
+    y.backward(dy.cuda().to(y.dtype))
+    assert rel(xg.grad, dx_ref) < GTOL["bf16"]
+    cmp_grads({k: p.grad for k, p in blk.named_parameters()}, g_ref, GTOL["bf16"], "Encoder@C4")
+
+
+def _calibrated_curve_check(gpu, f32, f64, first, first_tol, horizon_min, factor):
+    """Loss-curve parity for a chaotic map (adversarial training + Adam), SURVEY 7.3 item 4: (a) the first `first` steps within
+    `first_tol` of the fp32 reference; (b) while the fp32 reference itself is still within 1e-2 of the fp64 run of the same code,
+    |candidate - fp64| <= factor x running-max |fp32 reference - fp64| (the candidate tracks the exact trajectory as well as the
+    reference's own arithmetic does, up to `factor`)."""
+    assert torch.isfinite(gpu).all()
+    assert rel(gpu[:first], f32[:first]) < first_tol, rel(gpu[:first], f32[:first])
+    ref_dev = (f32 - f64).abs().amax(1).cummax(0).values
+    gpu_dev = (gpu - f64).abs().amax(1)
+    horizon = int((ref_dev < 1e-2).sum())
+    assert horizon >= horizon_min, horizon
+    worst = (gpu_dev[:horizon] / (ref_dev[:horizon] + 1e-12)).max()
+    assert (gpu_dev[:horizon] <= factor * ref_dev[:horizon] + 1e-5).all(), worst
+    return horizon
+
+
+def test_v1_200_step_loss_curve(vb):
+    """BASELINE.json: loss curves over 200 synthetic steps, v1 GAN (SLN generator, L2-attention spectral discriminator) at 32 px,
+    B = 2, the reference's own step sequence (src/v1/gan.py:222-252) with torch Adam(0.5, 0.999).  Three trajectories: CUDA fp32
+    path, CPU oracle fp32 (bit-exact to the reference), CPU oracle fp64; calibrated envelope as for v2, then the bf16 path's
+    first 10 steps at 2e-2."""
+    steps, B = 200, 2
+    cfg = o1.V1Config(image_size=32)
+    batches = harness.synthetic_batches_v1(cfg, B, steps)
+    orc32 = harness.OracleV1(cfg, seed=0)
+    orc64 = harness.OracleV1(cfg, seed=0, dtype=torch.float64)
+    f32 = torch.stack([torch.stack(orc32.step(r, z)) for r, z in batches]).double()
+    f64 = torch.stack([torch.stack(orc64.step(r.double(), z.double())) for r, z in batches])
+
+    def run_cuda(prec, n):
+        vb.set_precision(prec)
+        torch.manual_seed(0)
+        G, D = vb.v1.Generator(vb.v1.V1Config(image_size=32)).cuda(), vb.v1.Discriminator(vb.v1.V1Config(image_size=32)).cuda()
+        go = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        do = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        return torch.stack([torch.stack(vb.train.gan_step(G, D, go, do, r.cuda(), z.cuda(), "bce")).cpu() for r, z in batches[:n]]).double()
+
+    gpu = run_cuda("fp32", steps)
+    _calibrated_curve_check(gpu, f32, f64, first=20, first_tol=1e-4, horizon_min=20, factor=30)
+    bf = run_cuda("bf16", 40)
+    assert torch.isfinite(bf).all() and rel(bf[:10], f32[:10]) < 2e-2
+    vb.set_precision("bf16")
+
+
+def test_v2_bf16_loss_curve_over_correlated_horizon(vb):
+    """The bf16 path over the horizon in which a loss curve is still a function of the arithmetic (not of the chaotic dynamics):
+    default v2 model, B = 8.  A bf16 run rounds every activation to 2^-9, i.e. ~2^15 fp32 ulps, so its deviation is compared with
+    the fp32 reference's by that factor's order: within 2e-2 of the fp32 reference for as long as the fp32 reference stays within
+    2e-5 of fp64 (1e-3 x the bf16 tolerance), and at least over the first 10 steps."""
+    steps, B = 60, 8
+    ocfg = o2.V2Config(batch_size=3 * 32 * 32)
+    batches = harness.synthetic_batches_v2(ocfg, B, steps)
+    orc32 = harness.OracleV2(ocfg, seed=0)
+    orc64 = harness.OracleV2(ocfg, seed=0, dtype=torch.float64)
+    f32 = torch.stack([torch.stack(orc32.step(r, n)) for r, n in batches]).double()
+    f64 = torch.stack([torch.stack(orc64.step(r.double(), n.double())) for r, n in batches])
+    vb.set_precision("bf16")
+    torch.manual_seed(0)
+    gan = vb.v2.ViTGAN(vb.v2.Config(batch_size=3 * 32 * 32)).cuda()
+    go = torch.optim.AdamW(gan.generator.parameters(), lr=5e-4, weight_decay=1e-3)
+    do = torch.optim.AdamW(gan.discriminator.parameters(), lr=5e-4, weight_decay=1e-3)
+    bf = torch.stack([torch.stack(vb.train.gan_step(gan.generator, gan.discriminator, go, do, r.cuda(), n_.cuda(), "ce")).cpu()
+                      for r, n_ in batches]).double()
+    assert torch.isfinite(bf).all()
+    ref_dev = (f32 - f64).abs().amax(1).cummax(0).values
+    horizon = max(10, int((ref_dev < 2e-5).sum()))
+    assert rel(bf[:horizon], f32[:horizon]) < 2e-2, (horizon, rel(bf[:horizon], f32[:horizon]))

@@ -107,8 +107,8 @@ def test_gemm_epilogue(vb, path, act):
                            aux=aux.cuda() if act >= 5 else None, residual=res.cuda(), want_pre=True,
                            path=L.GEMM_TCGEN05 if path == "tc" else L.GEMM_SIMT)
     tol = FP32_TOL if dt == torch.float32 else BF16_TOL
-    if act in (3, 7) and dt != torch.float32:
-        tol = 0.1   # sin(30 x) amplifies the bf16 rounding of the stored output 30x; the fp32 accumulator path is exact
+    # SIN / MUL_DSIN (omega_0 = 30): the sine is taken on the fp32 accumulator, and aux is the same bf16 tensor on both sides,
+    # so the bf16 path meets the plain 2e-2 as well
     assert rel(pre, pre_ref) < tol and rel(out, ref) < tol
 
 
