@@ -175,11 +175,44 @@ def v1_default(image_size=32):
                 losses=torch.stack(losses))
 
 
+def curves_200():
+    """200-step loss curves of the REAL reference modules under the reference's own step sequence, in fp32 and in fp64 (the same
+    modules after .double()): the pair calibrates the loss-curve parity tests (the fp32 reference's own drift from fp64 is the
+    yardstick).  v2: default model, B = 8, AdamW(5e-4, wd 1e-3); v1: 32 px, B = 2, Adam(2e-4, (0.5, 0.999))."""
+    out = {}
+    steps = 200
+    c2 = o2.V2Config(batch_size=3 * 32 * 32)
+    b2 = synthetic_batches_v2(c2, 8, steps)
+    for name, dt in (("v2_f32", torch.float32), ("v2_f64", torch.float64)):
+        gan, c = refimport.build_v2(seed=0)
+        gan = gan.to(dt)
+        go = torch.optim.AdamW(gan.generator.parameters(), lr=c.generator_learning_rate, weight_decay=1e-3)
+        do = torch.optim.AdamW(gan.discriminator.parameters(), lr=c.discriminator_learning_rate, weight_decay=1e-3)
+        out[name] = torch.stack([torch.stack(gan_step(gan.generator, gan.discriminator, go, do, r.to(dt), n.to(dt), "ce")) for r, n in b2]).double()
+    c1 = o1.V1Config(image_size=32)
+    b1 = synthetic_batches_v1(c1, 2, steps)
+    for name, dt in (("v1_f32", torch.float32), ("v1_f64", torch.float64)):
+        G, D = refimport.build_v1(32, seed=0)
+        G, D = G.to(dt), D.to(dt)
+        for m in D.modules():                                   # the construction-time spectra are python floats of fp32 SVDs; keep them
+            if hasattr(m, "init_spectrum"):
+                m.init_spectrum = [torch.as_tensor(s, dtype=dt) if not torch.is_tensor(s) else s.to(dt) for s in m.init_spectrum]
+        go = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        do = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        out[name] = torch.stack([torch.stack(gan_step(G, D, go, do, r.to(dt), z.to(dt), "bce")) for r, z in b1]).double()
+    out["steps"], out["v2_batch"], out["v1_batch"], out["seed"], out["data_seed"] = steps, 8, 2, 0, 1234
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert refimport.available(), "needs /root/reference"
+    import sys
+    only = sys.argv[1:]
     for name, fn in (("v2_tiny", v2_tiny), ("v2_blocks", v2_blocks), ("v2_default", v2_default),
-                     ("v1_blocks", v1_blocks), ("v1_default", v1_default)):
+                     ("v1_blocks", v1_blocks), ("v1_default", v1_default), ("curves_200", curves_200)):
+        if only and name not in only:
+            continue
         obj = fn()
         path = os.path.join(OUT, name + ".pt")
         torch.save(obj, path)

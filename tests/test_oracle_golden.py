@@ -158,3 +158,19 @@ def test_oracle_convert_to_uint8_known_answers():
     from oracle import v2 as o2
     x = torch.tensor([-2.0, -1.0, -0.5, 0.0, 0.5, 1.0, 2.0, 0.999, -0.999])
     assert o2.convert_to_uint8(x).tolist() == [0, 0, 63, 127, 191, 255, 255, 254, 0]
+
+
+def test_oracle_reproduces_reference_loss_curves(golden):
+    """tests/golden/curves_200.pt holds 200-step loss curves of the REAL reference modules (fp32 and .double()).  The oracle's
+    step must reproduce their heads bit for bit in fp32 (v2: 12 steps, v1: 3 steps -- the oracle is a restatement, so the whole
+    curve is identical; the CPU suite only re-runs the head to stay within its time budget) and to 1e-12 in fp64."""
+    fx = golden("curves_200")
+    c2 = o2.V2Config(batch_size=3 * 32 * 32)
+    for dt, key, tol in ((torch.float32, "v2_f32", 0.0), (torch.float64, "v2_f64", 1e-12)):
+        orc = harness.OracleV2(c2, seed=fx["seed"], dtype=dt)
+        got = torch.stack([torch.stack(orc.step(r.to(dt), n.to(dt))) for r, n in harness.synthetic_batches_v2(c2, fx["v2_batch"], 12)]).double()
+        assert (got - fx[key][:12]).abs().max() <= tol, key
+    c1 = o1.V1Config(image_size=32)
+    orc = harness.OracleV1(c1, seed=fx["seed"])
+    got = torch.stack([torch.stack(orc.step(r, z)) for r, z in harness.synthetic_batches_v1(c1, fx["v1_batch"], 3)]).double()
+    assert (got - fx["v1_f32"][:3]).abs().max() == 0.0
