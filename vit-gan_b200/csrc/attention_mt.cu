@@ -94,33 +94,34 @@ template <int D> struct Stg {
   static constexpr bool R32 = (D % 64) >= 32;
   static constexpr bool R16 = (D % 32) >= 16;
 };
-template <int D>
+// ROWS = rows of the staging tile (128: a whole accumulator tile; 64: one half, staged in a ring stage)
+template <int D, int ROWS = 128>
 __device__ __forceinline__ uint32_t stg_addr(uint32_t base, int row, int c8) {   // 16-byte chunk c8 = column / 8 of `row`
   constexpr int FULL = Stg<D>::FULL;
-  if (c8 < FULL * 8) return base + (uint32_t)(c8 >> 3) * QCH + (uint32_t)row * 128u + ((((uint32_t)c8 & 7u) ^ ((uint32_t)row & 7u)) << 4);
-  uint32_t b2 = base + FULL * QCH;
+  if (c8 < FULL * 8) return base + (uint32_t)(c8 >> 3) * (ROWS * 128) + (uint32_t)row * 128u + ((((uint32_t)c8 & 7u) ^ ((uint32_t)row & 7u)) << 4);
+  uint32_t b2 = base + FULL * (ROWS * 128);
   int c = c8 - FULL * 8;
   if (Stg<D>::R32) {
     if (c < 4) return b2 + (uint32_t)row * 64u + (((uint32_t)c ^ (((uint32_t)row >> 1) & 3u)) << 4);
-    b2 += 128 * 64; c -= 4;
+    b2 += ROWS * 64; c -= 4;
   }
   return b2 + (uint32_t)row * 32u + (((uint32_t)c ^ (((uint32_t)row >> 2) & 1u)) << 4);
 }
-template <int D>
+template <int D, int ROWS = 128>
 __device__ __forceinline__ void stg_store(const OutMaps& m, uint32_t base, int col0, int row0, int b) {
   constexpr int FULL = Stg<D>::FULL;
 #pragma unroll
-  for (int i = 0; i < FULL; ++i) tma_store_3d(&m.m64, base + i * QCH, col0 + 64 * i, row0, b);
-  if (Stg<D>::R32) tma_store_3d(&m.m32, base + FULL * QCH, col0 + 64 * FULL, row0, b);
-  if (Stg<D>::R16) tma_store_3d(&m.m16, base + FULL * QCH + (Stg<D>::R32 ? 128 * 64 : 0), col0 + 64 * FULL + (Stg<D>::R32 ? 32 : 0), row0, b);
+  for (int i = 0; i < FULL; ++i) tma_store_3d(&m.m64, base + i * (ROWS * 128), col0 + 64 * i, row0, b);
+  if (Stg<D>::R32) tma_store_3d(&m.m32, base + FULL * (ROWS * 128), col0 + 64 * FULL, row0, b);
+  if (Stg<D>::R16) tma_store_3d(&m.m16, base + FULL * (ROWS * 128) + (Stg<D>::R32 ? ROWS * 64 : 0), col0 + 64 * FULL + (Stg<D>::R32 ? 32 : 0), row0, b);
 }
 // 32 (or 16) fp32 accumulator values -> bf16 -> staging columns [c, c + n) of `row`
-template <int D>
+template <int D, int ROWS = 128>
 __device__ __forceinline__ void stg_write(uint32_t base, int row, int c, const float* o, int n) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (8 * i < n)
-      sts128(stg_addr<D>(base, row, (c >> 3) + i), pack_bf16(o[8 * i], o[8 * i + 1]), pack_bf16(o[8 * i + 2], o[8 * i + 3]),
+      sts128(stg_addr<D, ROWS>(base, row, (c >> 3) + i), pack_bf16(o[8 * i], o[8 * i + 1]), pack_bf16(o[8 * i + 2], o[8 * i + 3]),
              pack_bf16(o[8 * i + 4], o[8 * i + 5]), pack_bf16(o[8 * i + 6], o[8 * i + 7]));
 }
 // squared norm of D contiguous bf16 (16-byte aligned), fp32
@@ -535,24 +536,31 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // their dO row anyway for delta = rowsum(dO * O) -- copy both rows into TMEM once per tile (tcgen05.st, two bf16 per column) and
 // S = Q K_j^T, dP = dO V_j^T run as TS-MMAs.  TMEM: Q | dO as operands (D columns), one [S | dP] pair of 64-key blocks (128 columns;
 // released as soon as the block sits in registers, so the next pair is computed while this one is exponentiated), dQ (D columns).
-// dS goes to smem (double buffered) as the A operand of dQ += dS K_j.  The dQ staging tile is the Q smem tile (free once copied);
-// the producer warp stores it and then fetches the next tile's Q into it, while the next dO tile was already prefetched.
+// dS goes to smem (double buffered) as the A operand of dQ += dS K_j.
+//
+// Shared memory is ONE in-order pool of [64 rows x D] stages.  A TMA load takes ~2 us here while a 64-key block lasts ~1 us, and a
+// K block lives from its S MMA to its dQ MMA, so separate two-stage K / V rings left the tensor core waiting for K in every
+// block.  Through the pool flow, in a fixed order per tile: the two halves of dO and of Q (released once copied to TMEM), then
+// V_j, K_j for every key block, then the two halves of the dQ staging tile.  Every role derives a request's stage and phase from
+// the running request number, so the producer runs up to a whole pool (~3 key blocks, and the next tile's dO / Q) ahead; it also
+// issues the dQ stores (it polls for the staged tile between its loads), so no compute thread waits for a store.
 template <int D> struct DqCfg {
   static constexpr int DC = (D + 63) / 64, KS = D / 16;
-  static constexpr int NS = D > 128 ? 2 : 3;                 // ring stages per operand (K blocks, V blocks)
+  static constexpr int STG_BYTES = DC * BCH;                 // one [64 rows x D] stage
+  static constexpr int NP = D > 128 ? 8 : 12;                // pool stages
   static constexpr int QA_COL = 0, DOA_COL = D / 2, S_COL = D, DP_COL = D + 64, DQ_COL = D + 128;
   static_assert(DQ_COL + D <= 512, "TMEM layout");
-  static constexpr int Q_OFF = 0, DO_OFF = DC * QCH, KR_OFF = 2 * DC * QCH, VR_OFF = KR_OFF + NS * DC * BCH;
-  static constexpr int DS_OFF = VR_OFF + NS * DC * BCH, KN_OFF = DS_OFF + 2 * QCH, BAR_OFF = KN_OFF + MAXNK * 4;
-  static constexpr int NBAR = 9 + 4 * NS + 4;
+  static constexpr int POOL_OFF = 0, DS_OFF = NP * STG_BYTES, KN_OFF = DS_OFF + 2 * QCH, BAR_OFF = KN_OFF + MAXNK * 4;
+  static constexpr int NBAR = 2 * NP + 10;
   static constexpr int SMEM = BAR_OFF + NBAR * 8 + 16;
+  static_assert(STG_BYTES >= 64 * D * 2, "a staging half fits a stage");
 };
 
-// this thread's row of a K-major [128 x D] SW128 operand tile -> TMEM columns [col, col + D / 2) of its lane (bf16 A operand of a
-// TS-MMA: element k of the row in column k / 2, low half first), 32 elements (16 columns) at a time; `f(c, r)` sees every chunk
-// (c = first TMEM column of the chunk, r = its 16 -- or 8 for the tail -- packed registers)
+// this thread's row of a K-major [rows x D] SW128 operand tile (64-column chunks `chunk_bytes` apart) -> TMEM columns
+// [col, col + D / 2) of its lane (bf16 A operand of a TS-MMA: element k of the row in column k / 2, low half first), 32 elements
+// (16 columns) at a time; `f(c, r, n)` sees every chunk (c = first TMEM column of the chunk, r = its n = 16 or 8 packed registers)
 template <int D, typename F>
-__device__ __forceinline__ void row_to_tmem(uint32_t tile, int row, uint32_t taddr, F&& f) {
+__device__ __forceinline__ void row_to_tmem(uint32_t tile, uint32_t chunk_bytes, int row, uint32_t taddr, F&& f) {
 #pragma unroll
   for (int c = 0; c < D / 2; c += 16) {
     uint32_t r[16];
@@ -561,7 +569,7 @@ __device__ __forceinline__ void row_to_tmem(uint32_t tile, int row, uint32_t tad
     for (int i = 0; i < 4; ++i)
       if (4 * i < n) {
         const int c8 = (c >> 2) + i;                       // 16-byte chunk = 8 elements = 4 columns
-        lds128(swz(tile + (uint32_t)(c8 >> 3) * QCH, row, c8 & 7), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        lds128(swz(tile + (uint32_t)(c8 >> 3) * chunk_bytes, row, c8 & 7), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
       }
     if (n == 16) tmem_st16(taddr + (uint32_t)c, r); else tmem_st8(taddr + (uint32_t)c, r);
     f(c, r, n);
@@ -574,23 +582,23 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                       const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                       const __grid_constant__ OutMaps map_dq, const MtGeo g) {
   using C = DqCfg<D>;
-  constexpr int DC = C::DC, KS = C::KS, NS = C::NS, QA_COL = C::QA_COL, DOA_COL = C::DOA_COL, S_COL = C::S_COL, DP_COL = C::DP_COL, DQ_COL = C::DQ_COL;
+  constexpr int DC = C::DC, KS = C::KS, NP = C::NP, STG = C::STG_BYTES;
+  constexpr int QA_COL = C::QA_COL, DOA_COL = C::DOA_COL, S_COL = C::S_COL, DP_COL = C::DP_COL, DQ_COL = C::DQ_COL;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t base = smem_u32(smem_dyn);
-  const uint32_t q_t = base + C::Q_OFF, do_t = base + C::DO_OFF, kr = base + C::KR_OFF, vr = base + C::VR_OFF, ds_t = base + C::DS_OFF;
-  const uint32_t bar = base + C::BAR_OFF;
+  const uint32_t pool = base + C::POOL_OFF, ds_t = base + C::DS_OFF, bar = base + C::BAR_OFF;
   float* kn = reinterpret_cast<float*>(smem_dyn + C::KN_OFF);
-  const uint32_t q_full = bar, do_full = bar + 8, do_free = bar + 16, a_ready = bar + 24, stg_full = bar + 32, dq_full = bar + 40,
-                 dq_free = bar + 48, sdp_full = bar + 56, sdp_free = bar + 64;
-  auto k_full = [&](int i) { return bar + 8u * (9 + i); };
-  auto k_empty = [&](int i) { return bar + 8u * (9 + NS + i); };
-  auto v_full = [&](int i) { return bar + 8u * (9 + 2 * NS + i); };
-  auto v_empty = [&](int i) { return bar + 8u * (9 + 3 * NS + i); };
-  auto ds_full = [&](int i) { return bar + 8u * (9 + 4 * NS + i); };
-  auto ds_empty = [&](int i) { return bar + 8u * (11 + 4 * NS + i); };
+  auto full = [&](uint32_t st) { return bar + 8u * st; };
+  auto empty = [&](uint32_t st) { return bar + 8u * (NP + st); };
+  const uint32_t a_ready = bar + 8u * (2 * NP), stg_full = a_ready + 16, dq_full = a_ready + 24, dq_free = a_ready + 32,
+                 sdp_full = a_ready + 40, sdp_free = a_ready + 48;
+  auto ds_full = [&](int i) { return a_ready + 8u * (7 + i); };
+  auto ds_empty = [&](int i) { return a_ready + 8u * (9 + i); };
   const uint32_t tmem_slot = bar + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + C::BAR_OFF + 8 * C::NBAR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // request numbering inside a tile: 0,1 dO halves; 2,3 Q halves; 4 + 2 j V_j; 5 + 2 j K_j; R - 2, R - 1 staging halves
+  const uint32_t R = 6u + 2u * (uint32_t)g.n_b;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) { printf("attention_mt: dynamic smem base not 1024-aligned\n"); __trap(); }
@@ -598,9 +606,9 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-    mbar_init(q_full, 1); mbar_init(do_full, 1); mbar_init(do_free, 128); mbar_init(a_ready, 128); mbar_init(stg_full, 128);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 128); mbar_init(sdp_full, 1); mbar_init(sdp_free, 128);
-    for (int i = 0; i < NS; ++i) { mbar_init(k_full(i), 1); mbar_init(k_empty(i), 1); mbar_init(v_full(i), 1); mbar_init(v_empty(i), 1); }
+    for (int i = 0; i < NP; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(a_ready, 128); mbar_init(stg_full, 128); mbar_init(dq_full, 1); mbar_init(dq_free, 128);
+    mbar_init(sdp_full, 1); mbar_init(sdp_free, 128);
     for (int i = 0; i < 2; ++i) { mbar_init(ds_full(i), 128); mbar_init(ds_empty(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -615,47 +623,69 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t bc = 0, tc = 0;                       // key-block counter, tile counter
+      uint32_t tc = 0;                               // tile counter
       Tracer tr(g.trace, 3);
-      int pend_w = -1, pend_t = 0;                   // tile whose dQ the compute threads stage into the Q smem tile
-      auto store_pending = [&]() {
+      // the previous tile's staged dQ: stored as soon as the compute threads have written it (polled between the loads below)
+      int pend_w = -1, pend_t = 0;
+      uint32_t pend_rq = 0, pend_par = 0;
+      auto service_store = [&](bool block) {
         if (pend_w < 0) return;
-        mbar_wait(stg_full, (tc - 1) & 1u);
-        stg_store<D>(map_dq, q_t, (pend_w % g.H) * D, pend_t * 128, pend_w / g.H);
+        if (!block && !mbar_test(stg_full, pend_par)) return;
+        if (block) mbar_wait(stg_full, pend_par);
+        const int pb = pend_w / g.H, pc = (pend_w % g.H) * D;
+        stg_store<D, 64>(map_dq, pool + (pend_rq % NP) * STG, pc, pend_t * 128, pb);
+        stg_store<D, 64>(map_dq, pool + ((pend_rq + 1) % NP) * STG, pc, pend_t * 128 + 64, pb);
         tma_commit();
         tma_wait_read();
+        mbar_arrive(empty(pend_rq % NP));
+        mbar_arrive(empty((pend_rq + 1) % NP));
         pend_w = -1;
+      };
+      auto acquire = [&](uint32_t rq) {              // the stage of request rq is free again (its previous user released it)
+        const uint32_t st = rq % NP;
+        if (pend_w >= 0 && (st == pend_rq % NP || st == (pend_rq + 1) % NP)) service_store(true);
+        mbar_wait(empty(st), ((rq / NP) & 1u) ^ 1u);
+        return st;
       };
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / g.H, col0 = (w % g.H) * D;
         for (int t = 0; t < g.n_t; ++t, ++tc) {
-          mbar_wait(do_free, (tc & 1u) ^ 1u);          // the previous tile's dO rows sit in TMEM: its smem tile is free
-          mbar_expect_tx(do_full, DC * QCH);
+          const uint32_t rq0 = tc * R;
+          for (int hf = 0; hf < 2; ++hf) {           // dO halves, then Q halves
+            const uint32_t st = acquire(rq0 + hf);
+            mbar_expect_tx(full(st), STG);
 #pragma unroll
-          for (int c = 0; c < DC; ++c) tma_load_3d(do_t + c * QCH, &map_do, do_full, col0 + 64 * c, t * 128, b);
-          store_pending();                             // previous tile's dQ leaves the Q smem tile ...
-          tr(1);
-          mbar_expect_tx(q_full, DC * QCH);            // ... and this tile's Q enters it
-#pragma unroll
-          for (int c = 0; c < DC; ++c) tma_load_3d(q_t + c * QCH, &map_q, q_full, col0 + 64 * c, t * 128, b);
-          for (int kb = 0; kb < g.n_b; ++kb, ++bc) {           // V stages are released first (after dP), K stages after dQ
-            const int st = bc % NS;
-            const uint32_t par = ((bc / NS) & 1u) ^ 1u;
-            mbar_wait(v_empty(st), par);
-            tr(110 + kb);
-            mbar_expect_tx(v_full(st), DC * BCH);
-#pragma unroll
-            for (int c = 0; c < DC; ++c) tma_load_3d(vr + (st * DC + c) * BCH, &map_v, v_full(st), col0 + 64 * c, kb * 64, b);
-            mbar_wait(k_empty(st), par);
-            tr(100 + kb);
-            mbar_expect_tx(k_full(st), DC * BCH);
-#pragma unroll
-            for (int c = 0; c < DC; ++c) tma_load_3d(kr + (st * DC + c) * BCH, &map_k, k_full(st), col0 + 64 * c, kb * 64, b);
+            for (int c = 0; c < DC; ++c) tma_load_3d(pool + st * STG + c * BCH, &map_do, full(st), col0 + 64 * c, t * 128 + 64 * hf, b);
           }
-          pend_w = w; pend_t = t;
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t st = acquire(rq0 + 2 + hf);
+            mbar_expect_tx(full(st), STG);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(pool + st * STG + c * BCH, &map_q, full(st), col0 + 64 * c, t * 128 + 64 * hf, b);
+          }
+          tr(1);
+          for (int kb = 0; kb < g.n_b; ++kb) {
+            service_store(false);
+            uint32_t st = acquire(rq0 + 4 + 2 * kb);
+            tr(110 + kb);
+            mbar_expect_tx(full(st), STG);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(pool + st * STG + c * BCH, &map_v, full(st), col0 + 64 * c, kb * 64, b);
+            st = acquire(rq0 + 5 + 2 * kb);
+            tr(100 + kb);
+            mbar_expect_tx(full(st), STG);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) tma_load_3d(pool + st * STG + c * BCH, &map_k, full(st), col0 + 64 * c, kb * 64, b);
+          }
+          service_store(true);                       // at the latest here: one staged tile outstanding at a time
+          // this tile's staging halves: wait until their previous users are done, then hand them to the compute threads by
+          // completing the stages' `full` phase (every request completes exactly one phase of its stage's barrier pair)
+          mbar_arrive(full(acquire(rq0 + R - 2)));
+          mbar_arrive(full(acquire(rq0 + R - 1)));
+          pend_w = w; pend_t = t; pend_rq = rq0 + R - 2; pend_par = tc & 1u;
         }
       }
-      store_pending();
+      service_store(true);
       tma_wait_all();
     }
   } else if (warp == 1) {
@@ -667,48 +697,48 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       Tracer tr(lane == 0 ? g.trace : nullptr, 4);
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int t = 0; t < g.n_t; ++t, ++tc) {
-          const uint32_t tpar = tc & 1u;
+          const uint32_t tpar = tc & 1u, rq0 = tc * R;
           mbar_wait(a_ready, tpar);                                   // Q and dO rows of this tile are in TMEM
           tr(10);
           tc_fence_after();
-          // event loop: dQ(j) as soon as its dS block is written (it releases the K stage the next load is waiting for),
-          // otherwise the next S / dP pair as soon as its K, V blocks have landed and the previous pair sits in registers
+          // event loop: dQ(j) as soon as its dS block is written (it releases the K stage), otherwise the next S / dP pair as
+          // soon as its K, V blocks have landed and the previous pair sits in registers
           int js = 0, jq = 0;                                         // next block to issue S/dP for, next block to issue dQ for
           while (jq < g.n_b) {
             if (jq < js) {
-              const uint32_t c = bc0 + jq;
-              const int buf = c & 1, st = c % NS, nk = min(64, g.NK - 64 * jq);
-              if (mbar_try_wait(ds_full(buf), (c >> 1) & 1u) && (jq > 0 || mbar_try_wait(dq_free, tpar ^ 1u))) {
+              const uint32_t c = bc0 + jq, rk = rq0 + 5 + 2 * jq;
+              const int buf = c & 1, nk = min(64, g.NK - 64 * jq);
+              if (mbar_test(ds_full(buf), (c >> 1) & 1u) && (jq > 0 || mbar_test(dq_free, tpar ^ 1u))) {
                 tr(40 + jq);
                 tc_fence_after();
-                const SDesc kd = sdesc_mn(kr + st * DC * BCH, BCH), dsd = sdesc_k(ds_t + buf * QCH);
+                const SDesc kd = sdesc_mn(pool + (rk % NP) * STG, BCH), dsd = sdesc_k(ds_t + buf * QCH);
                 if (elect_one()) {
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk)
                     if (kk < nk / 16) tc_mma_d(tm + DQ_COL, dsd, kk * 2u, kd, kk * 128u, idesc_dq, (jq > 0 || kk > 0) ? 1u : 0u);
                   tc_commit(ds_empty(buf));
-                  tc_commit(k_empty(st));
+                  tc_commit(empty(rk % NP));
                 }
                 __syncwarp();
                 ++jq;
                 continue;
               }
             }
-            if (js < g.n_b && js < jq + 2) {
-              const uint32_t c = bc0 + js;
-              const int st = c % NS, nk = min(64, g.NK - 64 * js);
-              if (mbar_try_wait(k_full(st), (c / NS) & 1u) && mbar_try_wait(v_full(st), (c / NS) & 1u) && mbar_try_wait(sdp_free, (c & 1u) ^ 1u)) {
+            if (js < g.n_b) {
+              const uint32_t c = bc0 + js, rv = rq0 + 4 + 2 * js, rk = rv + 1;
+              const int nk = min(64, g.NK - 64 * js);
+              if (mbar_test(full(rk % NP), (rk / NP) & 1u) && mbar_test(full(rv % NP), (rv / NP) & 1u) && mbar_test(sdp_free, (c & 1u) ^ 1u)) {
                 tr(20 + js);
                 tc_fence_after();
                 const uint32_t idesc_s = make_idesc(128, nk, 0, 0);
-                const SDesc kd = sdesc_k(kr + st * DC * BCH), vd = sdesc_k(vr + st * DC * BCH);
+                const SDesc kd = sdesc_k(pool + (rk % NP) * STG), vd = sdesc_k(pool + (rv % NP) * STG);
                 if (elect_one()) {
 #pragma unroll
                   for (int k = 0; k < KS; ++k) tc_mma_ts_d(tm + S_COL, tm + (uint32_t)(QA_COL + 8 * k), kd, kstep_off(k, BCH), idesc_s, k > 0);
 #pragma unroll
                   for (int k = 0; k < KS; ++k) tc_mma_ts_d(tm + DP_COL, tm + (uint32_t)(DOA_COL + 8 * k), vd, kstep_off(k, BCH), idesc_s, k > 0);
                   tc_commit(sdp_full);
-                  tc_commit(v_empty(st));
+                  tc_commit(empty(rv % NP));
                 }
                 __syncwarp();
                 ++js;
@@ -727,6 +757,7 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const float sc2 = g.scale * LOG2E;
+    const int hf = row >> 6, lrow = row & 63;          // this row's half of the Q / dO / staging tiles, and its row inside the stage
     uint32_t bc0 = 0, tc = 0;
     Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 5);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -738,7 +769,7 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         named_bar(2, 128);
       }
       for (int t = 0; t < g.n_t; ++t, ++tc) {
-        const uint32_t tpar = tc & 1u;
+        const uint32_t tpar = tc & 1u, rq0 = tc * R;
         const int row_g = t * 128 + row;
         const bool row_on = row_g < g.S;
         const bool warp_on = t * 128 + quad * 32 < g.S;
@@ -750,11 +781,12 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           for (int c8 = 0; c8 < D / 8; ++c8) orow[c8] = __ldg(reinterpret_cast<const uint4*>(op + 8 * c8));
         }
         float delta = 0.f, lse2 = 1e30f, qq = 0.f;
-        mbar_wait(do_full, tpar);
+        const uint32_t r_do = rq0 + hf, r_q = rq0 + 2 + hf;
+        mbar_wait(full(r_do % NP), (r_do / NP) & 1u);
         tr(50);
         {                                                // dO row -> TMEM (rows beyond S were zero-filled by TMA); delta = rowsum(dO * O)
           float d4[4] = {0.f, 0.f, 0.f, 0.f};
-          row_to_tmem<D>(do_t, row, t_lane + DOA_COL, [&](int c, const uint32_t (&r)[16], int n) {
+          row_to_tmem<D>(pool + (r_do % NP) * STG, BCH, lrow, t_lane + DOA_COL, [&](int c, const uint32_t (&r)[16], int n) {
             if (row_on) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -773,9 +805,8 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           g.delta[(int64_t)w * g.S + row_g] = delta;
           lse2 = __ldg(g.lse + (int64_t)w * g.S + row_g) * LOG2E;
         }
-        mbar_arrive(do_free);                            // the dO smem tile has been read: the next tile's may be fetched
-        mbar_wait(q_full, tpar);
-        row_to_tmem<D>(q_t, row, t_lane + QA_COL, [&](int c, const uint32_t (&r)[16], int n) {
+        mbar_wait(full(r_q % NP), (r_q / NP) & 1u);
+        row_to_tmem<D>(pool + (r_q % NP) * STG, BCH, lrow, t_lane + QA_COL, [&](int c, const uint32_t (&r)[16], int n) {
           if (MODE == VG_ATTN_L2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -784,7 +815,9 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         });
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(a_ready);                            // both operand rows are in TMEM; the Q smem tile is free (dQ staging)
+        mbar_arrive(a_ready);                            // both operand rows are in TMEM
+        named_bar(3 + hf, 64);                           // the 64 threads of this half have read their dO and Q stages ...
+        if (lrow == 0) { mbar_arrive(empty(r_do % NP)); mbar_arrive(empty(r_q % NP)); }   // ... which go back to the pool
         tr(51);
         float gsum = 0.f;
         for (int j = 0; j < g.n_b; ++j) {
@@ -829,10 +862,14 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tr(80 + j);
         }
         bc0 += g.n_b;
-        // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> staging over the Q smem tile -> TMA store by the producer warp
+        // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> this row's half of the staging tile (two pool stages) -> the
+        //      producer warp stores it
         mbar_wait(dq_full, tpar);                       // every MMA of the tile is complete (the TMEM operand rows may be replaced)
         tr(55);
         tc_fence_after();
+        const uint32_t r_st = rq0 + R - 2 + hf;
+        mbar_wait(full(r_st % NP), (r_st / NP) & 1u);   // this half's staging stage has left its previous user
+        const uint32_t stg = pool + (r_st % NP) * STG;
         if (warp_on) {
 #pragma unroll
           for (int c = 0; c < D; c += 32) {
@@ -851,7 +888,7 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               o[jj] = __uint_as_float(v[jj]);
               if (MODE == VG_ATTN_L2 && jj < n) o[jj] = fmaf(gsum, (jj & 1) ? bf16_hi(qv[jj >> 1]) : bf16_lo(qv[jj >> 1]), -o[jj]);
             }
-            stg_write<D>(q_t, row, c, o, n);
+            stg_write<D, 64>(stg, lrow, c, o, n);
           }
         }
         tc_fence_before();
@@ -992,7 +1029,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             if (ik < ip) {
               const uint32_t c = bc0 + ik;
               const int st = c % NS, ni = min(64, g.NK - 64 * ik);
-              if (mbar_try_wait(dst_full, c & 1u)) {
+              if (mbar_test(dst_full, c & 1u)) {
                 tr(45 + ik);
                 tc_fence_after();
                 const SDesc qd = sdesc_mn(qr + st * DC * BCH, BCH);
@@ -1011,7 +1048,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             if (ip < is) {
               const uint32_t c = bc0 + ip;
               const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * ip);
-              if (mbar_try_wait(pt_full, c & 1u) && (ip > 0 || mbar_try_wait(out_free, ipar ^ 1u))) {   // P^T in smem; S^T fully read
+              if (mbar_test(pt_full, c & 1u) && (ip > 0 || mbar_test(out_free, ipar ^ 1u))) {   // P^T in smem; S^T fully read
                 tr(40 + ip);
                 tc_fence_after();
                 const uint32_t idesc_s = make_idesc(128, ni, 0, 0);
@@ -1033,7 +1070,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             if (is < g.n_b && is < ip + 2) {
               const uint32_t c = bc0 + is;
               const int buf = c & 1, st = c % NS, ni = min(64, g.NK - 64 * is);
-              if (mbar_try_wait(qdo_full(st), (c / NS) & 1u) && mbar_try_wait(st_free(buf), ((c >> 1) & 1u) ^ 1u)) {
+              if (mbar_test(qdo_full(st), (c / NS) & 1u) && mbar_test(st_free(buf), ((c >> 1) & 1u) ^ 1u)) {
                 tr(20 + is);
                 tc_fence_after();
                 const uint32_t idesc_s = make_idesc(128, ni, 0, 0);
@@ -1224,12 +1261,12 @@ int make_map(CUtensorMap* map, const void* ptr, int B, int S, int cols, int64_t 
              cols, (long long)ld, box_cols, box_rows);
   return VG_OK;
 }
-int make_out_maps(OutMaps* m, const void* ptr, int B, int S, int cols, int64_t ld, int d) {
+int make_out_maps(OutMaps* m, const void* ptr, int B, int S, int cols, int64_t ld, int d, int rows = 128) {
   int rc;
   memset(m, 0, sizeof(*m));
-  if (d >= 64 && (rc = make_map(&m->m64, ptr, B, S, cols, ld, 64, 128))) return rc;
-  if ((d % 64) >= 32 && (rc = make_map(&m->m32, ptr, B, S, cols, ld, 32, 128))) return rc;
-  if ((d % 32) >= 16 && (rc = make_map(&m->m16, ptr, B, S, cols, ld, 16, 128))) return rc;
+  if (d >= 64 && (rc = make_map(&m->m64, ptr, B, S, cols, ld, 64, rows))) return rc;
+  if ((d % 64) >= 32 && (rc = make_map(&m->m32, ptr, B, S, cols, ld, 32, rows))) return rc;
+  if ((d % 32) >= 16 && (rc = make_map(&m->m16, ptr, B, S, cols, ld, 16, rows))) return rc;
   return VG_OK;
 }
 
@@ -1274,7 +1311,7 @@ int launch_bwd(const CUtensorMap& mq128, const CUtensorMap& mdo128, const CUtens
   rc = set_smem_once(attn_bwd_dkv_mt_kernel<D, MODE>, DkvCfg<D>::smem(MODE), &set2);
   if (rc) return rc;
   const int grid = min(g.B * g.H, num_sms());
-  launch_pdl(attn_bwd_dq_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DqCfg<D>::SMEM, st, mq128, mdo128, mk64, mv64, mdq, g);
+  launch_pdl(attn_bwd_dq_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DqCfg<D>::SMEM, st, mq64, mdo64, mk64, mv64, mdq, g);
   rc = check_launch("attention_bwd_dq_mt");
   if (rc) return rc;
   launch_pdl(attn_bwd_dkv_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DkvCfg<D>::smem(MODE), st, mk128, mv128, mq64, mdo64, mdk, mdv, g);
@@ -1343,7 +1380,7 @@ int attention_bwd_mt(int mode, int B, int H, int S, int d, const void* q, const 
   if ((rc = make_map(&mv128, v, B, S, cols, ld, 64, 128))) return rc;
   if ((rc = make_map(&mq64, q, B, S, cols, ld, 64, 64))) return rc;
   if ((rc = make_map(&mdo64, d_o, B, S, cols, ldo, 64, 64))) return rc;
-  if ((rc = make_out_maps(&mdq, dq, B, S, cols, ldd, d))) return rc;
+  if ((rc = make_out_maps(&mdq, dq, B, S, cols, ldd, d, 64))) return rc;
   if ((rc = make_out_maps(&mdk, dk, B, S, cols, ldd, d))) return rc;
   if ((rc = make_out_maps(&mdv, dv, B, S, cols, ldd, d))) return rc;
   const MtGeo g = make_geo(B, H, S, ld, ldo, scale, q, k, o, const_cast<float*>(lse), delta);
