@@ -37,6 +37,7 @@ namespace vg {
 namespace {
 
 constexpr int NTHREADS = 192;
+constexpr int NTHREADS_BWD = 320, NCOMP_BWD = 256;       // dK / dV kernel: 8 compute warps (two per TMEM lane quadrant)
 constexpr int QCH = 128 * 128;            // one [128 rows x 64 bf16] swizzled chunk
 constexpr int BCH = 64 * 128;             // one [64 rows x 64 bf16] swizzled chunk
 constexpr int MAXNK = 272;                // S rounded up to 16 must fit the S region of TMEM
@@ -58,6 +59,9 @@ struct MtGeo {
   float* lse;               // [B, H, S]
   float* delta;             // [B, H, S]
   const bf16 *q, *k, *o;
+  bf16 *dq, *dk, *dv;       // backward outputs written straight from registers (row pitch ldd)
+  int64_t ldd;
+  int skew_ns, no_prefetch;    // experiment knobs (VG_ATTN_SKEW, VG_ATTN_NOPF)
   unsigned long long* trace;   // bring-up timeline of CTA 0 (vg_attention_set_trace) or NULL
 };
 
@@ -547,18 +551,32 @@ attn_fwd_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 template <int D> struct DqCfg {
   static constexpr int DC = (D + 63) / 64, KS = D / 16;
   static constexpr int STG_BYTES = DC * BCH;                 // one [64 rows x D] stage
-  static constexpr int NP = D > 128 ? 8 : 12;                // pool stages
+  static constexpr int NP = D > 128 ? 8 : 11;                // pool stages
   static constexpr int QA_COL = 0, DOA_COL = D / 2, S_COL = D, DP_COL = D + 64, DQ_COL = D + 128;
   static_assert(DQ_COL + D <= 512, "TMEM layout");
-  static constexpr int POOL_OFF = 0, DS_OFF = NP * STG_BYTES, KN_OFF = DS_OFF + 2 * QCH, BAR_OFF = KN_OFF + MAXNK * 4;
+  static constexpr int POOL_OFF = 0, DS_OFF = NP * STG_BYTES, KN_OFF = DS_OFF + 2 * QCH, XCH_OFF = KN_OFF + MAXNK * 4,
+                        BAR_OFF = XCH_OFF + (D > 128 ? 2 : 4) * 128 * 4;   // XCH: per-row delta, |q|^2 and (L2, D <= 128) rowsum(G) halves, exchanged between a row's two threads
   static constexpr int NBAR = 2 * NP + 10;
   static constexpr int SMEM = BAR_OFF + NBAR * 8 + 16;
+  static_assert(SMEM <= 232448, "shared memory");
   static_assert(STG_BYTES >= 64 * D * 2, "a staging half fits a stage");
 };
 
 // this thread's row of a K-major [rows x D] SW128 operand tile (64-column chunks `chunk_bytes` apart) -> TMEM columns
 // [col, col + D / 2) of its lane (bf16 A operand of a TS-MMA: element k of the row in column k / 2, low half first), 32 elements
 // (16 columns) at a time; `f(c, r, n)` sees every chunk (c = first TMEM column of the chunk, r = its n = 16 or 8 packed registers)
+// n (32 or 16) fp32 values -> bf16 -> 16-byte global stores (p 16-byte aligned)
+__device__ __forceinline__ void store_row_bf16(bf16* p, const float (&o)[32], int n) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (8 * i < n) {
+      uint4 u;
+      u.x = pack_bf16(o[8 * i], o[8 * i + 1]); u.y = pack_bf16(o[8 * i + 2], o[8 * i + 3]);
+      u.z = pack_bf16(o[8 * i + 4], o[8 * i + 5]); u.w = pack_bf16(o[8 * i + 6], o[8 * i + 7]);
+      *reinterpret_cast<uint4*>(p + 8 * i) = u;
+    }
+}
+
 template <int D, typename F>
 __device__ __forceinline__ void row_to_tmem(uint32_t tile, uint32_t chunk_bytes, int row, uint32_t taddr, F&& f) {
 #pragma unroll
@@ -577,7 +595,7 @@ __device__ __forceinline__ void row_to_tmem(uint32_t tile, uint32_t chunk_bytes,
 }
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_BWD, 1)      // 10 warps: 3 on two of the four sub-partitions -> at most 168 registers
 attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                       const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                       const __grid_constant__ OutMaps map_dq, const MtGeo g) {
@@ -588,6 +606,8 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const uint32_t base = smem_u32(smem_dyn);
   const uint32_t pool = base + C::POOL_OFF, ds_t = base + C::DS_OFF, bar = base + C::BAR_OFF;
   float* kn = reinterpret_cast<float*>(smem_dyn + C::KN_OFF);
+  float* xd = reinterpret_cast<float*>(smem_dyn + C::XCH_OFF);     // delta of a row (written by the row's first thread)
+  float* xq = xd + 128;                                            // L2: |q|^2 (second thread), then [128, 384): rowsum(G) halves
   auto full = [&](uint32_t st) { return bar + 8u * st; };
   auto empty = [&](uint32_t st) { return bar + 8u * (NP + st); };
   const uint32_t a_ready = bar + 8u * (2 * NP), stg_full = a_ready + 16, dq_full = a_ready + 24, dq_free = a_ready + 32,
@@ -607,9 +627,9 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     for (int i = 0; i < NP; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
-    mbar_init(a_ready, 128); mbar_init(stg_full, 128); mbar_init(dq_full, 1); mbar_init(dq_free, 128);
-    mbar_init(sdp_full, 1); mbar_init(sdp_free, 128);
-    for (int i = 0; i < 2; ++i) { mbar_init(ds_full(i), 128); mbar_init(ds_empty(i), 1); }
+    mbar_init(a_ready, NCOMP_BWD); mbar_init(stg_full, NCOMP_BWD); mbar_init(dq_full, 1); mbar_init(dq_free, NCOMP_BWD);
+    mbar_init(sdp_full, 1); mbar_init(sdp_free, NCOMP_BWD);
+    for (int i = 0; i < 2; ++i) { mbar_init(ds_full(i), NCOMP_BWD); mbar_init(ds_empty(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc512(tmem_slot);
@@ -619,6 +639,7 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const uint32_t tmem = *tmem_slot_ptr;
   pdl_trigger();
   pdl_wait();
+  if (g.skew_ns > 0) { const unsigned ns = (blockIdx.x % 4u) * (unsigned)g.skew_ns; if (ns) __nanosleep(ns); }
   const int total = g.B * g.H;
 
   if (warp == 0) {
@@ -664,6 +685,20 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             for (int c = 0; c < DC; ++c) tma_load_3d(pool + st * STG + c * BCH, &map_q, full(st), col0 + 64 * c, t * 128 + 64 * hf, b);
           }
           tr(1);
+          {
+            // ask for the NEXT tile's operands in L2 now, a whole tile ahead: their TMA loads then only pay the L2 latency
+            const bool last_t = t + 1 == g.n_t;
+            const int wn = last_t ? w + (int)gridDim.x : w, tn = last_t ? 0 : t + 1;
+            if (wn < total && !g.no_prefetch) {
+              const int bn = wn / g.H, cn = (wn % g.H) * D;
+              for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int c = 0; c < DC; ++c) {
+                  tma_prefetch_3d(&map_do, cn + 64 * c, tn * 128 + 64 * hf, bn);
+                  tma_prefetch_3d(&map_q, cn + 64 * c, tn * 128 + 64 * hf, bn);
+                }
+            }
+          }
           for (int kb = 0; kb < g.n_b; ++kb) {
             service_store(false);
             uint32_t st = acquire(rq0 + 4 + 2 * kb);
@@ -753,108 +788,131 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
     }
   } else {
-    // ---------------------------------------------------------------- thread = query row
-    const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
+    // ---------------------------------------------------------------- two threads per query row (two warps per TMEM lane
+    // quadrant, so that each scheduler has a second warp to run while the first waits on TMEM, MUFU or shared memory): the first
+    // (half 0) moves the dO row to TMEM and computes delta, the second the Q row; in the block loop each owns 32 of the 64 keys;
+    // at the end each drains half of the dQ columns
+    const int quad = warp & 3, half = (warp - 2) >> 2, row = quad * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const float sc2 = g.scale * LOG2E;
     const int hf = row >> 6, lrow = row & 63;          // this row's half of the Q / dO / staging tiles, and its row inside the stage
+    constexpr int NCH = (D + 31) / 32, CH0 = (NCH + 1) / 2;                 // 32-column drain chunks; the first thread takes CH0 of them
     uint32_t bc0 = 0, tc = 0;
-    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 5);
+    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 5);                  // warp 4: quadrant 0, half 0
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / g.H, h = w % g.H, col0 = h * D;
       if (MODE == VG_ATTN_L2) {
-        named_bar(2, 128);
-        for (int j = tid; j < g.NK; j += 128)
+        named_bar(2, NCOMP_BWD);
+        for (int j = tid; j < g.NK; j += NCOMP_BWD)
           kn[j] = j < g.S ? row_sqnorm<D>(g.k + ((int64_t)b * g.S + j) * g.ld + col0) : 0.f;
-        named_bar(2, 128);
       }
       for (int t = 0; t < g.n_t; ++t, ++tc) {
         const uint32_t tpar = tc & 1u, rq0 = tc * R;
         const int row_g = t * 128 + row;
         const bool row_on = row_g < g.S;
         const bool warp_on = t * 128 + quad * 32 < g.S;
-        // this row of O comes from global memory and is requested BEFORE the wait for the dO tile so that the latencies overlap
-        uint4 orow[D / 8];
-        if (row_on) {
-          const bf16* op = g.o + ((int64_t)b * g.S + row_g) * g.ldo + col0;
-#pragma unroll
-          for (int c8 = 0; c8 < D / 8; ++c8) orow[c8] = __ldg(reinterpret_cast<const uint4*>(op + 8 * c8));
-        }
         float delta = 0.f, lse2 = 1e30f, qq = 0.f;
         const uint32_t r_do = rq0 + hf, r_q = rq0 + 2 + hf;
+        // delta = rowsum(dO * O).  O comes from global memory; eight lanes share a row so that every request is a whole 128-byte
+        // line (one row per thread costs an L1 wavefront per row and instruction: ~2 us per tile).  This warp takes 16 rows of its
+        // quadrant, four at a time; the loads are issued BEFORE the wait for the dO tile so that the latencies overlap.
+        const int g8 = lane >> 3, p8 = lane & 7;
+        const int dr0 = quad * 32 + half * 16 + g8;      // + 4 s: the rows this lane helps with
+        uint4 ov[4][DC];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int rg = t * 128 + dr0 + 4 * s4;
+          const bf16* op = g.o + ((int64_t)b * g.S + min(rg, g.S - 1)) * g.ldo + col0 + 8 * p8;
+#pragma unroll
+          for (int c = 0; c < DC; ++c)
+            ov[s4][c] = (rg < g.S && 64 * c + 8 * p8 < D) ? __ldg(reinterpret_cast<const uint4*>(op + 64 * c)) : make_uint4(0u, 0u, 0u, 0u);
+        }
         mbar_wait(full(r_do % NP), (r_do / NP) & 1u);
         tr(50);
-        {                                                // dO row -> TMEM (rows beyond S were zero-filled by TMA); delta = rowsum(dO * O)
-          float d4[4] = {0.f, 0.f, 0.f, 0.f};
-          row_to_tmem<D>(pool + (r_do % NP) * STG, BCH, lrow, t_lane + DOA_COL, [&](int c, const uint32_t (&r)[16], int n) {
-            if (row_on) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (4 * i < n) {
-                  const uint4 ov = orow[(c >> 2) + i];
-                  d4[0] = fmaf(bf16_lo(r[4 * i]), bf16_lo(ov.x), d4[0]); d4[1] = fmaf(bf16_hi(r[4 * i]), bf16_hi(ov.x), d4[1]);
-                  d4[2] = fmaf(bf16_lo(r[4 * i + 1]), bf16_lo(ov.y), d4[2]); d4[3] = fmaf(bf16_hi(r[4 * i + 1]), bf16_hi(ov.y), d4[3]);
-                  d4[0] = fmaf(bf16_lo(r[4 * i + 2]), bf16_lo(ov.z), d4[0]); d4[1] = fmaf(bf16_hi(r[4 * i + 2]), bf16_hi(ov.z), d4[1]);
-                  d4[2] = fmaf(bf16_lo(r[4 * i + 3]), bf16_lo(ov.w), d4[2]); d4[3] = fmaf(bf16_hi(r[4 * i + 3]), bf16_hi(ov.w), d4[3]);
-                }
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int rr = dr0 + 4 * s4;                   // row of the tile (same 64-row half, i.e. same stage, as this thread's row)
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < DC; ++c)
+            if (64 * c + 8 * p8 < D) {
+              uint32_t x, y, z, wv;
+              lds128(swz(pool + (r_do % NP) * STG + c * BCH, rr & 63, p8), x, y, z, wv);
+              const uint4 o4 = ov[s4][c];
+              d4[0] = fmaf(bf16_lo(x), bf16_lo(o4.x), d4[0]); d4[1] = fmaf(bf16_hi(x), bf16_hi(o4.x), d4[1]);
+              d4[2] = fmaf(bf16_lo(y), bf16_lo(o4.y), d4[2]); d4[3] = fmaf(bf16_hi(y), bf16_hi(o4.y), d4[3]);
+              d4[0] = fmaf(bf16_lo(z), bf16_lo(o4.z), d4[0]); d4[1] = fmaf(bf16_hi(z), bf16_hi(o4.z), d4[1]);
+              d4[2] = fmaf(bf16_lo(wv), bf16_lo(o4.w), d4[2]); d4[3] = fmaf(bf16_hi(wv), bf16_hi(o4.w), d4[3]);
+            }
+          float dsum = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+          dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+          dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+          if (p8 == 0) {
+            xd[rr] = dsum;
+            if (t * 128 + rr < g.S) g.delta[(int64_t)w * g.S + t * 128 + rr] = dsum;
+          }
+        }
+        if (half == 0) {                                 // dO row -> TMEM (rows beyond S were zero-filled by TMA)
+          row_to_tmem<D>(pool + (r_do % NP) * STG, BCH, lrow, t_lane + DOA_COL, [&](int, const uint32_t (&)[16], int) {});
+        } else {
+          mbar_wait(full(r_q % NP), (r_q / NP) & 1u);
+          row_to_tmem<D>(pool + (r_q % NP) * STG, BCH, lrow, t_lane + QA_COL, [&](int c, const uint32_t (&r)[16], int n) {
+            if (MODE == VG_ATTN_L2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < n) { const float a = bf16_lo(r[i]), bb = bf16_hi(r[i]); qq = fmaf(a, a, qq); qq = fmaf(bb, bb, qq); }
             }
           });
-          delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          if (MODE == VG_ATTN_L2) xq[row] = qq;
         }
-        if (row_on) {
-          g.delta[(int64_t)w * g.S + row_g] = delta;
-          lse2 = __ldg(g.lse + (int64_t)w * g.S + row_g) * LOG2E;
-        }
-        mbar_wait(full(r_q % NP), (r_q / NP) & 1u);
-        row_to_tmem<D>(pool + (r_q % NP) * STG, BCH, lrow, t_lane + QA_COL, [&](int c, const uint32_t (&r)[16], int n) {
-          if (MODE == VG_ATTN_L2) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < n) { const float a = bf16_lo(r[i]), bb = bf16_hi(r[i]); qq = fmaf(a, a, qq); qq = fmaf(bb, bb, qq); }
-          }
-        });
+        if (row_on) lse2 = __ldg(g.lse + (int64_t)w * g.S + row_g) * LOG2E;
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(a_ready);                            // both operand rows are in TMEM
-        named_bar(3 + hf, 64);                           // the 64 threads of this half have read their dO and Q stages ...
-        if (lrow == 0) { mbar_arrive(empty(r_do % NP)); mbar_arrive(empty(r_q % NP)); }   // ... which go back to the pool
+        mbar_arrive(a_ready);                            // this thread's operand row is in TMEM
+        named_bar(3 + hf, 128);                          // the 128 threads that read this half's dO and Q stages are done with them ...
+        if (lrow == 0 && half == 0) { mbar_arrive(empty(r_do % NP)); mbar_arrive(empty(r_q % NP)); }   // ... which go back to the pool
+        {                                                // next tile's O row and lse entry: into L2 (see the producer's prefetch)
+          const bool last_t = t + 1 == g.n_t;
+          const int wn = last_t ? w + (int)gridDim.x : w, rn = (last_t ? 0 : t + 1) * 128 + row;
+          if (half == 0 && wn < total && rn < g.S && !g.no_prefetch) {
+            const bf16* op = g.o + ((int64_t)(wn / g.H) * g.S + rn) * g.ldo + (wn % g.H) * D;
+#pragma unroll
+            for (int c = 0; c < D; c += 64) prefetch_l2(op + c);
+            if ((row & 31) == 0) prefetch_l2(g.lse + (int64_t)wn * g.S + rn);
+          }
+        }
+        named_bar(2, NCOMP_BWD);                         // delta and |q|^2 of every row are in shared memory (and, L2, the key norms)
+        delta = xd[row];
+        if (MODE == VG_ATTN_L2) qq = xq[row];
         tr(51);
         float gsum = 0.f;
         for (int j = 0; j < g.n_b; ++j) {
           const uint32_t c = bc0 + j;
-          const int buf = c & 1, nk = min(64, g.NK - 64 * j), c0 = 64 * j;
-          uint32_t s0[32], s1[32], p0[32], p1[32], pk[16];
+          const int buf = c & 1, nk = min(64, g.NK - 64 * j), c0 = 64 * j + 32 * half;
+          const int mine = min(32, nk - 32 * half);      // this thread's keys of the block: 32, 16 or none
+          uint32_t s0[32], p0[32], pk[16];
           mbar_wait(sdp_full, c & 1u);
           tr(60 + j);
           tc_fence_after();
-          if (warp_on) {                                 // the whole block into registers, then the TMEM pair is released at once
-            if (nk >= 32) { tmem_ld32_nowait(t_lane + S_COL, s0); tmem_ld32_nowait(t_lane + DP_COL, p0); }
-            else { tmem_ld16p(t_lane + S_COL, s0); tmem_ld16p(t_lane + DP_COL, p0); }
-            if (nk == 64) { tmem_ld32_nowait(t_lane + S_COL + 32, s1); tmem_ld32_nowait(t_lane + DP_COL + 32, p1); }
-            else if (nk == 48) { tmem_ld16p(t_lane + S_COL + 32, s1); tmem_ld16p(t_lane + DP_COL + 32, p1); }
+          if (warp_on && mine > 0) {                     // the thread's part into registers, then the TMEM pair is released at once
+            if (mine == 32) { tmem_ld32_nowait(t_lane + S_COL + 32 * half, s0); tmem_ld32_nowait(t_lane + DP_COL + 32 * half, p0); }
+            else { tmem_ld16p(t_lane + S_COL + 32 * half, s0); tmem_ld16p(t_lane + DP_COL + 32 * half, p0); }
             tmem_ld_wait();
           }
           tc_fence_before();
           mbar_arrive(sdp_free);                         // the next S / dP pair is computed while this one is exponentiated
           mbar_wait(ds_empty(buf), ((c >> 1) & 1u) ^ 1u);           // dQ MMA of block j-2 has consumed this dS buffer
           tr(70 + j);
-          if (warp_on) {
+          if (warp_on && mine > 0) {
             const uint32_t tile = ds_t + buf * QCH;
-            if (nk >= 32) {
+            if (mine == 32) {
               if (c0 + 32 <= g.S) dq_group<32, false, MODE>(s0, p0, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
               else dq_group<32, true, MODE>(s0, p0, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-              put_row<32>(tile, row, 0, pk);
+              put_row<32>(tile, row, 32 * half, pk);
             } else {
               dq_group<16, true, MODE>(s0, p0, c0, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-              put_row<16>(tile, row, 0, pk);
-            }
-            if (nk == 64) {
-              if (c0 + 64 <= g.S) dq_group<32, false, MODE>(s1, p1, c0 + 32, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-              else dq_group<32, true, MODE>(s1, p1, c0 + 32, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-              put_row<32>(tile, row, 32, pk);
-            } else if (nk == 48) {
-              dq_group<16, true, MODE>(s1, p1, c0 + 32, g.S, qq, kn, sc2, lse2, delta, g.scale, gsum, pk);
-              put_row<16>(tile, row, 32, pk);
+              put_row<16>(tile, row, 32 * half, pk);
             }
           }
           fence_async_smem();
@@ -862,6 +920,11 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tr(80 + j);
         }
         bc0 += g.n_b;
+        if (MODE == VG_ATTN_L2) {                        // rowsum(G) of a row = the sum of its two threads' halves
+          xq[128 + 128 * half + row] = gsum;
+          named_bar(2, NCOMP_BWD);
+          gsum += xq[128 + 128 * (half ^ 1) + row];
+        }
         // ---- drain dQ: TMEM -> (L2: rowsum(G) q - G K) -> bf16 -> this row's half of the staging tile (two pool stages) -> the
         //      producer warp stores it
         mbar_wait(dq_full, tpar);                       // every MMA of the tile is complete (the TMEM operand rows may be replaced)
@@ -872,7 +935,9 @@ attn_bwd_dq_mt_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const uint32_t stg = pool + (r_st % NP) * STG;
         if (warp_on) {
 #pragma unroll
-          for (int c = 0; c < D; c += 32) {
+          for (int k = 0; k < NCH; ++k) {
+            if ((k < CH0) != (half == 0)) continue;
+            const int c = 32 * k;
             uint32_t v[32], qv[16];
             const int n = (D - c) >= 32 ? 32 : 16;
             if (MODE == VG_ATTN_L2) {                    // the q row is still in TMEM (operand columns, two bf16 per column)
@@ -913,18 +978,18 @@ template <int D> struct DkvCfg {
   static constexpr int PT_OFF = DOR_OFF + NS * DC * BCH, DST_OFF = PT_OFF + QCH;
   static constexpr int LSE_OFF = DST_OFF + QCH, DEL_OFF = LSE_OFF + MAXNK * 4, QN_OFF = DEL_OFF + MAXNK * 4;
   static constexpr int NBAR = 8 + 2 * NS + 7;
-  static constexpr int smem(int mode) { return (mode == VG_ATTN_L2 ? QN_OFF + MAXNK * 4 : QN_OFF) + NBAR * 8 + 16; }
+  static constexpr int smem(int mode) { return (mode == VG_ATTN_L2 ? QN_OFF + MAXNK * 4 + 512 : QN_OFF) + NBAR * 8 + 16; }   // L2: |q|^2 table + 128 floats
   static_assert(NS * DC * BCH >= 128 * D * 2, "the dK / dV staging tiles alias the Q and dO rings");
 };
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_BWD, 1)
 attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                        const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                        const __grid_constant__ OutMaps map_dk, const __grid_constant__ OutMaps map_dv, const MtGeo g) {
   using C = DkvCfg<D>;
   constexpr int DC = C::DC, KS = C::KS, NS = C::NS, DK_COL = C::DK_COL, DV_COL = C::DV_COL;
-  constexpr int BAR_OFF = MODE == VG_ATTN_L2 ? C::QN_OFF + MAXNK * 4 : C::QN_OFF;
+  constexpr int BAR_OFF = MODE == VG_ATTN_L2 ? C::QN_OFF + MAXNK * 4 + 512 : C::QN_OFF;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t base = smem_u32(smem_dyn);
   const uint32_t k_t = base + C::K_OFF, v_t = base + C::V_OFF, qr = base + C::QR_OFF, dor = base + C::DOR_OFF;
@@ -932,6 +997,7 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   float* lse_s = reinterpret_cast<float*>(smem_dyn + C::LSE_OFF);
   float* del_s = reinterpret_cast<float*>(smem_dyn + C::DEL_OFF);
   float* qn_s = reinterpret_cast<float*>(smem_dyn + C::QN_OFF);      // L2 mode only
+  float* gs_s = qn_s + MAXNK;                                         // L2 mode only: colsum(G) exchange between a row's two threads
   const uint32_t kvt_full = bar, kvt_empty = bar + 8, out_full = bar + 16, out_free = bar + 24;
   const uint32_t pt_full = bar + 32, pt_empty = bar + 40, dst_full = bar + 48, dst_empty = bar + 56;
   auto qdo_full = [&](int i) { return bar + 8u * (8 + i); };
@@ -950,10 +1016,10 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
-    mbar_init(kvt_full, 1); mbar_init(kvt_empty, 1); mbar_init(out_full, 1); mbar_init(out_free, 128); mbar_init(stg_full, 128);
-    mbar_init(pt_full, 128); mbar_init(pt_empty, 1); mbar_init(dst_full, 128); mbar_init(dst_empty, 1);
+    mbar_init(kvt_full, 1); mbar_init(kvt_empty, 1); mbar_init(out_full, 1); mbar_init(out_free, NCOMP_BWD); mbar_init(stg_full, NCOMP_BWD);
+    mbar_init(pt_full, NCOMP_BWD); mbar_init(pt_empty, 1); mbar_init(dst_full, NCOMP_BWD); mbar_init(dst_empty, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(qdo_full(i), 1); mbar_init(qdo_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(st_full(i), 1); mbar_init(st_free(i), 128); mbar_init(dpt_full(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(st_full(i), 1); mbar_init(st_free(i), NCOMP_BWD); mbar_init(dpt_full(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc512(tmem_slot);
@@ -991,6 +1057,27 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             tma_load_3d(v_t + c * QCH, &map_v, kvt_full, col0 + 64 * c, t * 128, b);
           }
           store_pending();                             // the ring is refilled only after the staged outputs have been read from it
+          {
+            // the CTAs run in lock step, so first-touch loads reach HBM as bursts: ask for the next item's K / V tiles (and, on the
+            // last key tile of a (b, h), for the next (b, h)'s Q / dO blocks) in L2 one item ahead
+            const bool last_t = t + 1 == g.n_t;
+            const int wn = last_t ? w + (int)gridDim.x : w, tn = last_t ? 0 : t + 1;
+            if (wn < total) {
+              const int bn = wn / g.H, cn = (wn % g.H) * D;
+#pragma unroll
+              for (int c = 0; c < DC; ++c) {
+                tma_prefetch_3d(&map_k, cn + 64 * c, tn * 128, bn);
+                tma_prefetch_3d(&map_v, cn + 64 * c, tn * 128, bn);
+              }
+              if (last_t)
+                for (int i = 0; i < g.n_b; ++i)
+#pragma unroll
+                  for (int c = 0; c < DC; ++c) {
+                    tma_prefetch_3d(&map_q, cn + 64 * c, i * 64, bn);
+                    tma_prefetch_3d(&map_do, cn + 64 * c, i * 64, bn);
+                  }
+            }
+          }
           for (int i = 0; i < g.n_b; ++i, ++bc) {
             const int st = bc % NS;
             mbar_wait(qdo_empty(st), ((bc / NS) & 1u) ^ 1u);
@@ -1093,24 +1180,25 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
       }
     }
   } else {
-    // ---------------------------------------------------------------- thread = key row
-    const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
+    // ---------------------------------------------------------------- two threads per key row: each owns one 32-query half of
+    // every 64-query block (two warps per scheduler hide each other's TMEM / MUFU / shared-memory latencies)
+    const int quad = warp & 3, half = (warp - 2) >> 2, row = quad * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const float sc2 = g.scale * LOG2E;
     uint32_t bc0 = 0, ic = 0;
-    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 8);
+    Tracer tr(threadIdx.x == 128 ? g.trace : nullptr, 8);        // warp 4: quadrant 0, half 0
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / g.H, h = w % g.H, col0 = h * D;
       tr(50);
       // per-query statistics of this problem -> smem: lse * log2e (+huge for padding queries: P = 0), delta, (L2) |q|^2
-      named_bar(2, 128);
-      for (int q = tid; q < g.n_b * 64 && q < MAXNK; q += 128) {
+      named_bar(2, NCOMP_BWD);
+      for (int q = tid; q < g.n_b * 64 && q < MAXNK; q += NCOMP_BWD) {
         const bool on = q < g.S;
         lse_s[q] = on ? __ldg(g.lse + (int64_t)w * g.S + q) * LOG2E : 1e30f;
         del_s[q] = on ? __ldg(g.delta + (int64_t)w * g.S + q) : 0.f;
         if (MODE == VG_ATTN_L2) qn_s[q] = on ? row_sqnorm<D>(g.q + ((int64_t)b * g.S + q) * g.ld + col0) : 0.f;
       }
-      named_bar(2, 128);
+      named_bar(2, NCOMP_BWD);
       for (int t = 0; t < g.n_t; ++t, ++ic) {
         const uint32_t ipar = ic & 1u;
         const int key_g = t * 128 + row;
@@ -1120,29 +1208,25 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
         for (int i = 0; i < g.n_b; ++i) {
           const uint32_t c = bc0 + i;
           const int buf = c & 1, ni = min(64, g.NK - 64 * i);
-          uint32_t f[32];                               // P * scale (dot) or P * scale / dist (L2) of this key row, packed bf16
+          uint32_t f[16];                               // P * scale (dot) or P * scale / dist (L2) of this thread's 32 queries, packed bf16
           // stage A: S^T -> P^T (smem, A operand of dV) and the factor f kept in registers
           mbar_wait(st_full(buf), (c >> 1) & 1u);
           tr(60 + i);
           tc_fence_after();
           mbar_wait(pt_empty, (c & 1u) ^ 1u);             // dV MMA of the previous block has consumed the P^T buffer
           tr(65 + i);
-          if (warp_on) {
-#pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
-              if (cc >= ni) break;
-              uint32_t sv[32], pk[16];
-              const int q0 = 64 * i + cc;
-              if (ni - cc >= 32) {
-                tmem_ld32(t_lane + (uint32_t)(64 * buf + cc), sv);
-                dkv_stage_a<32, MODE>(sv, q0, kk2, qn_s, lse_s, sc2, g.scale, pk, &f[cc >> 1]);
-                put_row<32>(pt_t, row, cc, pk);
-              } else {
-                tmem_ld16p(t_lane + (uint32_t)(64 * buf + cc), sv);
-                tmem_ld_wait();
-                dkv_stage_a<16, MODE>(sv, q0, kk2, qn_s, lse_s, sc2, g.scale, pk, &f[cc >> 1]);
-                put_row<16>(pt_t, row, cc, pk);
-              }
+          const int cc = 32 * half, q0 = 64 * i + cc;
+          if (warp_on && cc < ni) {
+            uint32_t sv[32], pk[16];
+            if (ni - cc >= 32) {
+              tmem_ld32(t_lane + (uint32_t)(64 * buf + cc), sv);
+              dkv_stage_a<32, MODE>(sv, q0, kk2, qn_s, lse_s, sc2, g.scale, pk, f);
+              put_row<32>(pt_t, row, cc, pk);
+            } else {
+              tmem_ld16p(t_lane + (uint32_t)(64 * buf + cc), sv);
+              tmem_ld_wait();
+              dkv_stage_a<16, MODE>(sv, q0, kk2, qn_s, lse_s, sc2, g.scale, pk, f);
+              put_row<16>(pt_t, row, cc, pk);
             }
           }
           tc_fence_before();
@@ -1155,22 +1239,17 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
           tc_fence_after();
           mbar_wait(dst_empty, (c & 1u) ^ 1u);
           tr(80 + i);
-          if (warp_on) {
-#pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
-              if (cc >= ni) break;
-              uint32_t dv[32], pk[16];
-              const int q0 = 64 * i + cc;
-              if (ni - cc >= 32) {
-                tmem_ld32(t_lane + (uint32_t)(64 * buf + cc), dv);
-                dkv_stage_b<32, MODE>(dv, q0, del_s, &f[cc >> 1], gsum, pk);
-                put_row<32>(dst_t, row, cc, pk);
-              } else {
-                tmem_ld16p(t_lane + (uint32_t)(64 * buf + cc), dv);
-                tmem_ld_wait();
-                dkv_stage_b<16, MODE>(dv, q0, del_s, &f[cc >> 1], gsum, pk);
-                put_row<16>(dst_t, row, cc, pk);
-              }
+          if (warp_on && cc < ni) {
+            uint32_t dv[32], pk[16];
+            if (ni - cc >= 32) {
+              tmem_ld32(t_lane + (uint32_t)(64 * buf + cc), dv);
+              dkv_stage_b<32, MODE>(dv, q0, del_s, f, gsum, pk);
+              put_row<32>(dst_t, row, cc, pk);
+            } else {
+              tmem_ld16p(t_lane + (uint32_t)(64 * buf + cc), dv);
+              tmem_ld_wait();
+              dkv_stage_b<16, MODE>(dv, q0, del_s, f, gsum, pk);
+              put_row<16>(dst_t, row, cc, pk);
             }
           }
           tc_fence_before();
@@ -1185,7 +1264,13 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
         tr(55);
         tc_fence_after();
         const bf16* kg = g.k + ((int64_t)b * g.S + min(key_g, g.S - 1)) * g.ld + col0;    // L2: this key's row (the smem K tile is being refilled)
-        if (warp_on) {
+        if (MODE == VG_ATTN_L2) {                        // colsum(G) of a key row = the sum of its two threads' halves
+          if (half == 1) gs_s[row] = gsum;
+          named_bar(2, NCOMP_BWD);
+          gsum += gs_s[row];
+          named_bar(2, NCOMP_BWD);
+        }
+        if (warp_on && half == 0) {                      // dK by the first thread of the row, dV by the second
 #pragma unroll
           for (int c = 0; c < D; c += 32) {
             uint32_t v[32];
@@ -1208,6 +1293,8 @@ attn_bwd_dkv_mt_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             }
             stg_write<D>(qr, row, c, o, n);
           }
+        }
+        if (warp_on && half == 1) {
 #pragma unroll
           for (int c = 0; c < D; c += 32) {
             uint32_t v[32];
@@ -1278,6 +1365,8 @@ MtGeo make_geo(int B, int H, int S, int64_t ld, int64_t ldo, float scale, const 
   g.B = B; g.H = H; g.S = S; g.NK = (S + 15) / 16 * 16; g.n_t = (S + 127) / 128; g.n_b = (g.NK + 63) / 64; g.ld = ld; g.ldo = ldo;
   g.scale = scale; g.lse = lse; g.delta = delta;
   g.q = static_cast<const bf16*>(q); g.k = static_cast<const bf16*>(k); g.o = static_cast<const bf16*>(o);
+  g.dq = g.dk = g.dv = nullptr; g.ldd = 0;
+  { const char* e = getenv("VG_ATTN_SKEW"); g.skew_ns = e ? atoi(e) : 0; e = getenv("VG_ATTN_NOPF"); g.no_prefetch = e ? atoi(e) : 0; }
   return g;
 }
 
@@ -1311,10 +1400,10 @@ int launch_bwd(const CUtensorMap& mq128, const CUtensorMap& mdo128, const CUtens
   rc = set_smem_once(attn_bwd_dkv_mt_kernel<D, MODE>, DkvCfg<D>::smem(MODE), &set2);
   if (rc) return rc;
   const int grid = min(g.B * g.H, num_sms());
-  launch_pdl(attn_bwd_dq_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DqCfg<D>::SMEM, st, mq64, mdo64, mk64, mv64, mdq, g);
+  launch_pdl(attn_bwd_dq_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS_BWD), (size_t)DqCfg<D>::SMEM, st, mq64, mdo64, mk64, mv64, mdq, g);
   rc = check_launch("attention_bwd_dq_mt");
   if (rc) return rc;
-  launch_pdl(attn_bwd_dkv_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)DkvCfg<D>::smem(MODE), st, mk128, mv128, mq64, mdo64, mdk, mdv, g);
+  launch_pdl(attn_bwd_dkv_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS_BWD), (size_t)DkvCfg<D>::smem(MODE), st, mk128, mv128, mq64, mdo64, mdk, mdv, g);
   return check_launch("attention_bwd_dkv_mt");
 }
 
@@ -1383,7 +1472,8 @@ int attention_bwd_mt(int mode, int B, int H, int S, int d, const void* q, const 
   if ((rc = make_out_maps(&mdq, dq, B, S, cols, ldd, d, 64))) return rc;
   if ((rc = make_out_maps(&mdk, dk, B, S, cols, ldd, d))) return rc;
   if ((rc = make_out_maps(&mdv, dv, B, S, cols, ldd, d))) return rc;
-  const MtGeo g = make_geo(B, H, S, ld, ldo, scale, q, k, o, const_cast<float*>(lse), delta);
+  MtGeo g = make_geo(B, H, S, ld, ldo, scale, q, k, o, const_cast<float*>(lse), delta);
+  g.dq = static_cast<bf16*>(dq); g.dk = static_cast<bf16*>(dk); g.dv = static_cast<bf16*>(dv); g.ldd = ldd;
   VG_MT_DISPATCH(d, mode, (rc = launch_bwd<D, MODE>(mq128, mdo128, mk64, mv64, mdq, mk128, mv128, mq64, mdo64, mdk, mdv, g, st)));
   return rc;
 }
