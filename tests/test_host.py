@@ -79,6 +79,10 @@ def test_mirrors_keep_reference_state_dict_and_init():
 def test_no_cpu_fallback_and_no_oracle_import():
     import vitgan_b200 as vb
     gan = vb.v2.ViTGAN(vb.v2.Config(embeddings_dimension=32, transformer_blocks_count=1, image_size=16, batch_size=768))
+    # reference default p = 0.1 in training mode (src/v2/modules.py:99,179-180): unsupported => error, never silently skipped
+    with pytest.raises(RuntimeError, match="nn.Dropout"):
+        gan.discriminator(torch.randn(2, 3, 16, 16))
+    gan.eval()
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         gan.discriminator(torch.randn(2, 3, 16, 16))
     out = subprocess.check_output([sys.executable, "-c",
