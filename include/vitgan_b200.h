@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VG_ABI_VERSION 4
+#define VG_ABI_VERSION 5
 
 typedef enum { VG_F32 = 0, VG_BF16 = 1 } vg_dtype;
 typedef enum {
@@ -220,6 +220,11 @@ int vg_act_backward(int dtype, int64_t n, const void* dy, const void* aux, int a
  * captured step).  fp32 logits [rows, C]; rows %% rows_per_group == 0; at most 64 groups. */
 int vg_softmax_ce(const float* logits, const int64_t* targets, int rows, int C, int rows_per_group, float* losses,
                   float* dlogits, void* stream);
+
+/* Fused nn.BCELoss (mean reduction, float targets in [0,1]; src/v1/gan.py:16-20 pick_criterion, used at gan.py:222-252) over
+ * rows/rows_per_group groups of consecutive probabilities (D's sigmoid output [rows, 1]): losses[g] = mean BCE of group g with
+ * torch's log clamp at -100; dprob = d(sum_g losses[g])/dprob with torch's 1e-12 denominator clamp.  At most 64 groups. */
+int vg_bce(const float* prob, const float* target, int rows, int rows_per_group, float* losses, float* dprob, void* stream);
 
 /* utils.convert_to_uint8 (src/v2/utils.py:194-196): out = uint8(clamp(x * 127.5 + 127.5, 0, 255)), the de-normalisation at
  * the end of the sampling path (src/v2/generation.py:47-56, utils.py:165-166); byte-exact vs torch on identical fp32 input. */

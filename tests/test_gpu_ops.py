@@ -403,6 +403,33 @@ def test_softmax_ce_fused_head(vb):
         assert rel(got, ref.detach()) < 1e-5 and rel(zc.grad, z.grad) < 1e-5
 
 
+def test_bce_fused_head(vb):
+    """vg_bce == nn.BCELoss per group (src/v1/gan.py:16-20): values and gradient of the summed losses at fp32 1e-5, including
+    saturated probabilities (torch's -100 log clamp and 1e-12 denominator clamp)."""
+    g = gen(78)
+    for rows, rpg in ((256, 128), (128, 128), (96, 32)):
+        p = torch.sigmoid(torch.randn(rows, 1, generator=g) * 4)
+        p[0, 0], p[1, 0] = 0.0, 1.0
+        p.requires_grad_(True)
+        t = (torch.rand(rows, 1, generator=g) > 0.5).float()
+        t[0, 0], t[1, 0] = 0.0, 1.0                  # saturated and correct: loss 0, gradient 0
+        ref = torch.stack([F.binary_cross_entropy(p[i:i + rpg], t[i:i + rpg]) for i in range(0, rows, rpg)])
+        ref.sum().backward()
+        pc = p.detach().cuda().requires_grad_(True)
+        got = vb.functional.bce(pc, t.cuda(), rpg)
+        got.sum().backward()
+        assert rel(got, ref.detach()) < 1e-5 and rel(pc.grad, p.grad) < 1e-5
+    p = torch.tensor([[1.0], [0.0], [0.3]])          # saturated and wrong: -100 clamp, 1e12 gradient
+    t = torch.tensor([[0.0], [1.0], [1.0]])
+    pr = p.clone().requires_grad_(True)
+    ref = F.binary_cross_entropy(pr, t)
+    ref.backward()
+    pc = p.cuda().requires_grad_(True)
+    got = vb.functional.bce(pc, t.cuda())
+    got.sum().backward()
+    assert rel(got, ref.detach().reshape(1)) < 1e-6 and rel(pc.grad, pr.grad) < 1e-6
+
+
 def test_denorm_u8_is_byte_exact(vb):
     """vg_denorm_u8 == utils.convert_to_uint8 of the reference (src/v2/utils.py:194-196), bit for bit."""
     from oracle import v2 as o2

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/vitgan_b200.h but not exported"
     from vitgan_b200 import lib as L
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
-    assert L.lib.vg_version() == 4 and L.lib.vg_last_error() is not None
+    assert L.lib.vg_version() == 5 and L.lib.vg_last_error() is not None
 
 
 def test_ctypes_signatures_match_header_prototypes():

@@ -246,6 +246,27 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
   for (int g = threadIdx.x; g < n_groups; g += blockDim.x) losses[g] = s_loss[g];
 }
 
+// Fused nn.BCELoss (mean reduction, float targets: src/v1/gan.py:16-20, 222-252) over rows/rows_per_group groups of probabilities
+// (the discriminator's sigmoid output, one value per row): losses[g] = mean_{r in g} -(t log p + (1 - t) log(1 - p)) with both
+// logs clamped at -100 (torch's BCELoss), dprob = d(sum_g losses[g]) / dp = (p - t) / max(p (1 - p), 1e-12) / rows_per_group.
+__global__ void __launch_bounds__(1024)
+bce_kernel(const float* __restrict__ prob, const float* __restrict__ target, int rows, int rows_per_group,
+           float* __restrict__ losses, float* __restrict__ dprob) {
+  __shared__ float s_loss[64];
+  const int n_groups = rows / rows_per_group;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_loss[i] = 0.f;
+  __syncthreads();
+  const float inv = 1.0f / (float)rows_per_group;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float p = prob[r], t = target[r];
+    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
+    dprob[r] = (p - t) / fmaxf((1.0f - p) * p, 1e-12f) * inv;
+    atomicAdd(&s_loss[r / rows_per_group], -(t * lp + (1.0f - t) * lq) * inv);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < n_groups; g += blockDim.x) losses[g] = s_loss[g];
+}
+
 // utils.convert_to_uint8 (src/v2/utils.py:194-196): (images * 127.5 + 127.5).clamp(0, 255).to(uint8) -- two separately rounded
 // fp32 operations (no FMA contraction) and truncation, so the bytes equal the reference's on identical inputs.
 __device__ __forceinline__ uint8_t to_u8(float v) { return (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(v, 127.5f), 127.5f), 0.f), 255.f); }
@@ -395,6 +416,14 @@ extern "C" int vg_softmax_ce(const float* logits, const int64_t* targets, int ro
              "softmax_ce: rows %d must be a multiple of rows_per_group %d with at most 64 groups", rows, rows_per_group);
   softmax_ce_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, targets, rows, C, rows_per_group, losses, dlogits);
   return check_launch("softmax_ce");
+}
+
+extern "C" int vg_bce(const float* prob, const float* target, int rows, int rows_per_group, float* losses, float* dprob, void* stream) {
+  VG_REQUIRE(prob && target && losses && dprob, VG_ERR_ARG, "bce: NULL argument");
+  VG_REQUIRE(rows >= 1 && rows_per_group >= 1 && rows % rows_per_group == 0 && rows / rows_per_group <= 64, VG_ERR_SHAPE,
+             "bce: rows %d must be a multiple of rows_per_group %d with at most 64 groups", rows, rows_per_group);
+  bce_kernel<<<1, 1024, 0, as_stream(stream)>>>(prob, target, rows, rows_per_group, losses, dprob);
+  return check_launch("bce");
 }
 
 extern "C" int vg_denorm_u8(int dtype, const void* x, int64_t n, uint8_t* out, void* stream) {

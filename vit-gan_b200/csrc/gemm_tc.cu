@@ -550,138 +550,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 
-// ================================================================================================ weight-stationary variant
-// For the skinny Linear layers of the small ViT configs (K <= 384, N <= 384: the whole weight matrix is <= 96 KB of bf16)
-// the generic kernel re-fetches the B tile for every output tile (QKV at C2: 50 MB of L2->SM traffic for 8.6 MB of unique
-// operands).  Here B is loaded ONCE per CTA and stays resident; A is streamed once per 128-row m-tile through a ring of
-// k-block stages and multiplied against every n-tile (up to 3 accumulators side by side in TMEM, 4 rotating slots).
-//   smem: [B: n_tiles*kb_total tiles of 16 KB][A ring: na_stages x 16 KB][staging 64 KB][bias][barriers]
-template <int MODE, int ACT>
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
-                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
-  constexpr int NSLOT = 4;                       // TMEM accumulator slots of 128 columns
-  extern __shared__ uint8_t smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const int nb_tiles = p.n_tiles * p.kb_total;
-  const uint32_t b_base = smem_base;
-  const uint32_t a_base = b_base + (uint32_t)nb_tiles * B_BYTES;
-  const uint32_t stg_base = a_base + (uint32_t)p.na_stages * A_BYTES;
-  const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;
-  const uint32_t bar_base = bias_base + BIAS_BYTES;
-  auto a_full = [&](int s) { return bar_base + 8u * s; };              // 8
-  auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };       // 8
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };    // 4
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (20 + a); };   // 4
-  auto warp_bar = [&](int w) { return bar_base + 8u * (24 + w); };     // 8
-  const uint32_t b_full = bar_base + 8u * 32;
-  const uint32_t tmem_slot = bar_base + 8u * 33;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
-    for (int s = 0; s < 8; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
-    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(warp_bar(w), 1);
-    mbar_init(b_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_trigger();   // dependents may start their prologue; they wait for our completion before touching memory
-  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
-  const uint32_t b_lbo = p.trans_b ? 16u : p.mn_lbo, b_sbo = p.trans_b ? 1024u : p.mn_sbo, b_kstep = p.trans_b ? 32u : p.mn_kstep;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // B: every (n-tile, k-block) tile once
-      mbar_expect_tx(b_full, (uint32_t)nb_tiles * B_BYTES);
-      for (int n = 0; n < p.n_tiles; ++n)
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          const uint32_t sb = b_base + (uint32_t)(n * p.kb_total + kb) * B_BYTES;
-          if (p.trans_b) {
-            tma_load_2d(sb, &tmap_b, b_full, kb * BK, n * BN);
-          } else {
-            tma_load_2d(sb, &tmap_b, b_full, n * BN, kb * BK);
-            tma_load_2d(sb + 8192, &tmap_b, b_full, n * BN + 64, kb * BK);
-          }
-        }
-      // A: one pass per m-tile
-      int stage = 0; uint32_t phase = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(a_empty(stage), phase ^ 1u);
-          mbar_expect_tx(a_full(stage), A_BYTES);
-          tma_load_2d(a_base + stage * A_BYTES, &tmap_a, a_full(stage), kb * BK, mt * BM);
-          if (++stage == p.na_stages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.trans_b ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
-      mbar_wait(b_full, 0);
-      int stage = 0; uint32_t phase = 0;
-      uint32_t unit = 0;                              // running (m-tile, n-tile) counter -> TMEM slot = unit % 4
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(a_full(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = a_base + stage * A_BYTES;
-          for (int n = 0; n < p.n_tiles; ++n) {
-            if (kb == 0) {                            // first touch of this slot for this m-tile: the epilogue must have drained it
-              const uint32_t u = unit + n;
-              mbar_wait(tempty_bar(u % NSLOT), ((u / NSLOT) & 1u) ^ 1u);
-              tc_fence_after();
-            }
-            const uint32_t sb = b_base + (uint32_t)(n * p.kb_total + kb) * B_BYTES;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(((unit + n) % NSLOT) * BN);
-#pragma unroll
-            for (int k = 0; k < BK / UK; ++k)
-              tc_mma(d_tmem, make_desc(sa + k * 32u, 16u, 1024u), make_desc(sb + k * b_kstep, b_lbo, b_sbo), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          tc_commit(a_empty(stage));
-          if (++stage == p.na_stages) { stage = 0; phase ^= 1u; }
-        }
-        for (int n = 0; n < p.n_tiles; ++n) tc_commit(tfull_bar((unit + n) % NSLOT));
-        unit += p.n_tiles;
-      }
-    }
-  } else {
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
-    const uint32_t bufC = stg_base + (uint32_t)ew * STG_BYTES, bufX = bufC + 4096u;
-    const uint32_t wbar = warp_bar(ew);
-    uint32_t wphase = 0;
-    float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
-    uint32_t unit = 0;
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-      for (int n = 0; n < p.n_tiles; ++n, ++unit) {
-        const int slot = unit % NSLOT;
-        staged_tile<MODE, ACT>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BN + half * 64),
-                               tfull_bar(slot), (unit / NSLOT) & 1u, tempty_bar(slot), mt * BM + quad * 32, n * BN + half * 64, bufC, bufX, wbar,
-                               wphase, bias_s, lane);
-      }
-    }
-    if (lane == 0) tma_wait_read();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -757,7 +625,30 @@ bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
   return true;
 }
 
+// Bring-up knobs, read ONCE per process (thread-safe static initialisation; the launch path itself never calls getenv):
+//   VG_TC_DBG   bit 0 = epilogue skips global memory, bit 1 = force the direct (per-thread) epilogue
+//   VG_TC_BN    128 | 256 overrides the tile-width heuristic
+//   VG_TC_MN_DESC "lbo,sbo,kstep" (bytes) overrides the MN-major descriptor strides
+struct TcEnv {
+  int dbg = 0, bn = 0;
+  unsigned mn_lbo = 8192u, mn_sbo = 1024u, mn_kstep = 2048u;
+  TcEnv() {
+    if (const char* e = getenv("VG_TC_DBG")) dbg = atoi(e);
+    if (const char* e = getenv("VG_TC_BN")) bn = atoi(e);
+    if (const char* e = getenv("VG_TC_MN_DESC")) {
+      unsigned l = 0, sb = 0, ks = 0;
+      if (sscanf(e, "%u,%u,%u", &l, &sb, &ks) == 3) { mn_lbo = l; mn_sbo = sb; mn_kstep = ks; }
+    }
+  }
+};
+const TcEnv& tc_env() { static const TcEnv e; return e; }
+
+// one-time, thread-safe opt-in to the kernel's dynamic shared memory size (C++11 static initialisation)
+template <typename K>
+cudaError_t set_smem_once(K kernel, int bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
 int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
+  const TcEnv& env = tc_env();
   CUtensorMap ma, mb;
   int rc;
   // A: trans_a=0 stored [M,K] -> box {64 k, 128 m};  trans_a=1 stored [K,M] -> box {64 m, 64 k}
@@ -769,12 +660,10 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const int sms0 = num_sms();
   const int esz0 = a.c_dtype == VG_F32 ? 4 : 2;
   auto tma_ok0 = [&](const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz0) % 16 == 0; };
-  const char* dbg0 = getenv("VG_TC_DBG");
-  const bool stageable = !(dbg0 && (atoi(dbg0) & 2)) && a.c_row_group == 0 && a.res_row_mod == 0 && !a.a_rowsum && !a.ln_gamma && tma_ok0(a.C, a.ldc) &&
+  const bool stageable = !(env.dbg & 2) && a.c_row_group == 0 && a.res_row_mod == 0 && !a.a_rowsum && !a.ln_gamma && tma_ok0(a.C, a.ldc) &&
                          (!a.residual || tma_ok0(a.residual, a.ldres)) && (!a.aux || tma_ok0(a.aux, a.ldaux)) &&
                          (!a.c_pre || tma_ok0(a.c_pre, a.ldpre)) && !(a.c_dtype == VG_F32 && (a.aux || a.c_pre || a.act != VG_ACT_NONE));   // == epi_tma below
-  static int bn_env = -1;
-  if (bn_env < 0) { const char* e = getenv("VG_TC_BN"); bn_env = e ? atoi(e) : 0; }
+  const int bn_env = env.bn;
   bool wide = stageable && a.N % 256 == 0 && a.K >= 512 &&
               ((int64_t)((a.M + BM - 1) / BM) * (a.N / 256) >= sms0 ||
                (a.accumulate && a.K >= 4096 && (int64_t)((a.M + BM - 1) / BM) * (a.N / 256) >= 8));   // split-K supplies the parallelism
@@ -810,13 +699,8 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.act = a.act; p.act_param = a.act_param;
   p.aux = a.aux; p.ldaux = a.ldaux; p.residual = a.residual; p.ldres = a.ldres; p.c_pre = a.c_pre; p.ldpre = a.ldpre;
   p.c_row_group = a.c_row_group; p.res_row_mod = a.res_row_mod; p.res_row_off = a.res_row_off; p.accumulate = a.accumulate;
-  p.mn_lbo = 8192u; p.mn_sbo = 1024u; p.mn_kstep = 2048u;
-  if (const char* dbg = getenv("VG_TC_MN_DESC")) {   // bring-up knob: "lbo,sbo,kstep" in bytes
-    unsigned l = 0, sb = 0, ks = 0;
-    if (sscanf(dbg, "%u,%u,%u", &l, &sb, &ks) == 3) { p.mn_lbo = l; p.mn_sbo = sb; p.mn_kstep = ks; }
-  }
-  p.dbg = 0;
-  if (const char* d = getenv("VG_TC_DBG")) p.dbg = atoi(d);
+  p.mn_lbo = env.mn_lbo; p.mn_sbo = env.mn_sbo; p.mn_kstep = env.mn_kstep;
+  p.dbg = env.dbg;
   p.rowsum = a.a_rowsum;
   p.trace = g_trace;
   p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_mean = a.ln_mean; p.ln_rstd = a.ln_rstd; p.ln_eps = a.ln_eps;
@@ -853,62 +737,25 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   VG_REQUIRE(!(bn == 256 && mode == 0), VG_ERR_LAUNCH, "gemm_tc: internal: 256-wide tile without a staged epilogue");
   VG_REQUIRE(!a.ln_gamma || (mode == 1 && bn == 128), VG_ERR_UNSUPPORTED, "gemm_tc: fused LayerNorm needs the staged bf16 epilogue");
   const bool wide_k = bn == 256;
-  // weight-stationary variant: staged epilogue, A K-major, no split-K, whole B (+ >= 2 A stages) fits next to the staging tiles
-  const int nb_tiles = p.n_tiles * p.kb_total;
-  const int ws_budget = 227 * 1024 - (EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512);
-  int na = (ws_budget - nb_tiles * B_BYTES) / A_BYTES;
-  na = min(na, min(8, 2 * p.kb_total));
-  const bool ws_ok = !wide_k && !a.ln_gamma && mode != 0 && !a.trans_a && !a.accumulate && p.n_tiles <= 3 && na >= 2 && p.m_tiles >= 2 && (p.dbg & 8);   // opt-in (VG_TC_DBG=8): measured no faster than the generic kernel at C2 shapes
-  if (ws_ok) {
-    p.na_stages = na;
-    const int ws_smem = nb_tiles * B_BYTES + na * A_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + 1024 + 512;
-    const int ws_grid = min(p.m_tiles, sms);
-#define VG_WS_LAUNCH(MODE_, ACT_)                                                                                                 \
-  do {                                                                                                                            \
-    static int attr_smem = 0;                                                                                                     \
-    if (attr_smem < ws_smem) {                                                                                                    \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_ws_kernel<MODE_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc(ws): cudaFuncSetAttribute: %s", cudaGetErrorString(e));                \
-      attr_smem = 227 * 1024;                                                                                                     \
-    }                                                                                                                             \
-    launch_pdl(gemm_tc_ws_kernel<MODE_, ACT_>, dim3(ws_grid), dim3(NTHREADS), ws_smem, st, ma, mb, mc, mp, mr, mx, p);                                \
-  } while (0)
-    if (mode == 2) VG_WS_LAUNCH(2, 0);
-    else { VG_ACT_SWITCH(a.act, VG_WS_LAUNCH(1, ACT)) }
-#undef VG_WS_LAUNCH
-    return check_launch("gemm_tc_ws");
-  }
 #define VG_TC_LAUNCH(MODE_, ACT_, BN_)                                                                                         \
   do {                                                                                                                         \
     constexpr int smem_ = (BN_ == 256 ? 3 * (A_BYTES + 256 * BK * 2) : NSTAGES * STAGE_BYTES) + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512; \
-    static bool attr_set = false;                                                                                              \
-    if (!attr_set) {                                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE_, ACT_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_); \
-      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                 \
-      attr_set = true;                                                                                                         \
-    }                                                                                                                          \
+    static const cudaError_t attr_e = set_smem_once(gemm_tc_kernel<MODE_, ACT_, BN_>, smem_);                                  \
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_e));         \
     launch_pdl(gemm_tc_kernel<MODE_, ACT_, BN_>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);             \
   } while (0)
   if (remap) {
     constexpr int smem_ = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, VG_ACT_NONE, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_);
-      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
+    static const cudaError_t attr_e = set_smem_once(gemm_tc_kernel<1, VG_ACT_NONE, 128, false, true>, smem_);
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_e));
     launch_pdl(gemm_tc_kernel<1, VG_ACT_NONE, 128, false, true>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);
     return check_launch("gemm_tc");
   }
   if (a.ln_gamma) {
     VG_REQUIRE(a.act == VG_ACT_NONE, VG_ERR_UNSUPPORTED, "gemm_tc: fused LayerNorm is built for the activation-free epilogue");
     constexpr int smem_ = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, VG_ACT_NONE, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_);
-      VG_REQUIRE(e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
+    static const cudaError_t attr_e = set_smem_once(gemm_tc_kernel<1, VG_ACT_NONE, 128, true>, smem_);
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_e));
     launch_pdl(gemm_tc_kernel<1, VG_ACT_NONE, 128, true>, dim3(grid), dim3(NTHREADS), smem_, st, ma, mb, mc, mp, mr, mx, p);
     return check_launch("gemm_tc");
   }

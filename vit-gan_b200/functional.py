@@ -755,3 +755,25 @@ class SoftmaxCEFn(Function):
 
 def softmax_ce(logits, targets, rows_per_group=None):
     return SoftmaxCEFn.apply(logits, targets, rows_per_group or logits.shape[0])
+
+
+class BCEFn(Function):
+    """losses[g] = nn.BCELoss()(prob[g*n:(g+1)*n], target[...]) (src/v1/gan.py:16-20, 222-252), one launch forward,
+    one multiply backward."""
+
+    @staticmethod
+    def forward(ctx, prob, target, rows_per_group):
+        losses, dprob = ops.bce(prob.contiguous(), target.contiguous(), rows_per_group)
+        ctx.save_for_backward(dprob)
+        return losses
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dprob,) = ctx.saved_tensors
+        G = g.shape[0]
+        return (dprob.view(G, -1) * g.reshape(G, 1)).view_as(dprob), None, None
+
+
+def bce(prob, target, rows_per_group=None):
+    return BCEFn.apply(prob, target, rows_per_group or prob.numel())

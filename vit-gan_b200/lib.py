@@ -64,6 +64,7 @@ SIGNATURES = {
     "vg_broadcast_rows": [i32, vp, i64, i64, vp, i64, vp],
     "vg_act_backward": [i32, i64, vp, vp, i32, f32, vp, vp],
     "vg_softmax_ce": [vp, vp, i32, i32, i32, vp, vp, vp],
+    "vg_bce": [vp, vp, i32, i32, vp, vp, vp],
     "vg_denorm_u8": [i32, vp, i64, vp, vp],
     "vg_copy_rows": [i32, i64, i32, vp, i64, vp, i64, vp],
     "vg_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp, vp],

@@ -408,6 +408,21 @@ def softmax_ce(logits, targets, rows_per_group):
     return losses, dlog
 
 
+def bce(prob, target, rows_per_group):
+    """-> (losses[G], dprob[rows]) of the fused binary-cross-entropy head (see vg_bce)."""
+    _req(prob, "prob")
+    if prob.dtype != torch.float32 or target.dtype != torch.float32 or not prob.is_contiguous() or not target.is_contiguous():
+        raise TypeError("vitgan_b200.bce: contiguous fp32 probabilities and targets required")
+    if prob.numel() != target.numel():
+        raise ValueError("vitgan_b200.bce: probabilities and targets differ in size")
+    rows = prob.numel()
+    losses = torch.empty(rows // rows_per_group, dtype=torch.float32, device=prob.device)
+    dprob = torch.empty_like(prob)
+    check(lib.vg_bce(prob.data_ptr(), target.data_ptr(), rows, rows_per_group, losses.data_ptr(), dprob.data_ptr(), stream()), "vg_bce")
+    _count()
+    return losses, dprob
+
+
 def denorm_u8(x):
     """uint8(clamp(x * 127.5 + 127.5, 0, 255)) -- utils.convert_to_uint8 of the reference, same shape as x."""
     _req(x, "x")

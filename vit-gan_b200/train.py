@@ -186,6 +186,24 @@ class GradBuckets:
 # --------------------------------------------------------------------------------------------------
 # the step
 # --------------------------------------------------------------------------------------------------
+def _push(name):
+    """NVTX range around one phase of the step (the reference has no tracing; nsys / ncu --nvtx-include pick these up).
+    A push/pop costs ~0.1 us without a profiler attached and is legal during graph capture."""
+    torch.cuda.nvtx.range_push(name)
+
+
+def _pop():
+    torch.cuda.nvtx.range_pop()
+
+
+def _bce(prob, target, reduction="mean"):
+    """nn.BCELoss(reduction='mean') (src/v1/gan.py:16-20): on the GPU the one-launch fused head (vg_bce: loss + dprob),
+    on CPU tensors (host-logic tests only) torch's."""
+    if prob.is_cuda and reduction == "mean":
+        return Fn.bce(prob, target)[0]
+    return F.binary_cross_entropy(prob, target, reduction=reduction)
+
+
 def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_buckets=None, g_buckets=None,
              skip_unused_d_grads=False, merge_d_passes=False):
     """One adversarial iteration: D(real), G(noise), D(fake.detach()) -> D step; D(fake) -> G step.
@@ -207,8 +225,9 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
     else:
         ones = torch.ones(b, 1, device=dev)
         zeros = torch.zeros(b, 1, device=dev)
-        crit = F.binary_cross_entropy
+        crit = _bce
     fused_ce = loss_kind == "ce" and merge_d_passes      # the optimised step also uses the one-launch CE head (vg_softmax_ce)
+    _push("vg.d_update")
     disc_opt.zero_grad(set_to_none=False) if isinstance(disc_opt, FusedAdam) else disc_opt.zero_grad(set_to_none=True)
     if merge_d_passes:
         fake = gen(noise)
@@ -217,6 +236,10 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
         out = disc(torch.cat([real, fake.detach().to(real.dtype)], 0)).float()
         if fused_ce and out.is_cuda:
             per = Fn.softmax_ce(out, torch.cat([ones, zeros], 0), b)          # [loss_real, loss_fake], one launch
+            loss_real, loss_fake = per[0], per[1]
+            per.sum().backward()
+        elif loss_kind == "bce" and out.is_cuda:
+            per = Fn.bce(out, torch.cat([ones, zeros], 0), b)                 # fused BCELoss head (vg_bce), one launch
             loss_real, loss_fake = per[0], per[1]
             per.sum().backward()
         else:
@@ -234,7 +257,11 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
     if d_buckets is not None:
         d_buckets.finish()
     Fn.join_param_grad_stream()
+    _push("vg.d_optimizer")
     disc_opt.step()
+    _pop()
+    _pop()
+    _push("vg.g_update")
     gen_opt.zero_grad(set_to_none=False) if isinstance(gen_opt, FusedAdam) else gen_opt.zero_grad(set_to_none=True)
     if g_buckets is not None:
         g_buckets.arm()
@@ -248,7 +275,10 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
     if g_buckets is not None:
         g_buckets.finish()
     Fn.join_param_grad_stream()
+    _push("vg.g_optimizer")
     gen_opt.step()
+    _pop()
+    _pop()
     return loss_real.detach(), loss_fake.detach(), loss_g.detach()
 
 
@@ -269,9 +299,10 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
     if loss_kind == "ce":
         ones, zeros, crit = torch.ones(mb, dtype=torch.long, device=dev), torch.zeros(mb, dtype=torch.long, device=dev), F.cross_entropy
     else:
-        ones, zeros, crit = torch.ones(mb, 1, device=dev), torch.zeros(mb, 1, device=dev), F.binary_cross_entropy
+        ones, zeros, crit = torch.ones(mb, 1, device=dev), torch.zeros(mb, 1, device=dev), _bce
     inv = 1.0 / n_micro
     zg = lambda opt: opt.zero_grad(set_to_none=False) if isinstance(opt, FusedAdam) else opt.zero_grad(set_to_none=True)
+    _push("vg.d_update")
     zg(disc_opt)
     l_real = l_fake = l_g = 0.0
     for i in range(n_micro):
@@ -291,7 +322,11 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
     if d_buckets is not None:
         d_buckets.finish()
     Fn.join_param_grad_stream()
+    _push("vg.d_optimizer")
     disc_opt.step()
+    _pop()
+    _pop()
+    _push("vg.g_update")
     zg(gen_opt)
     for i in range(n_micro):
         z = noise[i * mb:(i + 1) * mb]
@@ -308,7 +343,10 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
     if g_buckets is not None:
         g_buckets.finish()
     Fn.join_param_grad_stream()
+    _push("vg.g_optimizer")
     gen_opt.step()
+    _pop()
+    _pop()
     return l_real, l_fake, l_g
 
 
