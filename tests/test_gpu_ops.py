@@ -535,6 +535,41 @@ def test_gemm_production_rows_all_epilogues(vb, M):
     assert rel(db, db0 + qkv.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("M", [257 * 256, 130 * 128 + 37])
+def test_gemm_cta_pair_wide_tiles(vb, M):
+    """Compute-bound shapes (E = 768, the scaled config of BASELINE.json configs[3]) run on the CTA-pair kernel (256 x 256 tile per
+    2-CTA cluster, tcgen05.mma.cta_group::2): every Linear product of the encoder block at production rows (65 792 = 257 pair
+    tiles) and at a row count that leaves the last pair half empty plus a ragged 37-row tail -- forward + bias, forward + GELU +
+    pre-activation, forward + bias + residual (side tile prefetched one group ahead), dgrad (B MN-major), dgrad * GELU'(u)
+    (aux chain), split-K wgrad (A and B MN-major, TMA reduce-add) -- against the fp32 formula on the same bf16 operands."""
+    L = vb.lib
+    g = gen(M % 1000)
+    E, m, dev = 768, 2, "cuda"
+    x = (torch.randn(M, E, generator=g) * 0.7).bfloat16().to(dev)
+    wqkv = (torch.randn(3 * E, E, generator=g) * 0.05).bfloat16().to(dev)
+    w1 = (torch.randn(m * E, E, generator=g) * 0.05).bfloat16().to(dev)
+    w2 = (torch.randn(E, m * E, generator=g) * 0.05).bfloat16().to(dev)
+    bq, b1, b2 = (torch.randn(n, generator=g).to(dev) for n in (3 * E, m * E, E))
+    xf = x.float()
+    qkv = vb.ops.gemm(x, wqkv, bias=bq, path=L.GEMM_TCGEN05)
+    assert rel(qkv, xf @ wqkv.float().t() + bq) < BF16_TOL
+    h, u = vb.ops.gemm(x, w1, bias=b1, act=L.ACT_GELU, want_pre=True, path=L.GEMM_TCGEN05)
+    u_ref = xf @ w1.float().t() + b1
+    assert rel(u, u_ref) < BF16_TOL and rel(h, F.gelu(u_ref)) < BF16_TOL
+    y = vb.ops.gemm(h, w2, bias=b2, residual=x, path=L.GEMM_TCGEN05)
+    assert rel(y, h.float() @ w2.float().t() + b2 + xf) < BF16_TOL
+    dqkv = (torch.randn(M, 3 * E, generator=g) * 0.5).bfloat16().to(dev)
+    dx = vb.ops.gemm(dqkv, wqkv, trans_b=False, path=L.GEMM_TCGEN05)
+    assert rel(dx, dqkv.float() @ wqkv.float()) < BF16_TOL
+    dy = torch.randn(M, E, generator=g).bfloat16().to(dev)
+    du = vb.ops.gemm(dy, w2, trans_b=False, act=L.ACT_MUL_DGELU, aux=u, path=L.GEMM_TCGEN05)
+    assert rel(du, act_ref(5, dy.float() @ w2.float(), u.float(), 0.0)) < BF16_TOL
+    dw0 = torch.randn(3 * E, E, generator=g).to(dev)
+    dw = dw0.clone()
+    vb.ops.gemm(dqkv, x, trans_a=True, trans_b=False, accumulate=True, out=dw, path=L.GEMM_TCGEN05)
+    assert rel(dw, dw0 + dqkv.float().t() @ xf) < 1e-4
+
+
 MT_SHAPES = [(2, 4, 257, 192, 0), (40, 4, 257, 192, 0), (1, 1, 128, 192, 0), (1, 2, 129, 192, 0), (3, 4, 64, 96, 0), (2, 4, 65, 112, 0),
              (2, 4, 65, 112, 1), (300, 4, 65, 112, 1), (2, 4, 64, 96, 1), (1, 2, 200, 112, 1), (2, 2, 272, 96, 0), (2, 2, 17, 96, 0),
              (3, 2, 1, 112, 1)]

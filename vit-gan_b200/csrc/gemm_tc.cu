@@ -36,6 +36,7 @@ constexpr int ONES_BYTES = 2048;        // [16 n x 64 k] bf16 tile of 1.0: B ope
 constexpr int LN_BYTES = EPI_WARPS * 128 * 4 + 2 * EPI_WARPS * 32 * 4;   // fused LayerNorm: per warp gamma|beta of its 64 columns + 2 exchange slots
 constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int TMEM_COLS = NACC * BN;   // 256: power of two >= 32
+constexpr int PAIR_STAGES = 5;          // CTA-pair kernel: operand ring depth (32 KB per stage per CTA)
 constexpr int RS_COL = TMEM_COLS, RS_N = 16;   // row-sum accumulators (a_rowsum): 16 columns per stage behind the tile accumulators
 
 struct Params {
@@ -141,7 +142,8 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 // bufC holds the residual tile on entry (if any) and the output on exit; bufX holds aux on entry or c_pre on exit.
 template <bool F32, int ACT, bool KEEP = false>
 __device__ __forceinline__ void staged_chunk(const Params& p, uint32_t (&r)[32], int lane, int cc, int n0,
-                                             uint32_t bufC, uint32_t bufX, const float* __restrict__ bias_s) {
+                                             uint32_t bufC, uint32_t bufX, const float* __restrict__ bias_s, bool res_in_x = false) {
+  // res_in_x (bf16, side-tile chain): the residual tile was loaded into bufX (which is never stored from) instead of bufC
   // KEEP (bf16 only): the final, bf16-ROUNDED output values are written back into r[] as floats (fused LayerNorm input:
   // the statistics are then taken over exactly the values a separate LayerNorm kernel would read from memory)
   const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
@@ -197,7 +199,7 @@ __device__ __forceinline__ void staged_chunk(const Params& p, uint32_t (&r)[32],
       }
       if (has_res) {
         uint32_t x0, x1, x2, x3;
-        lds128(bufC + off, x0, x1, x2, x3);
+        lds128((res_in_x ? bufX : bufC) + off, x0, x1, x2, x3);
         v[0] += bf16_lo(x0); v[1] += bf16_hi(x0); v[2] += bf16_lo(x1); v[3] += bf16_hi(x1);
         v[4] += bf16_lo(x2); v[5] += bf16_hi(x2); v[6] += bf16_lo(x3); v[7] += bf16_hi(x3);
       }
@@ -262,7 +264,13 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
                                             uint32_t tfull, uint32_t tfull_phase, uint32_t tempty, int m0, int n0, uint32_t bufC,
                                             uint32_t bufX, uint32_t wbar, uint32_t& wphase, float* bias_s, int lane,
                                             uint32_t rs_taddr = 0u, bool release = true, int ew = 0, LnScratch ln = LnScratch{nullptr, nullptr},
-                                            bool alt = false) {
+                                            bool alt = false, bool* aux_ready = nullptr, bool has_next = false, int next_m0 = 0, int next_n0 = 0,
+                                            uint32_t tempty_cluster = 0u) {
+  // tempty_cluster != 0 (CTA-pair kernel): the accumulator-drained arrival goes to the pair leader's barrier (shared::cluster address)
+  // aux_ready / has_next / next_*: aux-only epilogues (dgrad + activation derivative) prefetch the NEXT group's aux tile as soon
+  // as this group's math has consumed bufX -- the tile is never stored from, so it need not wait for this group's bulk store;
+  // otherwise the ~1 us TMA load of every group sat exposed between the accumulator being ready and the math (fc2 dgrad+GELU'
+  // at the C4 shape: 243 us vs 178 us for the plain GEMM of the same FLOPs)
   // alt (bf16 epilogues without residual / aux / c_pre / LayerNorm only): consecutive calls alternate between the warp's two
   // 4 KB staging tiles, so this tile is staged while the previous tile's bulk store is still reading the other one
   // release == false: more 64-column groups of the same accumulator follow (256-wide tiles); the last group frees TMEM
@@ -272,12 +280,17 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   // staging tiles are free once the previous tile's bulk stores have READ them
   const bool dbl = MODE == 1 && !LN && !has_res && !has_aux && !has_pre;
   if (dbl && alt) { const uint32_t t = bufC; bufC = bufX; bufX = t; }
+  float bv0 = 0.f, bv1 = 0.f;                 // this group's bias values: the loads are in flight while lane 0 waits below
+  if (p.bias) {
+    const int c0 = n0 + lane, c1 = n0 + 32 + lane;
+    bv0 = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
+    bv1 = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
+  }
   if (lane == 0) { if (dbl) tma_wait_read1(); else tma_wait_read(); }
   __syncwarp();
   if (p.bias) {                               // stage this warp's 64 bias values (previous tile's readers are past them)
-    const int c0 = n0 + lane, c1 = n0 + 32 + lane;
-    bias_s[lane] = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
-    bias_s[32 + lane] = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
+    bias_s[lane] = bv0;
+    bias_s[32 + lane] = bv1;
     __syncwarp();
   }
   constexpr bool do_ln = LN && MODE == 1;     // compile-time: the LayerNorm code exists only in the one instantiation that needs it
@@ -286,7 +299,15 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
     ln.gb[64 + lane] = __ldg(p.ln_beta + n0 + lane); ln.gb[96 + lane] = __ldg(p.ln_beta + n0 + 32 + lane);
     __syncwarp();
   }
-  if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
+  // side-tile chain: exactly one side input (aux or residual), no second output -> it lives in bufX and is prefetched one group ahead
+  const bool aux_chain = aux_ready != nullptr && (has_aux != has_res) && !has_pre && !f32 && !(LN && MODE == 1) && !REMAP;
+  const bool aux_here = !(aux_chain && *aux_ready);   // false: the previous group already issued this group's side-tile load
+  if (aux_chain) {
+    if (aux_here && lane == 0) {
+      mbar_expect_tx(wbar, 4096u);
+      tma_load_2d(bufX, has_aux ? tmap_aux : tmap_res, wbar, n0, m0);
+    }
+  } else if ((has_res || has_aux) && lane == 0) {    // prefetch residual / aux tiles while the MMAs run
     mbar_expect_tx(wbar, (has_res ? (f32 ? 8192u : 4096u) : 0u) + (has_aux ? 4096u : 0u));
     if (has_res) {
       // REMAP: the residual is a [mod (+off), N] table broadcast over the row groups (positional embedding)
@@ -305,7 +326,9 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   tmem_ld_wait();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0 && release) mbar_arrive(tempty);   // accumulator is in registers: release TMEM to the MMA warp
+  if (lane == 0 && release) {                      // accumulator is in registers: release TMEM to the MMA warp
+    if (tempty_cluster != 0u) mbar_arrive_cluster(tempty_cluster); else mbar_arrive(tempty);
+  }
   if (MODE == 2 && rs_taddr != 0u) bias_s[lane] = __uint_as_float(rs);   // bias staging is idle in accumulate mode
   if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
   if (!(p.dbg & 1)) {
@@ -314,11 +337,18 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
       staged_chunk<f32, ACT, do_ln>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
       ln_epilogue(p, r0, r1, lane, ew, m0 + lane, bufX, ln);
     } else {
-      staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
-      staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
+      staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s, aux_chain);
+      staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s, aux_chain);
     }
     fence_async_smem();                       // generic-proxy smem writes -> visible to the async (TMA) proxy
     __syncwarp();
+    if (aux_chain) {                          // bufX has been consumed by every lane: fetch the next group's aux tile now
+      *aux_ready = has_next;
+      if (has_next && lane == 0) {
+        mbar_expect_tx(wbar, 4096u);
+        tma_load_2d(bufX, has_aux ? tmap_aux : tmap_res, wbar, next_n0, next_m0);
+      }
+    }
     if (lane == 0 && m0 < p.M && n0 < p.N) {
       if (p.accumulate) {
         tma_reduce_add_2d(tmap_c, bufC, n0, m0);
@@ -497,16 +527,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float* ln_f = reinterpret_cast<float*>(smem_dyn + (ln_base - smem_u32(smem_dyn)));
       const LnScratch ln = LN ? LnScratch{ln_f + ew * 128, ln_f + EPI_WARPS * 128} : LnScratch{nullptr, nullptr};
       int n_staged = 0;
+      bool aux_ready = false;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % p.n_tiles, m_blk = (w / p.n_tiles) % p.m_tiles;
         const int m0 = m_blk * BM + quad * 32;
+        const int wn = w + (int)gridDim.x;             // this CTA's next tile (aux prefetch chain)
+        const int nn_blk = wn % p.n_tiles, nm0 = ((wn / p.n_tiles) % p.m_tiles) * BM + quad * 32;
         const uint32_t rs_taddr = (do_rs && n_blk == 0 && half == 0 && m0 < p.M) ? tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(RS_COL + acc * RS_N) : 0u;
 #pragma unroll
         for (int g = 0; g < BN / 128; ++g) {           // this warp's 64-column groups of the tile (one at BN = 128, two at 256)
           const int col = half * (BN / 2) + g * 64;
           staged_tile<MODE, ACT, LN, REMAP>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
                                      tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, rs_taddr,
-                                     g == BN / 128 - 1, ew, ln, (n_staged++ & 1) != 0);
+                                     g == BN / 128 - 1, ew, ln, (n_staged++ & 1) != 0, &aux_ready,
+                                     g + 1 < BN / 128 || wn < total_work, g + 1 < BN / 128 ? m0 : nm0,
+                                     g + 1 < BN / 128 ? n_blk * BN + col + 64 : nn_blk * BN + half * (BN / 2));
         }
         if (ew == 0 && lane == 0 && w == (int)blockIdx.x) trace_mark(p.trace, TR_STORE0);
         if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
@@ -549,6 +584,170 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+
+// ================================================================================================ CTA-pair variant
+// 256 x 256 output tile per 2-CTA cluster (tcgen05.mma.cta_group::2, M = 256): CTA rank r of the pair owns rows [128 r, 128 r + 128)
+// of the tile (its own TMEM lanes) and stages, per 64-deep k-block, its own 128 x 64 slab of A plus rows [128 r, 128 r + 128) of the
+// B tile -- 32 KB per SM per 512 clk of tensor pipe instead of the 48 KB of the 1-CTA 128 x 256 tile, whose tensor pipe sat at
+// 62 % because the operand fill (96 B/clk/SM) exceeds what L2 delivers to 148 SMs at once (profiles/r02b_ncu_full_c4_gemm.txt).
+// Roles per CTA as in gemm_tc_kernel (warp 0 TMA, warp 1 MMA, 8 epilogue warps); only the leader's warp 1 issues MMAs.
+//   full[s]   leader only: its producer's arrive.expect_tx of 2 x 32 KB, completed by both CTAs' TMA bytes
+//   empty[s]  per CTA, signalled in both CTAs by one multicast tcgen05.commit
+//   tfull[a]  per CTA, multicast commit;   tempty[a]  leader only, 2 x EPI_WARPS arrivals (the peer's arrive remotely)
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_pre,
+                const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
+  // Measured at 8192^3 (profiles/bench_gemm_big.py): MMAs alone (operand loads disabled) 1718 TFLOP/s, with loads 1232 TFLOP/s at
+  // 4 and at 5 stages alike -- the ring is deep enough; what remains is the chip's power cap (SM clock ~1.4-1.65 GHz under load).
+  // The full barrier takes ONE arrival (the leader's arrive.expect_tx for both CTAs' bytes): a second, remote arrive.expect_tx
+  // from the peer's producer per stage cost 1.7x (0.86 us per stage instead of 0.5 us).
+  constexpr int BN = 256, NST = PAIR_STAGES;             // pair tile width; stages of A (16 KB) + B half (16 KB)
+  constexpr int BH_BYTES = 128 * BK * 2, STAGE = A_BYTES + BH_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t smem_base = smem_u32(smem_dyn);         // no static shared memory in this kernel: the dynamic window starts 1024-aligned
+  if (threadIdx.x == 0 && (smem_base & 1023u) != 0u) { printf("vg gemm_tc2: dynamic shared memory not 1024-byte aligned\n"); __trap(); }
+  const uint32_t stg_base = smem_base + NST * STAGE;
+  const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;
+  const uint32_t bar_base = bias_base + BIAS_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * NST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NST + NACC + a); };
+  auto warp_bar = [&](int w) { return bar_base + 8u * (2 * NST + 2 * NACC + w); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NST + 2 * NACC + EPI_WARPS);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = leader
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    if (p.c_pre != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_pre) : "memory");
+    if (p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_res) : "memory");
+    if (p.aux != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_aux) : "memory");
+    for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(warp_bar(w), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // the same warp of BOTH CTAs: pair-wide TMEM allocation (all 512 columns: two 256-column accumulator stages)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit / pair TMA load
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
+
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  const int total_work = m_pairs * p.n_tiles * p.splits;
+  const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+  const uint32_t a_lbo = p.trans_a ? p.mn_lbo : 16u, a_sbo = p.trans_a ? p.mn_sbo : 1024u, a_kstep = p.trans_a ? p.mn_kstep : 32u;
+  const uint32_t b_lbo = p.trans_b ? 16u : p.mn_lbo, b_sbo = p.trans_b ? 1024u : p.mn_sbo, b_kstep = p.trans_b ? 32u : p.mn_kstep;
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = pair; w < total_work; w += npairs) {
+        const int n_blk = w % p.n_tiles, m_pair = (w / p.n_tiles) % m_pairs, split = w / (p.n_tiles * m_pairs);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int mrow = m_pair * 2 * BM + (int)rank * BM;          // this CTA's 128 rows of A (and of the output tile)
+        const int nrow = n_blk * BN + (int)rank * 128;              // this CTA's 128 rows of the B tile
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * STAGE, sb = sa + A_BYTES;
+          const uint32_t fb = mapa_u32(full_bar(stage), 0u);        // the leader's barrier counts both CTAs' bytes
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE);   // one local arrival; the peer's bytes may land before or after it
+          if (!p.trans_a) {
+            tma_load_2d_pair(sa, &tmap_a, fb, kb * BK, mrow);                       // box {64 k, 128 m}
+          } else {
+            tma_load_2d_pair(sa, &tmap_a, fb, mrow, kb * BK);                       // box {64 m, 64 k} x2
+            tma_load_2d_pair(sa + 8192, &tmap_a, fb, mrow + 64, kb * BK);
+          }
+          if (p.trans_b) {
+            tma_load_2d_pair(sb, &tmap_b, fb, kb * BK, nrow);                       // box {64 k, 128 n}
+          } else {
+            tma_load_2d_pair(sb, &tmap_b, fb, nrow, kb * BK);                       // box {64 n, 64 k} x2
+            tma_load_2d_pair(sb + 8192, &tmap_b, fb, nrow + 64, kb * BK);
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA only) ==============================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.trans_a ? 1u : 0u) << 15) |
+                             ((p.trans_b ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = pair; w < total_work; w += npairs) {
+        const int split = w / (p.n_tiles * m_pairs);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);                 // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t ad = make_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t bd = make_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            tc_mma_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_pair(empty_bar(stage), 3);               // frees the stage in BOTH CTAs when these MMAs retire
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_pair(tfull_bar(acc), 3);                   // accumulator complete -> both CTAs' epilogues
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ============================== epilogue (both CTAs, own 128 rows x 256 columns) ==============================
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t bufC = stg_base + (uint32_t)ew * STG_BYTES, bufX = bufC + 4096u;
+    const uint32_t wbar = warp_bar(ew);
+    uint32_t wphase = 0;
+    float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_u32(smem_dyn))) + ew * 64;
+    int n_staged = 0;
+    bool aux_ready = false;
+    for (int w = pair; w < total_work; w += npairs) {
+      const int n_blk = w % p.n_tiles, m_pair = (w / p.n_tiles) % m_pairs;
+      const int m0 = m_pair * 2 * BM + (int)rank * BM + quad * 32;
+      const int wn = w + npairs;
+      const int nn_blk = wn % p.n_tiles, nm0 = ((wn / p.n_tiles) % m_pairs) * 2 * BM + (int)rank * BM + quad * 32;
+      const uint32_t te = mapa_u32(tempty_bar(acc), 0u);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int col = half * 128 + g * 64;
+        staged_tile<MODE, ACT, false, false>(p, &tmap_c, &tmap_pre, &tmap_res, &tmap_aux, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col),
+                                             tfull_bar(acc), acc_phase, tempty_bar(acc), m0, n_blk * BN + col, bufC, bufX, wbar, wphase, bias_s, lane, 0u,
+                                             g == 1, ew, LnScratch{nullptr, nullptr}, (n_staged++ & 1) != 0, &aux_ready,
+                                             g == 0 || wn < total_work, g == 0 ? m0 : nm0, g == 0 ? n_blk * BN + col + 64 : nn_blk * BN + half * 128, te);
+      }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_wait_read();
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();            // neither CTA may free TMEM (or exit, taking its barriers and operand tiles away) while its peer still runs
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -626,15 +825,17 @@ bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
 }
 
 // Bring-up knobs, read ONCE per process (thread-safe static initialisation; the launch path itself never calls getenv):
-//   VG_TC_DBG   bit 0 = epilogue skips global memory, bit 1 = force the direct (per-thread) epilogue
+//   VG_TC_DBG   bit 0 = epilogue skips global memory, bit 1 = force the direct (per-thread) epilogue, bit 4 = print the pair-cluster capacity
 //   VG_TC_BN    128 | 256 overrides the tile-width heuristic
+//   VG_TC_PAIR  0 keeps the wide tiles on the 1-CTA kernel (A/B comparison with the CTA-pair kernel)
 //   VG_TC_MN_DESC "lbo,sbo,kstep" (bytes) overrides the MN-major descriptor strides
 struct TcEnv {
-  int dbg = 0, bn = 0;
+  int dbg = 0, bn = 0, pair = 1;
   unsigned mn_lbo = 8192u, mn_sbo = 1024u, mn_kstep = 2048u;
   TcEnv() {
     if (const char* e = getenv("VG_TC_DBG")) dbg = atoi(e);
     if (const char* e = getenv("VG_TC_BN")) bn = atoi(e);
+    if (const char* e = getenv("VG_TC_PAIR")) pair = atoi(e);
     if (const char* e = getenv("VG_TC_MN_DESC")) {
       unsigned l = 0, sb = 0, ks = 0;
       if (sscanf(e, "%u,%u,%u", &l, &sb, &ks) == 3) { mn_lbo = l; mn_sbo = sb; mn_kstep = ks; }
@@ -646,6 +847,48 @@ const TcEnv& tc_env() { static const TcEnv e; return e; }
 // one-time, thread-safe opt-in to the kernel's dynamic shared memory size (C++11 static initialisation)
 template <typename K>
 cudaError_t set_smem_once(K kernel, int bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
+// 2-CTA cluster launch (+ programmatic dependent launch)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pair(void (*kernel)(KArgs...), int grid, int smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// How many 2-CTA clusters of this kernel the device runs at once.  A pair needs both SMs of one TPC: on parts where yield
+// harvesting leaves single-SM TPCs this is LESS than num_sms / 2, and a persistent grid sized beyond it would run its surplus
+// clusters as a second wave (measured: 1.7x slower).  Queried once per kernel instantiation.
+template <typename K>
+int max_active_pairs(K kernel, int smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_sms()); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return n;
+}
+int pair_slots();
+constexpr int PAIR_SMEM = PAIR_STAGES * (A_BYTES + 128 * BK * 2) + EPI_WARPS * STG_BYTES + BIAS_BYTES + 512;
+
+// every instantiation has the same footprint (one CTA per SM by shared memory), so one query serves them all
+int pair_slots() {
+  static const int n = [] {
+    if (set_smem_once(gemm_tc2_kernel<1, 0>, PAIR_SMEM) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const int m = max_active_pairs(gemm_tc2_kernel<1, 0>, PAIR_SMEM);
+    if (tc_env().dbg & 16) fprintf(stderr, "vitgan_b200: gemm_tc CTA-pair kernel: %d active 2-CTA clusters on %d SMs\n", m, num_sms());
+    return m;
+  }();
+  return n;
+}
 
 int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   const TcEnv& env = tc_env();
@@ -670,7 +913,9 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   if (bn_env == 128) wide = false;
   if (bn_env == 256) wide = stageable && a.N >= 256;
   const int bn = wide ? 256 : BN;
-  rc = a.trans_b ? make_map(&mb, a.B, a.N, a.K, a.ldb, 64, bn) : make_map(&mb, a.B, a.K, a.N, a.ldb, 64, 64);
+  // wide tiles run on CTA pairs (256 x 256 per 2-CTA cluster, each CTA staging half of the B tile) when M spans at least one pair tile
+  const bool pair = wide && env.pair != 0 && a.M >= 2 * BM && pair_slots() >= 1;
+  rc = a.trans_b ? make_map(&mb, a.B, a.N, a.K, a.ldb, 64, pair ? 128 : bn) : make_map(&mb, a.B, a.K, a.N, a.ldb, 64, 64);
   if (rc) return rc;
 
   Params p;
@@ -682,12 +927,13 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   if (a.accumulate) {
     // split-K factor: the smallest s (each split keeps >= 4 k-blocks) whose tiles*s work items fill >= 90 % of the
     // CTA rounds they need, else the best-filling one (e.g. 54 wide tiles: s = 8 -> 432 items = 2.92 rounds of 148)
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int smax = max(1, min(sms, (p.kb_total + 3) / 4));
+    const int tiles = pair ? ((a.M + 2 * BM - 1) / (2 * BM)) * p.n_tiles : p.m_tiles * p.n_tiles;
+    const int slots = pair ? pair_slots() : sms;         // concurrently resident tiles (CTA pairs or CTAs)
+    const int smax = max(1, min(slots, (p.kb_total + 3) / 4));
     int best = 1; double best_eff = 0.0;
     for (int sp = 1; sp <= smax; ++sp) {
-      const int items = tiles * sp, rounds = (items + sms - 1) / sms;
-      const double eff = (double)items / ((double)rounds * sms);
+      const int items = tiles * sp, rounds = (items + slots - 1) / slots;
+      const double eff = (double)items / ((double)rounds * slots);
       if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
       if (eff >= 0.9) { best = sp; break; }
     }
@@ -737,6 +983,22 @@ int gemm_tc_launch(const vg_gemm_args& a, cudaStream_t st) {
   VG_REQUIRE(!(bn == 256 && mode == 0), VG_ERR_LAUNCH, "gemm_tc: internal: 256-wide tile without a staged epilogue");
   VG_REQUIRE(!a.ln_gamma || (mode == 1 && bn == 128), VG_ERR_UNSUPPORTED, "gemm_tc: fused LayerNorm needs the staged bf16 epilogue");
   const bool wide_k = bn == 256;
+  if (pair) {
+    VG_REQUIRE(mode != 0 && !a.ln_gamma && !remap, VG_ERR_LAUNCH, "gemm_tc: internal: CTA-pair tile without a plain staged epilogue");
+    const int units = ((a.M + 2 * BM - 1) / (2 * BM)) * p.n_tiles * p.splits;
+#define VG_TC2_LAUNCH(MODE_, ACT_)                                                                                             \
+  do {                                                                                                                         \
+    static const cudaError_t attr_e = set_smem_once(gemm_tc2_kernel<MODE_, ACT_>, PAIR_SMEM);                                  \
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_e));         \
+    const int grid2 = 2 * min(units, pair_slots());                                                                            \
+    cudaError_t le = launch_pair(gemm_tc2_kernel<MODE_, ACT_>, grid2, PAIR_SMEM, st, ma, mb, mc, mp, mr, mx, p);               \
+    VG_REQUIRE(le == cudaSuccess, VG_ERR_LAUNCH, "gemm_tc: CTA-pair launch: %s", cudaGetErrorString(le));                      \
+  } while (0)
+    if (mode == 2) VG_TC2_LAUNCH(2, 0);
+    else { VG_ACT_SWITCH(a.act, VG_TC2_LAUNCH(1, ACT)) }
+#undef VG_TC2_LAUNCH
+    return check_launch("gemm_tc2");
+  }
 #define VG_TC_LAUNCH(MODE_, ACT_, BN_)                                                                                         \
   do {                                                                                                                         \
     constexpr int smem_ = (BN_ == 256 ? 3 * (A_BYTES + 256 * BK * 2) : NSTAGES * STAGE_BYTES) + EPI_WARPS * STG_BYTES + BIAS_BYTES + ONES_BYTES + LN_BYTES + 1024 + 512; \
