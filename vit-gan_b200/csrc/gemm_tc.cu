@@ -213,6 +213,62 @@ __device__ __forceinline__ void staged_chunk(const Params& p, uint32_t (&r)[32],
   }
 }
 
+// ---- register-first variants of the bf16 staged epilogue (output-only bufC): the math runs while the previous group's bulk
+// store may still be reading the staging tile; the tile is touched only by put_chunk(), after the caller's wait.
+// bias (+ pre-activation copy to bufX) of one 32-column chunk, in place in r[] as floats
+__device__ __forceinline__ void bias_pre_chunk(const Params& p, uint32_t (&r)[32], int lane, int cc, uint32_t bufX, const float* __restrict__ bias_s,
+                                               bool write_pre) {
+  const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
+    if (p.bias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + h * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + h * 8 + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[h * 8 + j] = __float_as_uint(v[j]);
+    }
+    if (write_pre)
+      sts128(bufX + row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+// activation (aux from bufX) / residual (from bufX) of one 32-column chunk whose bias is already added -> 16 packed bf16 pairs
+template <int ACT>
+__device__ __forceinline__ void act_chunk_packed(const Params& p, const uint32_t (&r)[32], uint32_t (&q)[16], int lane, int cc, uint32_t bufX,
+                                                 bool aux_in_x, bool res_in_x) {
+  const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float v[8], a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
+    uint32_t x0 = 0u, x1 = 0u, x2 = 0u, x3 = 0u;
+    if (aux_in_x || res_in_x) lds128(bufX + row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4), x0, x1, x2, x3);
+    if (aux_in_x) {
+      a[0] = bf16_lo(x0); a[1] = bf16_hi(x0); a[2] = bf16_lo(x1); a[3] = bf16_hi(x1);
+      a[4] = bf16_lo(x2); a[5] = bf16_hi(x2); a[6] = bf16_lo(x3); a[7] = bf16_hi(x3);
+    }
+    if (ACT != VG_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_t<ACT, true>(v[j], a[j], p.act_param);
+    }
+    if (res_in_x) {
+      v[0] += bf16_lo(x0); v[1] += bf16_hi(x0); v[2] += bf16_lo(x1); v[3] += bf16_hi(x1);
+      v[4] += bf16_lo(x2); v[5] += bf16_hi(x2); v[6] += bf16_lo(x3); v[7] += bf16_hi(x3);
+    }
+    q[h * 4 + 0] = pack_bf16(v[0], v[1]); q[h * 4 + 1] = pack_bf16(v[2], v[3]); q[h * 4 + 2] = pack_bf16(v[4], v[5]); q[h * 4 + 3] = pack_bf16(v[6], v[7]);
+  }
+}
+__device__ __forceinline__ void put_chunk(const uint32_t (&q)[16], int lane, int cc, uint32_t bufC) {
+  const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+    sts128(bufC + row_off + ((((uint32_t)(cc * 4 + h)) ^ sw) << 4), q[h * 4 + 0], q[h * 4 + 1], q[h * 4 + 2], q[h * 4 + 3]);
+}
+
 // Fused LayerNorm of the 128-wide output row (N == BN == 128): this thread holds 64 of the row's values (r0 | r1, already
 // rounded to bf16), its partner warp (same TMEM lane quadrant, other column half) the other 64.  Two-pass statistics with one
 // smem exchange + 64-thread named barrier per pass; the normalised row goes to bufX (-> TMA store through the c_pre map).
@@ -279,6 +335,16 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr, has_pre = p.c_pre != nullptr;
   // staging tiles are free once the previous tile's bulk stores have READ them
   const bool dbl = MODE == 1 && !LN && !has_res && !has_aux && !has_pre;
+  // register-first flows (bf16, bufC output-only): `pre2` = bias -> pre-activation tile stored as its own bulk group, activation
+  // computed into registers while that store and the previous group's C store drain; `late` = side-tile chain (aux or residual in
+  // bufX, never stored from): the wait for bufC moves from the top of the group to just before the tile is written.
+  // Measured (profiles/bench_gemm_big.py, C4 shapes): the side-tile prefetch took fc2 dgrad x GELU' from 243 to 184 us and
+  // fc2 + residual from 144 to 132 us; moving the store waits off the critical path changed fc1 + GELU (+pre) by < 1 % (167.6 ->
+  // 166.2 us) -- at 128 KB of stores per 128 x 256 tile on top of 384 KB of operand fill that epilogue is bound by the SM's
+  // memory interface, not by the wait.
+  const bool side_chain = aux_ready != nullptr && (has_aux != has_res) && !has_pre && MODE == 1 && !(LN && MODE == 1) && !REMAP;
+  const bool pre2 = MODE == 1 && !LN && !REMAP && has_pre && !has_res && !has_aux && !p.accumulate;
+  const bool late = side_chain && !p.accumulate;
   if (dbl && alt) { const uint32_t t = bufC; bufC = bufX; bufX = t; }
   float bv0 = 0.f, bv1 = 0.f;                 // this group's bias values: the loads are in flight while lane 0 waits below
   if (p.bias) {
@@ -286,7 +352,10 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
     bv0 = c0 < p.N ? __ldg(p.bias + c0) : 0.f;
     bv1 = c1 < p.N ? __ldg(p.bias + c1) : 0.f;
   }
-  if (lane == 0) { if (dbl) tma_wait_read1(); else tma_wait_read(); }
+  if (lane == 0) {
+    if (dbl || pre2) tma_wait_read1();        // pre2: the previous group's pre-activation store (its C store may still be pending)
+    else if (!late) tma_wait_read();
+  }
   __syncwarp();
   if (p.bias) {                               // stage this warp's 64 bias values (previous tile's readers are past them)
     bias_s[lane] = bv0;
@@ -300,7 +369,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
     __syncwarp();
   }
   // side-tile chain: exactly one side input (aux or residual), no second output -> it lives in bufX and is prefetched one group ahead
-  const bool aux_chain = aux_ready != nullptr && (has_aux != has_res) && !has_pre && !f32 && !(LN && MODE == 1) && !REMAP;
+  const bool aux_chain = side_chain;
   const bool aux_here = !(aux_chain && *aux_ready);   // false: the previous group already issued this group's side-tile load
   if (aux_chain) {
     if (aux_here && lane == 0) {
@@ -331,7 +400,36 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   }
   if (MODE == 2 && rs_taddr != 0u) bias_s[lane] = __uint_as_float(rs);   // bias staging is idle in accumulate mode
   if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
-  if (!(p.dbg & 1)) {
+  if (MODE == 1 && !do_ln && !REMAP && (pre2 || late) && !(p.dbg & 1)) {
+    bias_pre_chunk(p, r0, lane, 0, bufX, bias_s, pre2);
+    bias_pre_chunk(p, r1, lane, 1, bufX, bias_s, pre2);
+    const bool live = m0 < p.M && n0 < p.N;
+    if (pre2) {                                // the pre-activation tile leaves as its own bulk group
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && live) { tma_store_2d(tmap_pre, bufX, n0, m0); tma_commit(); }
+    }
+    uint32_t q0[16], q1[16];
+    act_chunk_packed<ACT>(p, r0, q0, lane, 0, bufX, late && has_aux, late && has_res);
+    act_chunk_packed<ACT>(p, r1, q1, lane, 1, bufX, late && has_aux, late && has_res);
+    if (late) {                                // bufX consumed by every lane: fetch the next group's side tile now
+      fence_async_smem();
+      __syncwarp();
+      *aux_ready = has_next;
+      if (has_next && lane == 0) {
+        mbar_expect_tx(wbar, 4096u);
+        tma_load_2d(bufX, has_aux ? tmap_aux : tmap_res, wbar, next_n0, next_m0);
+      }
+    }
+    // bufC: the previous group's C store must have read it (pre2: all but the pre store just committed; late: everything)
+    if (lane == 0) { if (pre2 && live) tma_wait_read1(); else tma_wait_read(); }
+    __syncwarp();
+    put_chunk(q0, lane, 0, bufC);
+    put_chunk(q1, lane, 1, bufC);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0 && live) { tma_store_2d(tmap_c, bufC, n0, m0); tma_commit(); }
+  } else if (!(p.dbg & 1)) {
     if (do_ln) {
       staged_chunk<f32, ACT, do_ln>(p, r0, lane, 0, n0, bufC, bufX, bias_s);
       staged_chunk<f32, ACT, do_ln>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
