@@ -27,9 +27,8 @@ int check_launch(const char* what) {
 }
 
 bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("VG_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on != 0;
+  static const bool on = [] { const char* e = getenv("VG_PDL"); return !(e && e[0] == '0'); }();   // read once, thread-safe
+  return on;
 }
 
 int num_sms() {

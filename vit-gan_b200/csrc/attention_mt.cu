@@ -1366,25 +1366,24 @@ MtGeo make_geo(int B, int H, int S, int64_t ld, int64_t ldo, float scale, const 
   g.scale = scale; g.lse = lse; g.delta = delta;
   g.q = static_cast<const bf16*>(q); g.k = static_cast<const bf16*>(k); g.o = static_cast<const bf16*>(o);
   g.dq = g.dk = g.dv = nullptr; g.ldd = 0;
-  { const char* e = getenv("VG_ATTN_SKEW"); g.skew_ns = e ? atoi(e) : 0; e = getenv("VG_ATTN_NOPF"); g.no_prefetch = e ? atoi(e) : 0; }
+  static const int env_skew = [] { const char* e = getenv("VG_ATTN_SKEW"); return e ? atoi(e) : 0; }();      // experiment knobs, read once
+  static const int env_nopf = [] { const char* e = getenv("VG_ATTN_NOPF"); return e ? atoi(e) : 0; }();
+  g.skew_ns = env_skew; g.no_prefetch = env_nopf;
   return g;
 }
 
 template <typename K>
-int set_smem_once(K kern, int bytes, bool* done) {
-  if (!*done) {
-    VG_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess, VG_ERR_LAUNCH,
-               "attention_mt: cudaFuncSetAttribute(%d B) failed", bytes);
-    *done = true;
-  }
+int set_smem_once(K kern, int bytes) {      // callers keep the result in a function-local static: one-time, thread-safe
+  VG_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess, VG_ERR_LAUNCH,
+             "attention_mt: cudaFuncSetAttribute(%d B) failed", bytes);
   return VG_OK;
 }
 
 template <int D, int MODE>
 int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mk64, const CUtensorMap& mk16, const CUtensorMap& mv, const OutMaps& mo, const MtGeo& g,
                cudaStream_t st) {
-  static bool set = false;
-  int rc = set_smem_once(attn_fwd_mt_kernel<D, MODE>, FwdCfg<D>::SMEM, &set);
+  static const int attr_rc = set_smem_once(attn_fwd_mt_kernel<D, MODE>, FwdCfg<D>::SMEM);
+  int rc = attr_rc;
   if (rc) return rc;
   const int grid = min(g.B * g.H, num_sms());
   launch_pdl(attn_fwd_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS), (size_t)FwdCfg<D>::SMEM, st, mq, mk64, mk16, mv, mo, g);
@@ -1394,10 +1393,9 @@ template <int D, int MODE>
 int launch_bwd(const CUtensorMap& mq128, const CUtensorMap& mdo128, const CUtensorMap& mk64, const CUtensorMap& mv64, const OutMaps& mdq,
                const CUtensorMap& mk128, const CUtensorMap& mv128, const CUtensorMap& mq64, const CUtensorMap& mdo64, const OutMaps& mdk,
                const OutMaps& mdv, const MtGeo& g, cudaStream_t st) {
-  static bool set1 = false, set2 = false;
-  int rc = set_smem_once(attn_bwd_dq_mt_kernel<D, MODE>, DqCfg<D>::SMEM, &set1);
-  if (rc) return rc;
-  rc = set_smem_once(attn_bwd_dkv_mt_kernel<D, MODE>, DkvCfg<D>::smem(MODE), &set2);
+  static const int attr_rc1 = set_smem_once(attn_bwd_dq_mt_kernel<D, MODE>, DqCfg<D>::SMEM);
+  static const int attr_rc2 = set_smem_once(attn_bwd_dkv_mt_kernel<D, MODE>, DkvCfg<D>::smem(MODE));
+  int rc = attr_rc1 ? attr_rc1 : attr_rc2;
   if (rc) return rc;
   const int grid = min(g.B * g.H, num_sms());
   launch_pdl(attn_bwd_dq_mt_kernel<D, MODE>, dim3(grid), dim3(NTHREADS_BWD), (size_t)DqCfg<D>::SMEM, st, mq64, mdo64, mk64, mv64, mdq, g);

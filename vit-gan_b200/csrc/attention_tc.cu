@@ -1001,21 +1001,19 @@ int hp_bwd_smem(int D, int NK) {
   return 1024 + max(bar_end, p_end + (128 - NK) * 128);
 }
 bool hp_disabled() {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("VG_ATTN_HP"); off = (e && !strcmp(e, "0")) ? 1 : 0; }
-  return off == 1;
+  static const bool off = [] { const char* e = getenv("VG_ATTN_HP"); return e && !strcmp(e, "0"); }();   // read once, thread-safe
+  return off;
 }
 int hp_ctas_per_sm() {
-  static int n = 0;
-  if (n == 0) { const char* e = getenv("VG_ATTN_HP_CTAS"); n = e ? atoi(e) : 2; if (n < 1 || n > 4) n = 2; }
+  static const int n = [] { const char* e = getenv("VG_ATTN_HP_CTAS"); const int v = e ? atoi(e) : 2; return (v < 1 || v > 4) ? 2 : v; }();
   return n;
 }
 
 template <int D, int NKG>
 int launch_fwd_hp(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo, const Geo& g, cudaStream_t st) {
   const int smem = hp_fwd_smem(D, NKG * 16);
-  static bool set = false;
-  if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_hp_kernel<D, NKG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+  static const cudaError_t attr_e = cudaFuncSetAttribute(attn_fwd_hp_kernel<D, NKG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // one-time, thread-safe
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr");
   const int total = g.B * g.groups, grid = min(total, hp_ctas_per_sm() * num_sms());
   launch_pdl(attn_fwd_hp_kernel<D, NKG>, dim3(grid), dim3(128 * (64 / D)), (size_t)smem, st, mq, mk, mv, mo, g);
   return check_launch("attention_fwd_hp");
@@ -1024,8 +1022,8 @@ template <int D, int NKG>
 int launch_bwd_hp(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mdo, const CUtensorMap& mdq,
                   const CUtensorMap& mdk, const CUtensorMap& mdv, const Geo& g, cudaStream_t st) {
   const int smem = hp_bwd_smem(D, NKG * 16);
-  static bool set = false;
-  if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_hp_kernel<D, NKG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+  static const cudaError_t attr_e = cudaFuncSetAttribute(attn_bwd_hp_kernel<D, NKG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // one-time, thread-safe
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr");
   const int total = g.B * g.groups, grid = min(total, hp_ctas_per_sm() * num_sms());
   launch_pdl(attn_bwd_hp_kernel<D, NKG>, dim3(grid), dim3(128 * (64 / D)), (size_t)smem, st, mq, mk, mv, mdo, mdq, mdk, mdv, g);
   return check_launch("attention_bwd_hp");
@@ -1044,9 +1042,8 @@ int launch_bwd_hp(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMa
 
 bool attention_tc_supported(int dtype, int mode, int B, int H, int S, int d, const void* q, const void* k, const void* v,
                             int64_t ld_qkv, const void* o, int64_t ld_o) {
-  static int sm100 = -1, forced_off = -1;
-  if (sm100 < 0) sm100 = vg_device_is_sm100();
-  if (forced_off < 0) { const char* e = getenv("VG_ATTN_PATH"); forced_off = (e && !strcmp(e, "simt")) ? 1 : 0; }
+  static const int sm100 = vg_device_is_sm100();                                                               // one-time, thread-safe
+  static const bool forced_off = [] { const char* e = getenv("VG_ATTN_PATH"); return e && !strcmp(e, "simt"); }();
   if (!sm100 || forced_off) return false;
   if (dtype != VG_BF16 || mode != VG_ATTN_DOT) return false;
   if (!(d == 32 || d == 64) || S < 1 || S > 128) return false;
@@ -1076,12 +1073,12 @@ int attention_fwd_tc(int B, int H, int S, int d, const void* q, const void* k, c
   Geo g; g.B = B; g.H = H; g.S = S; g.NK = NK; g.groups = cols / 128; g.scale = scale; g.lse = lse;
   const int total = B * g.groups, grid = min(total, num_sms());
   if (d == 32) {
-    static bool set = false;
-    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    static const cudaError_t attr_e = cudaFuncSetAttribute(attn_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);   // one-time, thread-safe
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr");
     launch_pdl(attn_fwd_tc_kernel<32>, dim3(grid), dim3(NTHREADS), FWD_SMEM, st, mq, mk, mv, mo, g);
   } else {
-    static bool set = false;
-    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    static const cudaError_t attr_e = cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);   // one-time, thread-safe
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr");
     launch_pdl(attn_fwd_tc_kernel<64>, dim3(grid), dim3(NTHREADS), FWD_SMEM, st, mq, mk, mv, mo, g);
   }
   return check_launch("attention_fwd_tc");
@@ -1114,12 +1111,12 @@ int attention_bwd_tc(int B, int H, int S, int d, const void* q, const void* k, c
   Geo g; g.B = B; g.H = H; g.S = S; g.NK = NK; g.groups = cols / 128; g.scale = scale; g.lse = const_cast<float*>(lse);
   const int total = B * g.groups, grid = min(total, num_sms());
   if (d == 32) {
-    static bool set = false;
-    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<32>()) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    static const cudaError_t attr_e = cudaFuncSetAttribute(attn_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<32>());   // one-time, thread-safe
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr");
     launch_pdl(attn_bwd_tc_kernel<32>, dim3(grid), dim3(NTHREADS), bwd_smem<32>(), st, mq, mk, mv, mdo, mdq, mdk, mdv, g);
   } else {
-    static bool set = false;
-    if (!set) { VG_REQUIRE(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<64>()) == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr"); set = true; }
+    static const cudaError_t attr_e = cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<64>());   // one-time, thread-safe
+    VG_REQUIRE(attr_e == cudaSuccess, VG_ERR_LAUNCH, "attention_tc: smem attr");
     launch_pdl(attn_bwd_tc_kernel<64>, dim3(grid), dim3(NTHREADS), bwd_smem<64>(), st, mq, mk, mv, mdo, mdq, mdk, mdv, g);
   }
   return check_launch("attention_bwd_tc");

@@ -899,8 +899,7 @@ static unsigned long long* g_trace = nullptr;
 void gemm_tc_set_trace(unsigned long long* p) { g_trace = p; }
 
 bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
-  static int sm100 = -1;
-  if (sm100 < 0) sm100 = vg_device_is_sm100();
+  static const int sm100 = vg_device_is_sm100();   // one-time, thread-safe
   if (!sm100) { *why = "device is not sm_100"; return false; }
   if (a.ab_dtype != VG_BF16) { *why = "A/B must be bf16"; return false; }
   if (a.M < 1 || a.N < 8 || a.K < 1) { *why = "degenerate shape (N < 8)"; return false; }

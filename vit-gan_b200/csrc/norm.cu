@@ -815,9 +815,8 @@ int env_int(const char* name, int dflt) {
   return v >= 1 ? v : dflt;
 }
 bool x8_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("VG_LN_X8"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
+  static const bool on = [] { const char* e = getenv("VG_LN_X8"); return !(e && e[0] == '0'); }();   // read once, thread-safe
+  return on;
 }
 int grid_for_rows(int64_t rows, int ctas_per_sm) {
   const int64_t need = (rows + WARPS - 1) / WARPS;
@@ -873,10 +872,9 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
              "layernorm_bwd: dgamma/dbeta must be given together (both NULL = dx only, no column sums)");
   VG_REQUIRE(!(workspace && (!counter || ws_rows < 1)), VG_ERR_ARG, "layernorm_bwd: workspace needs a counter and ws_rows >= 1");
   if (rows == 0) return VG_OK;
-  static int per_sm = 0;
-  if (per_sm == 0) { const char* e = getenv("VG_LN_BWD_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 2; }
-  static int bwd_x8 = -1;       // opt-in (VG_LN_BWD_X8=1): fewer instructions per row but 193 registers; measured slower (19 vs 17 us at C2)
-  if (bwd_x8 < 0) { const char* e = getenv("VG_LN_BWD_X8"); bwd_x8 = (e && e[0] == '1') ? 1 : 0; }
+  static const int per_sm = [] { const char* e = getenv("VG_LN_BWD_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 2 : v; }();
+  // opt-in (VG_LN_BWD_X8=1): fewer instructions per row but 193 registers; measured slower (19 vs 17 us at C2)
+  static const int bwd_x8 = [] { const char* e = getenv("VG_LN_BWD_X8"); return (e && e[0] == '1') ? 1 : 0; }();
   if (E <= 128 && E % 8 == 0 && bwd_x8 == 1) {      // 8 lanes per row, 8 (bf16) / 4 (fp32) rows per warp in flight
     const int rpi = dtype == VG_F32 ? 4 : 8;
     const int g8 = grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_BWD_X8_CTAS_PER_SM", 2));
@@ -961,8 +959,7 @@ extern "C" int vg_layernorm_bwd_partials(int dtype, int64_t rows, int E, const v
   VG_REQUIRE(partials != nullptr && max_parts >= 1, VG_ERR_ARG, "layernorm_bwd_partials: no partial buffer");
   VG_REQUIRE(rows > 0, VG_ERR_SHAPE, "layernorm_bwd_partials: empty input");
   const int rpi = dtype == VG_F32 ? 4 : 8;
-  static int px8 = -1;
-  if (px8 < 0) { const char* e = getenv("VG_LN_BWD_X8"); px8 = (e && e[0] == '1') ? 1 : 0; }
+  static const int px8 = [] { const char* e = getenv("VG_LN_BWD_X8"); return (e && e[0] == '1') ? 1 : 0; }();
   if (px8 == 1 && E % 8 == 0) {          // experiment: 8-lanes-per-row variant (half the instructions, 193 registers -> 1 CTA/SM)
     const int g8 = min(grid_for_rows((rows + rpi - 1) / rpi, env_int("VG_LN_BWD_X8_CTAS_PER_SM", 1)), max_parts);
     if (dtype == VG_F32)
