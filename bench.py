@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing section (used for ncu launch lists)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW instead of the fused flat Adam kernel")
     ap.add_argument("--no-pg-stream", action="store_true", help="keep the weight-gradient GEMMs on the main stream")
+    ap.add_argument("--no-keep-g", action="store_true", help="micro-batched step: recompute every generator forward in the generator update")
     ap.add_argument("--separate-d-passes", action="store_true",
                     help="run D(real) and D(fake) of the discriminator update as two passes (reference call order) instead of one concatenated pass")
     ap.add_argument("--keep-unused-d-grads", action="store_true",
@@ -437,7 +438,7 @@ def measure(args, name, steps, warmup, full, rank, world, local):
     devb = [(r.cuda(), n.cuda()) for r, n in host]
     unit = "img/s"
     gs = d_b = g_b = None
-    n_micro = 1
+    n_micro, keep_g, keep_info = 1, 0, {}
 
     if spec["kind"] == "v2_sample":
         unit = "samples/s"
@@ -466,13 +467,38 @@ def measure(args, name, steps, warmup, full, rank, world, local):
         # micro-batch: ~50 GB of the 180 GB); every other workload is one batch
         n_micro = (args.micro if name == args.workload else None) or (max(1, B // 256) if spec["name"] == "c4" else 1)
 
+        vb.functional.set_param_grad_stream(not args.no_pg_stream)     # eager steps use the same two-stream schedule the graph captures
+        # generator graphs kept across the discriminator update (saves the second generator forward of those micro-batches):
+        # as many as the measured free HBM holds, the same number on every rank
+        keep_g, keep_info = 0, {}
+        if n_micro > 1 and not args.no_keep_g:
+            mbs = B // n_micro
+            keep_g = vb.train.plan_keep_g_graphs(gen, disc, devb[0][0][:mbs], devb[0][1][:mbs], n_micro, info=keep_info)
+            if world > 1:
+                kt = torch.tensor([keep_g], device="cuda")
+                dist.all_reduce(kt, op=dist.ReduceOp.MIN)
+                keep_g = int(kt.item())
+
         def eager(real, noise):
             return vb.train.gan_step_microbatched(gen, disc, gopt, dopt, real, noise, loss_kind, n_micro=n_micro, d_buckets=d_b,
-                                                  g_buckets=g_b, skip_unused_d_grads=skip_unused, merge_d_passes=merge_d)
-        vb.functional.set_param_grad_stream(not args.no_pg_stream)     # eager steps use the same two-stream schedule the graph captures
+                                                  g_buckets=g_b, skip_unused_d_grads=skip_unused, merge_d_passes=merge_d, keep_g_graphs=keep_g)
         # launches per step, counted on one eager step (the graph replays exactly these)
-        eager(*devb[0])
-        torch.cuda.synchronize()
+        try:
+            eager(*devb[0])
+            torch.cuda.synchronize()
+        except torch.cuda.OutOfMemoryError:      # the plan was too optimistic for this box: recompute every generator forward instead
+            if keep_g == 0:
+                raise
+            if rank == 0:
+                print(f"[bench] out of memory with {keep_g} kept generator graphs; falling back to 0", file=sys.stderr)
+            keep_g = 0
+            for opt_ in (gopt, dopt):
+                opt_.zero_grad(set_to_none=False) if isinstance(opt_, vb.train.FusedAdam) else opt_.zero_grad(set_to_none=True)
+            vb.functional.join_param_grad_stream()
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            eager(*devb[0])
+            torch.cuda.synchronize()
         vb.ops.launch_count = 0
         eager(*devb[1])
         torch.cuda.synchronize()
@@ -483,7 +509,7 @@ def measure(args, name, steps, warmup, full, rank, world, local):
             try:
                 gs = vb.train.GraphedStep(gen, disc, gopt, dopt, devb[0][0], devb[0][1], loss_kind, warmup=2, d_buckets=d_b,
                                           g_buckets=g_b, skip_unused_d_grads=skip_unused, n_micro=n_micro, merge_d_passes=merge_d,
-                                          param_grad_stream=not args.no_pg_stream)
+                                          param_grad_stream=not args.no_pg_stream, **({"keep_g_graphs": keep_g} if n_micro > 1 else {}))
                 step_fn, graph_used = gs, True
             except Exception as ex:      # fall back to eager launches of the same kernels (never to another implementation)
                 if rank == 0:
@@ -617,7 +643,7 @@ def measure(args, name, steps, warmup, full, rank, world, local):
             "dtype": prec, "data": "synthetic",
             "config": {"workload": f"{spec['name']}: {spec['desc']}", "per_gpu_batch": B, "global_batch": spec["global_batch"],
                        "parallelism": f"dp{world}", "cuda_graph": graph_used, "micro_batches": (n_micro if spec["kind"] != "v2_sample" else 1),
-                       "micro_batch_images": B // max(1, n_micro), "optimizer": "torch" if args.torch_optim else "fused flat Adam(W) kernel",
+                       "micro_batch_images": B // max(1, n_micro), "kept_generator_graphs": keep_g, "kept_generator_graphs_plan": keep_info, "optimizer": "torch" if args.torch_optim else "fused flat Adam(W) kernel",
                        "d_param_grads_in_g_pass": not skip_unused,
                        "d_update_passes": "D(real) and D(fake) as one concatenated pass (same gradient sum)" if (merge_d and spec["kind"] != "v2_sample" and n_micro == 1) else "separate",
                        "dropout": "p = 0 (parity protocol, SURVEY Q11)",
@@ -627,6 +653,7 @@ def measure(args, name, steps, warmup, full, rank, world, local):
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "wall_s_timed_region": t_wall, "losses_last_step": losses, "losses_finite": finite,
+            "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
             "step_flops_per_image": fl, "step_tflops_per_gpu": step_tf, "step_frac_of_bf16_sustained": step_tf / pk["tf_sust"],
             "step_frac_of_bf16_burst": step_tf / pk["tf_burst"],
             "peaks": pk, "roofline": roof, "kernels": all_k, "cpu_baseline": cpu, "dropin": dropin,

@@ -421,21 +421,30 @@ def test_v1_200_step_loss_curve(vb, golden):
 
 
 def test_microbatched_step_equals_full_batch(vb, golden):
-    """Exact mean-gradient accumulation: 3 micro-batches of 1 == one batch of 3 (fp32 path, up to summation order)."""
+    """Exact mean-gradient accumulation: 3 micro-batches of 1 == one batch of 3 (fp32 path, up to summation order), also when the
+    generator graphs of the first 2 / of all 3 micro-batches are kept across the discriminator update instead of being recomputed
+    (keep_g_graphs), against the reference-generated 3-step loss curve (src/v2/training.py:177-211)."""
     vb.set_precision("fp32")
     fx = golden("v2_tiny")
     cfg = vb.v2.Config(**fx["config"])
     ocfg = o2.V2Config(**fx["config"])
     losses = {}
-    for n_micro in (1, 3):
+    for n_micro, keep in ((1, 0), (3, 0), (3, 2), (3, 3)):
         gan = vb.v2.ViTGAN(cfg)
         gan.load_state_dict(fx["params"])
         gan = gan.cuda()
         go = torch.optim.AdamW(gan.generator.parameters(), lr=5e-4, weight_decay=1e-3)
         do = torch.optim.AdamW(gan.discriminator.parameters(), lr=5e-4, weight_decay=1e-3)
-        losses[n_micro] = torch.stack([torch.stack([t.reshape(()) for t in vb.train.gan_step_microbatched(
-            gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", n_micro=n_micro)]) for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
-    assert rel(losses[3], losses[1]) < 1e-4 and rel(losses[1], fx["losses"]) < 1e-4
+        losses[n_micro, keep] = torch.stack([torch.stack([t.reshape(()) for t in vb.train.gan_step_microbatched(
+            gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", n_micro=n_micro, keep_g_graphs=keep)])
+            for r, n in harness.synthetic_batches_v2(ocfg, 3, 3)])
+    assert rel(losses[1, 0], fx["losses"]) < 1e-4
+    for key in ((3, 0), (3, 2), (3, 3)):
+        assert rel(losses[key], losses[1, 0]) < 1e-4, key
+    # the planner returns a count in range and leaves no gradient behind
+    (r, n), = harness.synthetic_batches_v2(ocfg, 3, 1)
+    k = vb.train.plan_keep_g_graphs(gan.generator, gan.discriminator, r.cuda()[:1], n.cuda()[:1], 3)
+    assert 0 <= k <= 3 and all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in gan.discriminator.parameters())
     vb.set_precision("bf16")
 
 

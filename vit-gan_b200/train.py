@@ -282,15 +282,52 @@ def gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", d_bucket
     return loss_real.detach(), loss_fake.detach(), loss_g.detach()
 
 
+def plan_keep_g_graphs(gen, disc, real_mb, noise_mb, n_micro, reserve_bytes=12 << 30, info=None):
+    """How many micro-batches' generator graphs `gan_step_microbatched(keep_g_graphs=...)` can keep alive across the discriminator
+    update: measured, not guessed -- one eager generator forward (with grad) gives the bytes one kept graph pins, one
+    discriminator forward+backward on its output the transient peak beside it; the rest of the device's free memory
+    (minus `reserve_bytes` for the optimizer kernels, NCCL and allocator slack) is divided by the former.  `info`, if given, receives
+    the measured sizes."""
+    if n_micro <= 1:
+        return 0
+    dev = real_mb.device
+    torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
+    base = torch.cuda.memory_allocated(dev)
+    fake = gen(noise_mb)
+    torch.cuda.synchronize(dev)
+    g_bytes = torch.cuda.memory_allocated(dev) - base
+    torch.cuda.reset_peak_memory_stats(dev)
+    disc(fake.detach()).float().sum().backward()
+    Fn.join_param_grad_stream()
+    torch.cuda.synchronize(dev)
+    d_peak = torch.cuda.max_memory_allocated(dev) - base - g_bytes
+    del fake
+    for p in disc.parameters():      # the probe's gradients are not part of any step
+        if p.grad is not None:
+            p.grad.zero_()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info(dev)
+    room = free - int(1.25 * d_peak) - g_bytes - reserve_bytes      # one graph is alive in the generator update anyway
+    k = int(max(0, min(n_micro, room // max(g_bytes, 1))))
+    if info is not None:
+        info.update(graph_gb=round(g_bytes / 2 ** 30, 2), d_pass_peak_gb=round(d_peak / 2 ** 30, 2), free_gb=round(free / 2 ** 30, 2),
+                    reserve_gb=round(reserve_bytes / 2 ** 30, 2), kept=k)
+    return k
+
+
 def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="ce", n_micro=1, d_buckets=None, g_buckets=None,
-                          skip_unused_d_grads=False, merge_d_passes=False):
+                          skip_unused_d_grads=False, merge_d_passes=False, keep_g_graphs=0):
     """The same G+D iteration with the batch processed in `n_micro` equal chunks and exact mean-gradient accumulation
     (each chunk's loss is scaled by 1/n_micro; no BatchNorm on the path, so the result equals the full-batch step up to
     summation order).  Needed when the activations of the full batch do not fit (C4: global batch 2048 on one GPU).
 
     Phase D: per chunk  D(real) bwd, G(noise) without grad -> fake, D(fake) bwd;  then one D optimizer step.
     Phase G: per chunk  G(noise) with grad (G is unchanged, so this is the same fake), D(fake) bwd;  then one G step.
-    Cost vs. the un-chunked step: one extra generator forward."""
+    Cost vs. the un-chunked step: one extra generator forward per chunk -- except for the first `keep_g_graphs` chunks, whose
+    generator forward in phase D runs WITH grad and is kept (output + saved activations) until phase G reuses it: G does not
+    change between the two phases, so the values are the ones the second forward would recompute; 180 GB of HBM hold the graphs
+    of several 256-image chunks of the scaled config (`plan_keep_g_graphs` measures how many)."""
     if n_micro == 1:
         return gan_step(gen, disc, gen_opt, disc_opt, real, noise, loss_kind, d_buckets, g_buckets, skip_unused_d_grads, merge_d_passes)
     b, dev = real.shape[0], real.device
@@ -305,13 +342,19 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
     _push("vg.d_update")
     zg(disc_opt)
     l_real = l_fake = l_g = 0.0
+    kept = []
     for i in range(n_micro):
         r, z = real[i * mb:(i + 1) * mb], noise[i * mb:(i + 1) * mb]
         loss = crit(disc(r).float(), ones) * inv
         loss.backward()
         l_real = l_real + loss.detach()
-        with torch.no_grad():
-            fake = gen(z)
+        if i < keep_g_graphs:
+            fake_g = gen(z)              # with grad: the graph is reused by the generator update below
+            kept.append(fake_g)
+            fake = fake_g.detach()
+        else:
+            with torch.no_grad():
+                fake = gen(z)
         if d_buckets is not None and i == n_micro - 1:
             d_buckets.arm()
         loss = crit(disc(fake).float(), zeros) * inv
@@ -332,12 +375,16 @@ def gan_step_microbatched(gen, disc, gen_opt, disc_opt, real, noise, loss_kind="
         z = noise[i * mb:(i + 1) * mb]
         if g_buckets is not None and i == n_micro - 1:
             g_buckets.arm()
-        fake = gen(z)
+        if i < len(kept):
+            fake, kept[i] = kept[i], None     # the kept graph; freed by its backward
+        else:
+            fake = gen(z)
         with Fn.skip_param_grads(skip_unused_d_grads):
             out = disc(fake)
         loss = crit(out.float(), ones) * inv
         loss.backward()
         l_g = l_g + loss.detach()
+        fake = out = loss = None              # nothing of this chunk's graph outlives its backward
         if i + 1 < n_micro:
             Fn.join_param_grad_stream()
     if g_buckets is not None:
