@@ -703,3 +703,26 @@ def test_v2_c4_geometry_encoder_block_grads(vb):
     y.backward(dy.cuda().to(y.dtype))
     assert rel(xg.grad, dx_ref) < GTOL["bf16"]
     cmp_grads({k: p.grad for k, p in blk.named_parameters()}, g_ref, GTOL["bf16"], "Encoder@C4")
+
+
+def test_graphed_step_refuses_reallocated_buffers(vb):
+    """train.GraphedStep bakes raw device addresses into its CUDA graph: replaying after a parameter / gradient / optimizer
+    buffer was re-allocated must raise, not write through stale pointers; an untouched model replays to the eager losses."""
+    vb.set_precision("bf16")
+    cfg = vb.v2.Config(embeddings_dimension=64, attention_heads_count=2, transformer_blocks_count=1, image_size=16, patch_size=4,
+                       batch_size=3 * 16 * 16)
+    ocfg = o2.V2Config(embeddings_dimension=64, attention_heads_count=2, transformer_blocks_count=1, image_size=16, patch_size=4,
+                       batch_size=3 * 16 * 16)
+    torch.manual_seed(0)
+    gan = vb.v2.ViTGAN(cfg).cuda()
+    gnet, dnet = vb.train.FlatNet(gan.generator), vb.train.FlatNet(gan.discriminator)
+    go = vb.train.FusedAdam(gnet, 5e-4, weight_decay=1e-3, decoupled=True)
+    do = vb.train.FusedAdam(dnet, 5e-4, weight_decay=1e-3, decoupled=True)
+    (r, n), = harness.synthetic_batches_v2(ocfg, 4, 1)
+    gs = vb.train.GraphedStep(gan.generator, gan.discriminator, go, do, r.cuda(), n.cuda(), "ce", warmup=1)
+    losses = torch.stack([t.reshape(()) for t in gs(r.cuda(), n.cuda())]).cpu()
+    assert torch.isfinite(losses).all()
+    p0 = next(gan.discriminator.parameters())
+    p0.grad = torch.zeros_like(p0)                     # what zero_grad(set_to_none=True) + a backward would do: new storage
+    with pytest.raises(RuntimeError, match="re-allocated after capture"):
+        gs(r.cuda(), n.cuda())

@@ -403,7 +403,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   if (MODE == 1 && !do_ln && !REMAP && (pre2 || late) && !(p.dbg & 1)) {
     bias_pre_chunk(p, r0, lane, 0, bufX, bias_s, pre2);
     bias_pre_chunk(p, r1, lane, 1, bufX, bias_s, pre2);
-    const bool live = m0 < p.M && n0 < p.N;
+    const bool live = m0 < p.M && n0 < p.N && !(p.dbg & 4);
     if (pre2) {                                // the pre-activation tile leaves as its own bulk group
       fence_async_smem();
       __syncwarp();
@@ -447,7 +447,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
         tma_load_2d(bufX, has_aux ? tmap_aux : tmap_res, wbar, next_n0, next_m0);
       }
     }
-    if (lane == 0 && m0 < p.M && n0 < p.N) {
+    if (lane == 0 && m0 < p.M && n0 < p.N && !(p.dbg & 4)) {
       if (p.accumulate) {
         tma_reduce_add_2d(tmap_c, bufC, n0, m0);
         if (n0 + 32 < p.N) tma_reduce_add_2d(tmap_c, bufX, n0 + 32, m0);
@@ -922,7 +922,8 @@ bool gemm_tc_supported(const vg_gemm_args& a, const char** why) {
 }
 
 // Bring-up knobs, read ONCE per process (thread-safe static initialisation; the launch path itself never calls getenv):
-//   VG_TC_DBG   bit 0 = epilogue skips global memory, bit 1 = force the direct (per-thread) epilogue, bit 4 = print the pair-cluster capacity
+//   VG_TC_DBG   bit 0 = epilogue skips math and global memory, bit 1 = force the direct (per-thread) epilogue, bit 2 = epilogue math
+//               and staging but no TMA stores (timing experiments), bit 4 = print the pair-cluster capacity
 //   VG_TC_BN    128 | 256 overrides the tile-width heuristic
 //   VG_TC_PAIR  0 keeps the wide tiles on the 1-CTA kernel (A/B comparison with the CTA-pair kernel)
 //   VG_TC_MN_DESC "lbo,sbo,kstep" (bytes) overrides the MN-major descriptor strides

@@ -428,8 +428,27 @@ class GraphedStep:
         finally:
             Fn.set_param_grad_stream(prev_pg)             # the fork is baked into the graph; eager callers keep their setting
             Fn.set_operand_cache(prev_cache)              # eager callers get their cached operand copies back
+        # The graph holds raw device addresses (kernel arguments, tensor maps) of every parameter, gradient and optimizer buffer:
+        # remember them, so that a replay after one of them was re-allocated (load onto another device, .to(dtype), a new
+        # .grad tensor from zero_grad(set_to_none=True), ...) is an error instead of a silent write into freed memory.
+        self._captured = self._addresses()
+
+    def _addresses(self):
+        gen, disc, gen_opt, disc_opt = self.args
+        addr = []
+        for net in (gen, disc):
+            for p in net.parameters():
+                addr.append(p.data_ptr())
+                addr.append(p.grad.data_ptr() if p.grad is not None else 0)
+        for opt in (gen_opt, disc_opt):
+            if isinstance(opt, FusedAdam):
+                addr.extend(t.data_ptr() for t in (opt.net.flat_param, opt.net.flat_grad, opt.exp_avg, opt.exp_avg_sq, opt.step_count))
+        return addr
 
     def __call__(self, real, noise):
+        if self._addresses() != self._captured:
+            raise RuntimeError("vitgan_b200.GraphedStep: a parameter, gradient or optimizer buffer was re-allocated after capture; "
+                               "the captured graph still points at the old storage -- build a new GraphedStep")
         self.real.copy_(real, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
         self.graph.replay()
