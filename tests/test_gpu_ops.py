@@ -570,6 +570,33 @@ def test_gemm_cta_pair_wide_tiles(vb, M):
     assert rel(dw, dw0 + dqkv.float().t() @ xf) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(9605, 512, 520), (19000, 256, 1000), (2304, 768, 8200)])
+def test_gemm_cta_pair_ragged_shapes(vb, M, N, K):
+    """CTA-pair kernel at shapes that exercise its edges: a ragged last pair tile (M % 256 != 0, incl. a pair whose second CTA has
+    no rows), K % 64 != 0 (the last k-block is zero-filled by TMA), a single n-tile (N = 256), and -- third case, the wgrad
+    geometry -- split-K with a ragged last split reduce-added into a pre-filled fp32 output."""
+    L = vb.lib
+    g = gen(M + N + K)
+    dev = "cuda"
+    if K < 4096:
+        x = (torch.randn(M, K, generator=g) * 0.5).bfloat16().to(dev)
+        w = (torch.randn(N, K, generator=g) * 0.05).bfloat16().to(dev)
+        b = torch.randn(N, generator=g).to(dev)
+        y = vb.ops.gemm(x, w, bias=b, path=L.GEMM_TCGEN05)
+        assert rel(y, x.float() @ w.float().t() + b) < BF16_TOL
+        dy = (torch.randn(M, N, generator=g) * 0.5).bfloat16().to(dev)
+        dx = vb.ops.gemm(dy, w, trans_b=False, path=L.GEMM_TCGEN05) if K % 256 == 0 else None     # dgrad output width K must suit the wide tile
+        if dx is not None:
+            assert rel(dx, dy.float() @ w.float()) < BF16_TOL
+    else:
+        dy = (torch.randn(K, M, generator=g) * 0.5).bfloat16().to(dev)       # [rows, out_features]
+        x = (torch.randn(K, N, generator=g) * 0.5).bfloat16().to(dev)        # [rows, in_features]
+        dw0 = torch.randn(M, N, generator=g).to(dev)
+        dw = dw0.clone()
+        vb.ops.gemm(dy, x, trans_a=True, trans_b=False, accumulate=True, out=dw, path=L.GEMM_TCGEN05)
+        assert rel(dw, dw0 + dy.float().t() @ x.float()) < 1e-4
+
+
 MT_SHAPES = [(2, 4, 257, 192, 0), (40, 4, 257, 192, 0), (1, 1, 128, 192, 0), (1, 2, 129, 192, 0), (3, 4, 64, 96, 0), (2, 4, 65, 112, 0),
              (2, 4, 65, 112, 1), (300, 4, 65, 112, 1), (2, 4, 64, 96, 1), (1, 2, 200, 112, 1), (2, 2, 272, 96, 0), (2, 2, 17, 96, 0),
              (3, 2, 1, 112, 1)]
