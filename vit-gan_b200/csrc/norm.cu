@@ -219,7 +219,11 @@ ln_bwd_kernel(int64_t rows, int E, const T* __restrict__ dy, const T* __restrict
 template <int NV>
 struct PackedRow { uint2 x[NV], dy[NV], dr[NV]; float mu, rs; };
 
-template <int NV>
+// COLS: also accumulate colsum(dres) and colsum(dx) (the bias gradients of the Linear layers on either side).  Without them the
+// 2 x 4 NV accumulator registers they need hold a third row instead: the kernel is bound by the latency of its global loads
+// (ncu: IPC 1.6, a third of the stall cycles on the L1TEX scoreboard, 8 warps per SM at 255 registers), so rows in flight are
+// what it converts into bandwidth.
+template <int NV, bool COLS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 ln_bwd_wide_kernel(int64_t rows, int E, const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -285,9 +289,8 @@ ln_bwd_wide_kernel(int64_t rows, int E, const bf16* __restrict__ dy, const bf16*
       for (int j = 0; j < 4; ++j) {
         const float xh = (xv[j] - b.mu) * b.rs;
         const float t = b.rs * (dv[j] * g[i][j] - c1 - xh * c2);
-        adr[i][j] += rv[j];
         o[j] = rv[j] + t;
-        adx[i][j] += o[j];
+        if (COLS) { adr[i][j] += rv[j]; adx[i][j] += o[j]; }
       }
       if (c < E) Vec4<bf16>::store(dx + r * E + c, o);
     }
@@ -295,23 +298,41 @@ ln_bwd_wide_kernel(int64_t rows, int E, const bf16* __restrict__ dy, const bf16*
 
   PackedRow<NV> A, B;
   int64_t r = warp;
-  if (r < rows) fetch(A, r);
-  while (r < rows) {
-    const int64_t rn = r + nwarps;
-    if (rn < rows) fetch(B, rn);
-    process(A, r);
-    const int64_t r2 = rn + nwarps;
-    if (r2 < rows) fetch(A, r2);
-    if (rn < rows) process(B, rn);
-    r = r2;
+  if (COLS) {                        // two rows in flight
+    if (r < rows) fetch(A, r);
+    while (r < rows) {
+      const int64_t rn = r + nwarps;
+      if (rn < rows) fetch(B, rn);
+      process(A, r);
+      const int64_t r2 = rn + nwarps;
+      if (r2 < rows) fetch(A, r2);
+      if (rn < rows) process(B, rn);
+      r = r2;
+    }
+  } else {                           // three rows in flight
+    PackedRow<NV> Cq;
+    if (r < rows) fetch(A, r);
+    if (r + nwarps < rows) fetch(B, r + nwarps);
+    while (r < rows) {
+      const int64_t r1 = r + nwarps, r2 = r1 + nwarps, r3 = r2 + nwarps, r4 = r3 + nwarps;
+      if (r2 < rows) fetch(Cq, r2);
+      process(A, r);
+      if (r3 < rows) fetch(A, r3);
+      if (r1 < rows) process(B, r1);
+      if (r4 < rows) fetch(B, r4);
+      if (r2 < rows) process(Cq, r2);
+      r = r3;
+    }
   }
   if (!acc) return;                  // dx only (dgrad-only pass): no column reductions at all
   for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) s_all[i] = 0.f;
   __syncthreads();
   flush_cols(s_all, nullptr, adg, E, lane);
   flush_cols(s_all + E, nullptr, adb, E, lane);
-  flush_cols(s_all + 2 * E, nullptr, adr, E, lane);
-  flush_cols(s_all + 3 * E, nullptr, adx, E, lane);
+  if (COLS) {
+    flush_cols(s_all + 2 * E, nullptr, adr, E, lane);
+    flush_cols(s_all + 3 * E, nullptr, adx, E, lane);
+  }
   __syncthreads();
   if (ws != nullptr) {               // replicated accumulators, folded by the last CTA (same layout as ln_bwd_kernel)
     float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
@@ -901,9 +922,11 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
                                                    reinterpret_cast<uintptr_t>(dres)) & 7) == 0) {
     // wide rows: packed operands, two rows per warp in flight, one CTA per SM
     const int gridw = grid_for_rows(rows, 1);
-#define VG_LN_WIDE(NV_) launch_pdl(ln_bwd_wide_kernel<NV_>, dim3(gridw), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean, \
+#define VG_LN_WIDE_(NV_, COLS_) launch_pdl(ln_bwd_wide_kernel<NV_, COLS_>, dim3(gridw), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean, \
                                    rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter)
+#define VG_LN_WIDE(NV_) do { if (dres_colsum != nullptr || dx_colsum != nullptr) VG_LN_WIDE_(NV_, true); else VG_LN_WIDE_(NV_, false); } while (0)
     if (E <= 384) VG_LN_WIDE(3); else if (E <= 512) VG_LN_WIDE(4); else VG_LN_WIDE(6);
+#undef VG_LN_WIDE_
 #undef VG_LN_WIDE
     return check_launch("layernorm_bwd");
   }
