@@ -362,6 +362,21 @@ def kernel_rooflines(vb, spec, pk):
         return lambda: vb.ops.gemm(dy, x, trans_a=True, trans_b=False, accumulate=True, out=o, path=L.GEMM_TCGEN05)
     entry("gemm_tc wgrad qkv [3E,M]x[M,E] split-K", mk_wgrad, 2 * (M * 3 * E + M * E), 2.0 * M * 3 * E * E, 2.0 * (M * 3 * E + M * E) + 4.0 * 3 * E * E, it)
 
+    if big:      # the other GEMM epilogues of the block at the compute-bound shapes (c2 fuses LayerNorm into these; see profiles/r02_*)
+        w2, b2 = mk(E, m * E), torch.randn(E, device=dev)
+
+        def mk_fc2(i):
+            gact, x, o = mk(M, m * E), mk(M, E), torch.empty(M, E, device=dev, dtype=bf)
+            return lambda: vb.ops.gemm(gact, w2, bias=b2, residual=x, out=o, path=L.GEMM_TCGEN05)
+        entry("gemm_tc fwd fc2+bias+residual [M,mE]x[mE,E]", mk_fc2, 2 * (M * m * E + 2 * M * E), 2.0 * M * m * E * E,
+              2.0 * (M * m * E + m * E * E + 2 * M * E), it)
+
+        def mk_dgelu(i):
+            dy, u, o = mk(M, E), mk(M, m * E), torch.empty(M, m * E, device=dev, dtype=bf)
+            return lambda: vb.ops.gemm(dy, w2, trans_b=False, act=L.ACT_MUL_DGELU, aux=u, out=o, path=L.GEMM_TCGEN05)
+        entry("gemm_tc dgrad fc2 x gelu'(u) [M,E]x[E,mE]", mk_dgelu, 2 * (M * E + 2 * M * m * E), 2.0 * M * m * E * E,
+              2.0 * (M * E + m * E * E + 2 * M * m * E), it)
+
     attn_entries(f"B{B} H{H} S{S} d{d}", B, H, S, d, 0, scale, it)
 
     def mk_ln(i):
@@ -374,9 +389,16 @@ def kernel_rooflines(vb, spec, pk):
         _, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)
         return lambda: vb.ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dr)
     entry("layernorm bwd (+residual grad)", mk_lnb, 2 * 4 * M * E, 12.0 * M * E, 2.0 * 4 * M * E, it)
+
+    def mk_lnb_cs(i):
+        x, dy, dr = mk(M, E), mk(M, E), mk(M, E)
+        _, mean, rstd = vb.ops.layernorm_fwd(x, gam, bet)
+        cr, cx = torch.zeros(E, device=dev), torch.zeros(E, device=dev)
+        return lambda: vb.ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dr, dres_colsum=cr, dx_colsum=cx)
+    entry("layernorm bwd (+residual grad, + the two neighbouring bias gradients)", mk_lnb_cs, 2 * 4 * M * E, 14.0 * M * E, 2.0 * 4 * M * E, it)
     torch.cuda.empty_cache()
 
-    dom = out[0]                      # the top bucket of the step's launch list: profiles/r03_launches_c4_one_step.txt (c4), r02_* (c2)
+    dom = out[0]                      # the top bucket of the step's launch list: profiles/r06_launches_c4_one_step.txt (c4), r02_* (c2)
     key = "frac_tensor" if dom["bound"] == "tensor" else "frac_hbm"
     traffic = None
     try:       # DRAM bytes per launch of the same kernel at the same shape from the committed ncu --set full capture
