@@ -224,6 +224,31 @@ def test_v2_graphed_step_matches_eager(vb, golden):
     assert rel(torch.stack(graphed), torch.stack(eager)) < 2e-2
 
 
+def test_v2_bench_schedule_matches_reference_curve(vb, golden):
+    """The schedule bench.py measures at N < 8 -- micro-batches with exact gradient accumulation, the generator graphs kept across
+    the discriminator update, D's discarded weight gradients of the generator pass skipped, flat buffers + fused AdamW, the whole
+    step replayed as one CUDA graph -- reproduces the REFERENCE-generated loss curve of the same model and batches
+    (tests/golden/v2_tiny.pt, src/v2/training.py:177-211), fp32 path at 1e-4, over three consecutive replays."""
+    vb.set_precision("fp32")
+    fx = golden("v2_tiny")
+    cfg = vb.v2.Config(**fx["config"])
+    ocfg = o2.V2Config(**fx["config"])
+    batches = harness.synthetic_batches_v2(ocfg, 3, 3)
+    gan = vb.v2.ViTGAN(cfg)
+    gan.load_state_dict(fx["params"])
+    gan = gan.cuda()
+    gnet, dnet = vb.train.FlatNet(gan.generator), vb.train.FlatNet(gan.discriminator)
+    go = vb.train.FusedAdam(gnet, 5e-4, weight_decay=1e-3, decoupled=True)
+    do = vb.train.FusedAdam(dnet, 5e-4, weight_decay=1e-3, decoupled=True)
+    r0, n0 = batches[0]
+    step = vb.train.GraphedStep(gan.generator, gan.discriminator, go, do, r0.cuda(), n0.cuda(), "ce", warmup=0,
+                                n_micro=3, keep_g_graphs=3, skip_unused_d_grads=True)
+    got = torch.stack([torch.stack([t.reshape(()) for t in step(r.cuda(), n.cuda())]).cpu().clone() for r, n in batches])
+    vb.set_operand_cache(True)
+    assert rel(got, fx["losses"]) < 1e-4, rel(got, fx["losses"])
+    vb.set_precision("bf16")
+
+
 # ------------------------------------------------------------------------------------------------ v1
 def _two_input_block(vb, prec, mod, fx, oracle_fn, out_key):
     """Blocks with (h, w) inputs: SLN and TransformerSLN."""
