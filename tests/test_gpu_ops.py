@@ -165,7 +165,7 @@ def test_gemm_tc_rejects_and_errors(vb):
 
 
 @pytest.mark.parametrize("dt,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
-@pytest.mark.parametrize("rows,E", [(33, 32), (130, 128), (65 * 4, 432), (50, 768), (5000, 768), (4099, 384), (2500, 432), (3001, 512)])
+@pytest.mark.parametrize("rows,E", [(33, 32), (130, 128), (65 * 4, 432), (50, 768), (5000, 768), (4097, 768), (4099, 384), (2500, 432), (3001, 512)])
 def test_layernorm(vb, dt, tol, rows, E):
     g = gen(rows + E)
     x = (torch.randn(rows, E, generator=g) * 2 + 0.5).to(dt)
@@ -184,6 +184,11 @@ def test_layernorm(vb, dt, tol, rows, E):
     assert rel(dg, gr.grad) < max(tol, 1e-4) and rel(db, br.grad) < max(tol, 1e-4)
     # fused column sums (bias gradients of the neighbouring Linear layers): fp32 sums of the un-rounded values
     assert rel(cr, dres.float().sum(0)) < 1e-4 and rel(cx, (xr.grad + dres.float()).sum(0)) < max(tol, 1e-3)
+    # without the two bias-gradient column sums (a different kernel instantiation at wide rows), and dx only (no parameter gradients)
+    dx3, dg3, db3 = vb.ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dres=dres.cuda())
+    assert rel(dx3, xr.grad + dres.float()) < tol and rel(dg3, gr.grad) < max(tol, 1e-4) and rel(db3, br.grad) < max(tol, 1e-4)
+    dx4, _, _ = vb.ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dx_only=True)
+    assert rel(dx4, xr.grad) < tol
     if E <= 128:      # deferred column reductions: per-CTA partials + vg_fold_partials give the same five results
         dx2, part = vb.ops.layernorm_bwd_partials(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dres=dres.cuda())
         outs = [torch.zeros(E, device="cuda") for _ in range(4)]

@@ -348,6 +348,151 @@ ln_bwd_wide_kernel(int64_t rows, int E, const bf16* __restrict__ dy, const bf16*
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LN backward, E = 768 (bf16): three warps per row
+// ln_bwd_wide_kernel above gives every warp a whole row: 4 x 24 fp32 column accumulators + two packed rows per lane = 255
+// registers, 8 warps per SM, and ~29 instructions per element because x-hat and gamma*dy cannot stay in registers between its
+// two passes.  Here a row is shared by THREE warps (96 lanes x 8 columns = 768): 4 x 8 accumulators per lane, x-hat and gamma*dy
+// kept between the passes, two rows per warp triple per iteration with the next pair's 16-byte loads already in flight -> ~150
+// registers, 12 warps per SM (3 per scheduler instead of 2) and ~40 % fewer instructions.  The row sums c1 = mean(gamma dy),
+// c2 = mean(gamma dy x-hat) meet in shared memory: one 96-thread named barrier per pair of rows (slots alternate by iteration).
+// Same outputs and the same reduction tail as ln_bwd_wide_kernel.
+struct TriRow { uint4 x, dy, dr; float mu, rs; };
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <bool COLS>
+__global__ void __launch_bounds__(384, 1)
+ln_bwd_tri_kernel(int64_t rows, const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_colsum, float* __restrict__ dx_colsum,
+                  float* __restrict__ ws, int ws_rows, unsigned* __restrict__ counter) {
+  constexpr int E = 768, T = 4;
+  __shared__ float s_all[4 * E];
+  __shared__ float xch[T][2][2][3][2];            // [triple][iteration parity][row of the pair][warp of the triple][c1 | c2]
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tri = warp / 3, part = warp % 3;
+  const int col = (part * 32 + lane) * 8;
+  const bool acc = dgamma != nullptr, has_res = dres != nullptr;
+  float g[8], adg[8], adb[8], adr[8], adx[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { adg[j] = 0.f; adb[j] = 0.f; adr[j] = 0.f; adx[j] = 0.f; }
+  const float invE = 1.0f / (float)E;
+  const int64_t npairs = (rows + 1) / 2, stride = (int64_t)gridDim.x * T;
+
+  auto fetch = [&](TriRow (&b)[2], int64_t p) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t r = 2 * p + i;
+      if (r < rows) {
+        b[i].x = __ldg(reinterpret_cast<const uint4*>(x + r * E + col));
+        b[i].dy = __ldg(reinterpret_cast<const uint4*>(dy + r * E + col));
+        b[i].dr = has_res ? __ldg(reinterpret_cast<const uint4*>(dres + r * E + col)) : make_uint4(0u, 0u, 0u, 0u);
+        b[i].mu = __ldg(mean + r); b[i].rs = __ldg(rstd + r);
+      } else {                                     // odd row count: the missing row contributes nothing and is not stored
+        b[i].x = b[i].dy = b[i].dr = make_uint4(0u, 0u, 0u, 0u);
+        b[i].mu = 0.f; b[i].rs = 0.f;
+      }
+    }
+  };
+  auto unpack = [](const uint4& u, float (&v)[8]) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+    v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+    v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+  };
+  auto process = [&](const TriRow (&b)[2], int64_t p, int par) {
+    float xh[2][8], gd[2][8], c1[2], c2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float xv[8], dv[8];
+      unpack(b[i].x, xv); unpack(b[i].dy, dv);
+      const float nmr = -b[i].mu * b[i].rs;
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = fmaf(xv[j], b[i].rs, nmr);
+        gd[i][j] = dv[j] * g[j];
+        a1 += gd[i][j];
+        a2 = fmaf(gd[i][j], xh[i][j], a2);
+        adg[j] = fmaf(dv[j], xh[i][j], adg[j]);
+        adb[j] += dv[j];
+      }
+      c1[i] = a1; c2[i] = a2;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { c1[i] = warp_sum(c1[i]); c2[i] = warp_sum(c2[i]); }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { xch[tri][par][i][part][0] = c1[i]; xch[tri][par][i][part][1] = c2[i]; }
+    }
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + tri) : "memory");
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      c1[i] = ((xch[tri][par][i][0][0] + xch[tri][par][i][1][0]) + xch[tri][par][i][2][0]) * invE;
+      c2[i] = ((xch[tri][par][i][0][1] + xch[tri][par][i][1][1]) + xch[tri][par][i][2][1]) * invE;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t r = 2 * p + i;
+      float rv[8], o[8];
+      unpack(b[i].dr, rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = fmaf(-xh[i][j], c2[i], gd[i][j] - c1[i]);
+        o[j] = fmaf(b[i].rs, u, rv[j]);
+        if (COLS) { adr[j] += rv[j]; adx[j] += o[j]; }
+      }
+      if (r < rows) {
+        uint4 ov;
+        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dx + r * E + col) = ov;
+      }
+    }
+  };
+
+  TriRow A[2], B[2];
+  int64_t p = (int64_t)tri * gridDim.x + blockIdx.x;          // neighbouring CTAs work on neighbouring row pairs
+  if (p < npairs) fetch(A, p);
+  while (p < npairs) {                                         // unrolled by two: static buffers, no register copies
+    const int64_t pn = p + stride;
+    if (pn < npairs) fetch(B, pn);
+    process(A, p, 0);
+    const int64_t p2 = pn + stride;
+    if (p2 < npairs) fetch(A, p2);
+    if (pn < npairs) process(B, pn, 1);
+    p = p2;
+  }
+  if (!acc) return;                  // dx only (dgrad-only pass): no column reductions at all
+  for (int i = threadIdx.x; i < 4 * E; i += blockDim.x) s_all[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_all[col + j], adg[j]);
+    atomicAdd(&s_all[E + col + j], adb[j]);
+    if (COLS) { atomicAdd(&s_all[2 * E + col + j], adr[j]); atomicAdd(&s_all[3 * E + col + j], adx[j]); }
+  }
+  __syncthreads();
+  if (ws != nullptr) {               // replicated accumulators, folded by the last CTA (same layout as ln_bwd_kernel)
+    float* outs[4] = {dgamma, dbeta, dres_colsum, dx_colsum};
+    const int offs[4] = {0, E, 2 * E, 3 * E};
+    cta_replica_reduce(ws, ws_rows, counter, s_all, 4 * E, outs, offs, 4);
+    return;
+  }
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_all[i]);
+    atomicAdd(&dbeta[i], s_all[E + i]);
+    if (dres_colsum != nullptr) atomicAdd(&dres_colsum[i], s_all[2 * E + i]);
+    if (dx_colsum != nullptr) atomicAdd(&dx_colsum[i], s_all[3 * E + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LN backward, E <= 128
 // Same math as ln_bwd_kernel<T, 1>, restructured for memory-level parallelism: a warp keeps RPI = 8 (bf16) / 4 (fp32) rows
 // of all three inputs in flight as PACKED registers (one 8/16-byte load per lane per tensor per row) before any conversion
@@ -916,6 +1061,19 @@ extern "C" int vg_layernorm_bwd(int dtype, int64_t rows, int E, const void* dy, 
     else
       launch_pdl(ln_bwd_e128_kernel<bf16>, dim3(grid), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)dy, (const bf16*)x, mean,
                  rstd, gamma, (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter, (float*)nullptr);
+    return check_launch("layernorm_bwd");
+  }
+  static const bool tri_off = [] { const char* e = getenv("VG_LN_TRI"); return e && e[0] == '0'; }();
+  if (dtype == VG_BF16 && E == 768 && !tri_off && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                                                      reinterpret_cast<uintptr_t>(dres)) & 15) == 0) {
+    // three warps per row, 12 warps per SM (see ln_bwd_tri_kernel); VG_LN_TRI=0 keeps the one-warp-per-row kernel below
+    const int gridt = (int)max((int64_t)1, min((rows + 7) / 8, (int64_t)num_sms()));
+    if (dres_colsum != nullptr || dx_colsum != nullptr)
+      launch_pdl(ln_bwd_tri_kernel<true>, dim3(gridt), dim3(384), 0, as_stream(stream), rows, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+                 (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
+    else
+      launch_pdl(ln_bwd_tri_kernel<false>, dim3(gridt), dim3(384), 0, as_stream(stream), rows, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+                 (const bf16*)dres, (bf16*)dx, dgamma, dbeta, dres_colsum, dx_colsum, workspace, ws_rows, counter);
     return check_launch("layernorm_bwd");
   }
   if (dtype == VG_BF16 && E > 256 && E <= 768 && E % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
