@@ -493,6 +493,93 @@ ln_bwd_tri_kernel(int64_t rows, const bf16* __restrict__ dy, const bf16* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LN forward, E = 768 (bf16): three warps per row
+// ln_fwd_kernel gives every warp a whole 768-wide row (24 values + 48 gamma / beta registers per lane, ONE row in flight per warp,
+// 16 warps per SM): 24 KB of loads in flight per SM, 64 % of the HBM roofline.  With a row shared by three warps (8 columns per
+// lane, one 16-byte load) a lane needs ~80 registers, 24 warps fit, and every warp triple keeps four rows in flight plus the next
+// four requested: the two-pass statistics (mean, then sum of squared deviations: the same arithmetic as row_stats) meet in shared
+// memory on a 96-thread named barrier, twice per four rows.
+__global__ void __launch_bounds__(384, 2)
+ln_fwd_tri_kernel(int64_t rows, const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, float eps) {
+  constexpr int E = 768, T = 4, RB = 4;
+  __shared__ float xch[T][2][RB][3];              // [triple][sum | sum of squared deviations][row of the batch][warp of the triple]
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tri = warp / 3, part = warp % 3;
+  const int col = (part * 32 + lane) * 8;
+  float g[8], b[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  const float invE = 1.0f / (float)E;
+  const int64_t nbatch = (rows + RB - 1) / RB, stride = (int64_t)gridDim.x * T;
+  auto fetch = [&](uint4 (&raw)[RB], int64_t q) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t r = q * RB + i;
+      raw[i] = r < rows ? __ldg(reinterpret_cast<const uint4*>(x + r * E + col)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint4 nxt[RB];
+  int64_t q = (int64_t)tri * gridDim.x + blockIdx.x;
+  if (q < nbatch) fetch(nxt, q);
+  for (; q < nbatch; q += stride) {
+    float v[RB][8], st[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const uint4 u = nxt[i];
+      v[i][0] = __uint_as_float(u.x << 16); v[i][1] = __uint_as_float(u.x & 0xFFFF0000u);
+      v[i][2] = __uint_as_float(u.y << 16); v[i][3] = __uint_as_float(u.y & 0xFFFF0000u);
+      v[i][4] = __uint_as_float(u.z << 16); v[i][5] = __uint_as_float(u.z & 0xFFFF0000u);
+      v[i][6] = __uint_as_float(u.w << 16); v[i][7] = __uint_as_float(u.w & 0xFFFF0000u);
+    }
+    if (q + stride < nbatch) fetch(nxt, q + stride);           // the next four rows are in flight during both passes
+#pragma unroll
+    for (int i = 0; i < RB; ++i) st[i] = ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+#pragma unroll
+    for (int i = 0; i < RB; ++i) st[i] = warp_sum(st[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i) xch[tri][0][i][part] = st[i];
+    }
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + tri) : "memory");
+    float mean[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      mean[i] = ((xch[tri][0][i][0] + xch[tri][0][i][1]) + xch[tri][0][i][2]) * invE;
+      float s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[i][j] -= mean[i]; s2 = fmaf(v[i][j], v[i][j], s2); }
+      st[i] = s2;
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) st[i] = warp_sum(st[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i) xch[tri][1][i][part] = st[i];
+    }
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + tri) : "memory");
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t r = q * RB + i;
+      const float rstd = rsqrtf(((xch[tri][1][i][0] + xch[tri][1][i][1]) + xch[tri][1][i][2]) * invE + eps);
+      if (r < rows) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, g[j], b[j]);
+        uint4 ov;
+        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(y + r * E + col) = ov;
+        if (part == 0 && lane == 0) { mean_out[r] = mean[i]; rstd_out[r] = rstd; }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LN backward, E <= 128
 // Same math as ln_bwd_kernel<T, 1>, restructured for memory-level parallelism: a warp keeps RPI = 8 (bf16) / 4 (fp32) rows
 // of all three inputs in flight as PACKED registers (one 8/16-byte load per lane per tensor per row) before any conversion
@@ -1018,6 +1105,13 @@ extern "C" int vg_layernorm_fwd(int dtype, int64_t rows, int E, const void* x, c
       launch_pdl(ln_fwd_x8_kernel<float>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const float*)x, gamma, beta, (float*)y, mean, rstd, eps);
     else
       launch_pdl(ln_fwd_x8_kernel<bf16>, dim3(g8), dim3(WARPS * 32), 0, as_stream(stream), rows, E, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, eps);
+    return check_launch("layernorm_fwd");
+  }
+  static const bool tri_off = [] { const char* e = getenv("VG_LN_TRI"); return e && e[0] == '0'; }();
+  if (dtype == VG_BF16 && E == 768 && !tri_off && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    // three warps per row, 24 warps per SM (see ln_fwd_tri_kernel); VG_LN_TRI=0 keeps the one-warp-per-row kernel below
+    const int gridt = (int)max((int64_t)1, min((rows + 15) / 16, (int64_t)2 * num_sms()));
+    launch_pdl(ln_fwd_tri_kernel, dim3(gridt), dim3(384), 0, as_stream(stream), rows, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, eps);
     return check_launch("layernorm_fwd");
   }
   const int grid = grid_for_rows(rows, 8);
