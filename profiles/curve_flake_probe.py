@@ -37,6 +37,32 @@ def stats(cand, first, factor, noise_ratio, floor):
     return out
 
 
+def run_v1(prec, n):
+    from oracle import v1 as o1
+    vb.set_precision(prec)
+    torch.manual_seed(fx["seed"])
+    G, D = vb.v1.Generator(vb.v1.V1Config(image_size=32)).cuda(), vb.v1.Discriminator(vb.v1.V1Config(image_size=32)).cuda()
+    go = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    do = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    b1 = harness.synthetic_batches_v1(o1.V1Config(image_size=32), fx["v1_batch"], fx["steps"])
+    return torch.stack([torch.stack(vb.train.gan_step(G, D, go, do, r.cuda(), z.cuda(), "bce")).cpu() for r, z in b1[:n]]).double()
+
+
+def stats_v1(cand, first, factor, noise_ratio, floor):
+    global fx
+    keep = fx["v2_f32"], fx["v2_f64"]
+    fx["v2_f32"], fx["v2_f64"] = fx["v1_f32"], fx["v1_f64"]
+    try:
+        return stats(cand, first, factor, noise_ratio, floor)
+    finally:
+        fx["v2_f32"], fx["v2_f64"] = keep
+
+
+which = sys.argv[2] if len(sys.argv) > 2 else "v2"
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
-    print("fp32", stats(run("fp32", steps), 30, 30, 1.0, 1e-5), flush=True)
-    print("bf16", stats(run("bf16", 60), 10, 1, 2.0 ** 15, 2e-2), flush=True)
+    if which == "v2":
+        print("fp32", stats(run("fp32", steps), 30, 30, 1.0, 1e-5), flush=True)
+        print("bf16", stats(run("bf16", 60), 10, 1, 2.0 ** 15, 2e-2), flush=True)
+    else:      # the v1 test's parameters: first 8 steps, factor 100 (fp32) / noise ratio 2^15 (bf16)
+        print("v1 fp32", stats_v1(run_v1("fp32", steps), 8, 100, 1.0, 1e-5), flush=True)
+        print("v1 bf16", stats_v1(run_v1("bf16", 40), 8, 1, 2.0 ** 15, 2e-2), flush=True)
