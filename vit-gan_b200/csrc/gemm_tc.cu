@@ -142,8 +142,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 // bufC holds the residual tile on entry (if any) and the output on exit; bufX holds aux on entry or c_pre on exit.
 template <bool F32, int ACT, bool KEEP = false>
 __device__ __forceinline__ void staged_chunk(const Params& p, uint32_t (&r)[32], int lane, int cc, int n0,
-                                             uint32_t bufC, uint32_t bufX, const float* __restrict__ bias_s, bool res_in_x = false) {
-  // res_in_x (bf16, side-tile chain): the residual tile was loaded into bufX (which is never stored from) instead of bufC
+                                             uint32_t bufC, uint32_t bufX, const float* __restrict__ bias_s) {
   // KEEP (bf16 only): the final, bf16-ROUNDED output values are written back into r[] as floats (fused LayerNorm input:
   // the statistics are then taken over exactly the values a separate LayerNorm kernel would read from memory)
   const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
@@ -199,7 +198,7 @@ __device__ __forceinline__ void staged_chunk(const Params& p, uint32_t (&r)[32],
       }
       if (has_res) {
         uint32_t x0, x1, x2, x3;
-        lds128((res_in_x ? bufX : bufC) + off, x0, x1, x2, x3);
+        lds128(bufC + off, x0, x1, x2, x3);
         v[0] += bf16_lo(x0); v[1] += bf16_hi(x0); v[2] += bf16_lo(x1); v[3] += bf16_hi(x1);
         v[4] += bf16_lo(x2); v[5] += bf16_hi(x2); v[6] += bf16_lo(x3); v[7] += bf16_hi(x3);
       }
@@ -342,7 +341,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   // fc2 + residual from 144 to 132 us; moving the store waits off the critical path changed fc1 + GELU (+pre) by < 1 % (167.6 ->
   // 166.2 us) -- at 128 KB of stores per 128 x 256 tile on top of 384 KB of operand fill that epilogue is bound by the SM's
   // memory interface, not by the wait.
-  const bool side_chain = aux_ready != nullptr && (has_aux != has_res) && !has_pre && MODE == 1 && !(LN && MODE == 1) && !REMAP;
+  const bool side_chain = aux_ready != nullptr && (has_aux != has_res) && !has_pre && MODE == 1 && !(LN && MODE == 1) && !REMAP && !(p.dbg & 1);
   const bool pre2 = MODE == 1 && !LN && !REMAP && has_pre && !has_res && !has_aux && !p.accumulate;
   const bool late = side_chain && !p.accumulate;
   if (dbl && alt) { const uint32_t t = bufC; bufC = bufX; bufX = t; }
@@ -400,7 +399,7 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
   }
   if (MODE == 2 && rs_taddr != 0u) bias_s[lane] = __uint_as_float(rs);   // bias staging is idle in accumulate mode
   if (has_res || has_aux) { mbar_wait(wbar, wphase); wphase ^= 1u; }
-  if (MODE == 1 && !do_ln && !REMAP && (pre2 || late) && !(p.dbg & 1)) {
+  if (MODE == 1 && !do_ln && !REMAP && (pre2 || late) && !(p.dbg & 1)) {      // (late implies !(dbg & 1))
     bias_pre_chunk(p, r0, lane, 0, bufX, bias_s, pre2);
     bias_pre_chunk(p, r1, lane, 1, bufX, bias_s, pre2);
     const bool live = m0 < p.M && n0 < p.N && !(p.dbg & 4);
@@ -435,18 +434,11 @@ __device__ __forceinline__ void staged_tile(const Params& p, const CUtensorMap* 
       staged_chunk<f32, ACT, do_ln>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
       ln_epilogue(p, r0, r1, lane, ew, m0 + lane, bufX, ln);
     } else {
-      staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s, aux_chain);
-      staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s, aux_chain);
+      staged_chunk<f32, ACT>(p, r0, lane, 0, n0, bufC, bufX, bias_s);      // (the side-tile chain always takes the register-first flow above)
+      staged_chunk<f32, ACT>(p, r1, lane, 1, n0 + 32, bufC, bufX, bias_s);
     }
     fence_async_smem();                       // generic-proxy smem writes -> visible to the async (TMA) proxy
     __syncwarp();
-    if (aux_chain) {                          // bufX has been consumed by every lane: fetch the next group's aux tile now
-      *aux_ready = has_next;
-      if (has_next && lane == 0) {
-        mbar_expect_tx(wbar, 4096u);
-        tma_load_2d(bufX, has_aux ? tmap_aux : tmap_res, wbar, next_n0, next_m0);
-      }
-    }
     if (lane == 0 && m0 < p.M && n0 < p.N && !(p.dbg & 4)) {
       if (p.accumulate) {
         tma_reduce_add_2d(tmap_c, bufC, n0, m0);
