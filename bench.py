@@ -481,8 +481,11 @@ def measure(args, name, steps, warmup, full, rank, world, local):
             gnet, dnet = vb.train.FlatNet(gen), vb.train.FlatNet(disc, exclude=frozen)
             gopt, dopt = opt(gnet), opt(dnet)
             if world > 1:
-                d_b = vb.train.GradBuckets(dnet, n_buckets=2, average_in_place=False)
-                g_b = vb.train.GradBuckets(gnet, n_buckets=2, average_in_place=False)
+                # one all-reduce per network when it is small (< 32 MB of fp32 gradients: latency-bound, and every bucket boundary
+                # joins the parameter-gradient stream), two buckets (the first overlapping the rest of the backward) otherwise
+                nb = lambda net: 1 if net.numel * 4 < (32 << 20) else 2
+                d_b = vb.train.GradBuckets(dnet, n_buckets=nb(dnet), average_in_place=False)
+                g_b = vb.train.GradBuckets(gnet, n_buckets=nb(gnet), average_in_place=False)
                 gopt.grad_scale = dopt.grad_scale = 1.0 / world
 
         # micro-batching: c4's 2048/N images per GPU run as exact-gradient micro-batches of 256 (saved activations of one
